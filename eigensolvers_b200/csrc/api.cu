@@ -1,0 +1,723 @@
+// api.cu — C ABI of libcudavec: context, operator, BLAS-1 / tall-skinny / SpMV entry points.
+// Host-side glue only; kernels live in kernels_vec.cuh / kernels_spmv.cuh.
+#include <stdarg.h>
+#include <vector>
+#include "internal.h"
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+void cv_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char *cv_last_error(void) { return g_err; }
+extern "C" int cv_abi_version(void) { return CV_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+extern "C" size_t cv_ctx_scratch_bytes(void) {
+  return CV_N_COUNTERS * sizeof(unsigned) + (CV_N_SCALARS + CV_N_PARTIALS) * sizeof(double);
+}
+
+extern "C" int cv_ctx_create(int device, void *scratch_dev, size_t scratch_bytes, cv_ctx **out) {
+  CV_REQUIRE(out && scratch_dev, "cv_ctx_create: null argument");
+  CV_REQUIRE(scratch_bytes >= cv_ctx_scratch_bytes(), "cv_ctx_create: scratch too small (%zu < %zu)",
+             scratch_bytes, cv_ctx_scratch_bytes());
+  CV_REQUIRE(((uintptr_t)scratch_dev & 255) == 0, "cv_ctx_create: scratch must be 256-byte aligned");
+  CV_CUDA(cudaSetDevice(device));
+  cv_ctx *c = new cv_ctx();
+  c->device = device;
+  CV_CUDA(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device));
+  char *p = static_cast<char *>(scratch_dev);
+  c->counters = reinterpret_cast<unsigned *>(p);
+  p += CV_N_COUNTERS * sizeof(unsigned);
+  c->scalars = reinterpret_cast<double *>(p);
+  p += CV_N_SCALARS * sizeof(double);
+  c->partials = reinterpret_cast<double *>(p);
+  CV_CUDA(cudaMemset(scratch_dev, 0, CV_N_COUNTERS * sizeof(unsigned) + CV_N_SCALARS * sizeof(double)));
+  CV_CUDA(cudaMallocHost(&c->mailbox, CV_N_SCALARS * sizeof(double)));
+  c->launches = 0;
+  c->comm = nullptr;
+  c->rank = 0;
+  c->world = 1;
+  *out = c;
+  return CV_OK;
+}
+
+extern "C" int cv_ctx_destroy(cv_ctx *ctx) {
+  if (!ctx) return CV_OK;
+  if (ctx->comm) cv_comm_finalize(ctx);
+  if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
+  delete ctx;
+  return CV_OK;
+}
+
+extern "C" int cv_ctx_launch_count(cv_ctx *ctx, uint64_t *count) {
+  CV_REQUIRE(ctx && count, "cv_ctx_launch_count: null argument");
+  *count = ctx->launches;
+  return CV_OK;
+}
+
+extern "C" int cv_ctx_sm_count(cv_ctx *ctx, int *sms) {
+  CV_REQUIRE(ctx && sms, "cv_ctx_sm_count: null argument");
+  *sms = ctx->sms;
+  return CV_OK;
+}
+
+int cv_fetch_scalars(cv_ctx *ctx, int offset, int count, cudaStream_t st) {
+  CV_CUDA(cudaMemcpyAsync(ctx->mailbox + offset, ctx->scalars + offset, sizeof(double) * count,
+                          cudaMemcpyDeviceToHost, st));
+  CV_CUDA(cudaStreamSynchronize(st));
+  return CV_OK;
+}
+
+int cv_check_launch(cv_ctx *ctx, const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    cv_set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+    return CV_ERR_CUDA;
+  }
+  ctx->launches++;
+  return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// BLAS-1 (internal launchers are shared with solvers.cu through internal.h)
+// ------------------------------------------------------------------------------------------
+static inline int vecW(int cplx, std::initializer_list<const void *> ptrs) {
+  if (cplx) return 1;
+  for (const void *p : ptrs)
+    if (p && ((uintptr_t)p & 15)) return 1;
+  return 2;
+}
+
+extern "C" int cv_copy(cv_ctx *ctx, int64_t n, int cplx, const void *x, void *y, void *stream) {
+  CV_REQUIRE(ctx && x && y && n >= 0, "cv_copy: bad argument");
+  if (n == 0 || x == y) return CV_OK;
+  CV_CUDA(cudaMemcpyAsync(y, x, (size_t)n * (cplx ? 16 : 8), cudaMemcpyDeviceToDevice,
+                          (cudaStream_t)stream));
+  return CV_OK;
+}
+
+extern "C" int cv_scal(cv_ctx *ctx, int64_t n, int x_cplx, int y_cplx, double a_re, double a_im,
+                       const void *x, void *y, void *stream) {
+  CV_REQUIRE(ctx && x && y && n >= 0, "cv_scal: bad argument");
+  CV_REQUIRE(y_cplx || !x_cplx, "cv_scal: complex input needs complex output");
+  CV_REQUIRE(y_cplx || a_im == 0.0, "cv_scal: complex factor needs complex output");
+  if (n == 0) return CV_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!x_cplx && !y_cplx) {
+    int W = vecW(0, {x, y});
+    int grid = cv_grid_for(ctx, (n + W - 1) / W, CV_BLOCK);
+    if (W == 2)
+      k_scal_rr<2><<<grid, CV_BLOCK, 0, st>>>(n, a_re, (const double *)x, (double *)y);
+    else
+      k_scal_rr<1><<<grid, CV_BLOCK, 0, st>>>(n, a_re, (const double *)x, (double *)y);
+  } else {
+    int grid = cv_grid_for(ctx, n, CV_BLOCK);
+    cplx a = make_cplx(a_re, a_im);
+    if (x_cplx)
+      k_scal<cplx, cplx, cplx><<<grid, CV_BLOCK, 0, st>>>(n, a, (const cplx *)x, (cplx *)y);
+    else
+      k_scal<double, cplx, cplx><<<grid, CV_BLOCK, 0, st>>>(n, a, (const double *)x, (cplx *)y);
+  }
+  return cv_check_launch(ctx, "scal");
+}
+
+extern "C" int cv_real(cv_ctx *ctx, int64_t n, const void *x, double *y, void *stream) {
+  CV_REQUIRE(ctx && x && y && n >= 0, "cv_real: bad argument");
+  if (n == 0) return CV_OK;
+  k_real<<<cv_grid_for(ctx, n, CV_BLOCK), CV_BLOCK, 0, (cudaStream_t)stream>>>(n, (const cplx *)x, y);
+  return cv_check_launch(ctx, "real");
+}
+
+extern "C" int cv_conj(cv_ctx *ctx, int64_t n, const void *x, void *y, void *stream) {
+  CV_REQUIRE(ctx && x && y && n >= 0, "cv_conj: bad argument");
+  if (n == 0) return CV_OK;
+  k_conj<<<cv_grid_for(ctx, n, CV_BLOCK), CV_BLOCK, 0, (cudaStream_t)stream>>>(n, (const cplx *)x,
+                                                                                (cplx *)y);
+  return cv_check_launch(ctx, "conj");
+}
+
+// device-side dot into ctx->scalars[slot .. slot+NRED)
+int cv_dot_dev(cv_ctx *ctx, int64_t n, int cplx_, int conj, const void *x, const void *y, int slot,
+               cudaStream_t st) {
+  int W = vecW(cplx_, {x, y});
+  int grid = cv_grid_for(ctx, (n + W - 1) / W, CV_BLOCK);
+  double *out = ctx->scalars + slot;
+#define LAUNCH_DOT(T, WW, CJ) \
+  k_dot<T, WW, CJ><<<grid, CV_BLOCK, 0, st>>>(n, (const T *)x, (const T *)y, ctx->partials, ctx->counters, out)
+  if (cplx_) {
+    if (conj)
+      LAUNCH_DOT(cplx, 1, true);
+    else
+      LAUNCH_DOT(cplx, 1, false);
+  } else if (W == 2) {
+    LAUNCH_DOT(double, 2, false);
+  } else {
+    LAUNCH_DOT(double, 1, false);
+  }
+#undef LAUNCH_DOT
+  CV_TRY(cv_check_launch(ctx, "dot"));
+  return cv_reduce_ranks(ctx, slot, cplx_ ? 2 : 1, st);
+}
+
+int cv_nrm2sq_dev(cv_ctx *ctx, int64_t n, int cplx_, const void *x, int slot, cudaStream_t st) {
+  int W = vecW(cplx_, {x});
+  int grid = cv_grid_for(ctx, (n + W - 1) / W, CV_BLOCK);
+  double *out = ctx->scalars + slot;
+  if (cplx_)
+    k_nrm2sq<cplx, 1><<<grid, CV_BLOCK, 0, st>>>(n, (const cplx *)x, ctx->partials, ctx->counters, out);
+  else if (W == 2)
+    k_nrm2sq<double, 2><<<grid, CV_BLOCK, 0, st>>>(n, (const double *)x, ctx->partials, ctx->counters, out);
+  else
+    k_nrm2sq<double, 1><<<grid, CV_BLOCK, 0, st>>>(n, (const double *)x, ctx->partials, ctx->counters, out);
+  CV_TRY(cv_check_launch(ctx, "nrm2sq"));
+  return cv_reduce_ranks(ctx, slot, 1, st);
+}
+
+// x (and optionally x2) *= 1/sqrt(scalars[slot]); mode 1 keeps x when the factor is not finite
+int cv_scale_dev(cv_ctx *ctx, int64_t n, int cplx_, void *x, void *x2, int slot, int mode,
+                 cudaStream_t st) {
+  int W = vecW(cplx_, {x, x2});
+  int grid = cv_grid_for(ctx, (n + W - 1) / W, CV_BLOCK);
+  const double *s = ctx->scalars + slot;
+#define LAUNCH_SC(T, WW, MD) k_scale_dev<T, WW, MD><<<grid, CV_BLOCK, 0, st>>>(n, (T *)x, (T *)x2, s)
+  if (cplx_) {
+    if (mode) LAUNCH_SC(cplx, 1, 1); else LAUNCH_SC(cplx, 1, 0);
+  } else if (W == 2) {
+    if (mode) LAUNCH_SC(double, 2, 1); else LAUNCH_SC(double, 2, 0);
+  } else {
+    if (mode) LAUNCH_SC(double, 1, 1); else LAUNCH_SC(double, 1, 0);
+  }
+#undef LAUNCH_SC
+  return cv_check_launch(ctx, "scale_dev");
+}
+
+extern "C" int cv_dot(cv_ctx *ctx, int64_t n, int cplx_, int conj, const void *x, const void *y,
+                      double *out2_host, void *stream) {
+  CV_REQUIRE(ctx && x && y && out2_host && n >= 0, "cv_dot: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  out2_host[0] = out2_host[1] = 0.0;
+  if (n == 0 && ctx->world == 1) return CV_OK;
+  CV_TRY(cv_dot_dev(ctx, n, cplx_, conj, x, y, CV_S_TMP, st));
+  CV_TRY(cv_fetch_scalars(ctx, CV_S_TMP, 2, st));
+  out2_host[0] = ctx->mailbox[CV_S_TMP];
+  out2_host[1] = cplx_ ? ctx->mailbox[CV_S_TMP + 1] : 0.0;
+  return CV_OK;
+}
+
+extern "C" int cv_nrm2(cv_ctx *ctx, int64_t n, int cplx_, const void *x, double *out_host,
+                       void *stream) {
+  CV_REQUIRE(ctx && x && out_host && n >= 0, "cv_nrm2: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  *out_host = 0.0;
+  if (n == 0 && ctx->world == 1) return CV_OK;
+  CV_TRY(cv_nrm2sq_dev(ctx, n, cplx_, x, CV_S_TMP, st));
+  CV_TRY(cv_fetch_scalars(ctx, CV_S_TMP, 1, st));
+  *out_host = sqrt(ctx->mailbox[CV_S_TMP]);
+  return CV_OK;
+}
+
+extern "C" int cv_normalize(cv_ctx *ctx, int64_t n, int cplx_, void *x, double *norm_host,
+                            void *stream) {
+  CV_REQUIRE(ctx && x && n >= 0, "cv_normalize: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0 && ctx->world == 1) {
+    if (norm_host) *norm_host = 0.0;
+    return CV_OK;
+  }
+  CV_TRY(cv_nrm2sq_dev(ctx, n, cplx_, x, CV_S_TMP, st));
+  CV_TRY(cv_scale_dev(ctx, n, cplx_, x, nullptr, CV_S_TMP, 0, st));
+  if (norm_host) {
+    CV_TRY(cv_fetch_scalars(ctx, CV_S_TMP, 1, st));
+    *norm_host = sqrt(ctx->mailbox[CV_S_TMP]);
+  }
+  return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// linear combinations
+// ------------------------------------------------------------------------------------------
+template <typename TV, typename TC, typename TY, int W, bool NORM>
+static int launch_lincomb_nc(cv_ctx *ctx, const LcParams &p, int ncol, int grid, double *out_norm,
+                             cudaStream_t st) {
+#define LC(NC)                                                                                   \
+  k_lincomb<TV, TC, TY, W, NC, NORM><<<grid, CV_BLOCK, 0, st>>>(p, ctx->partials, ctx->counters, \
+                                                                out_norm)
+  switch (ncol) {
+    case 1: LC(1); break;
+    case 2: LC(2); break;
+    case 3: LC(3); break;
+    case 4: LC(4); break;
+    default:
+      cv_set_error("lincomb: internal chunk of %d columns", ncol);
+      return CV_ERR_ARG;
+  }
+#undef LC
+  return cv_check_launch(ctx, "lincomb");
+}
+
+// One launch: ncol <= 4 outputs, m*ncol*(c_cplx?2:1) <= CV_MAX_COEF.  coef row-major m x ldc.
+int cv_lincomb_launch(cv_ctx *ctx, int64_t n, int v_cplx, int c_cplx, int m, const void *const *v,
+                      int ncol, const double *coef, int ldc, int col0, void *const *y, int norm_slot,
+                      cudaStream_t st) {
+  LcParams p;
+  p.m = m;
+  p.ncol = ncol;
+  p.n = n;
+  const int cs = c_cplx ? 2 : 1;
+  for (int j = 0; j < m; ++j) {
+    p.v[j] = v[j];
+    for (int k = 0; k < ncol; ++k)
+      for (int c = 0; c < cs; ++c) p.coef[(j * ncol + k) * cs + c] = coef[((size_t)j * ldc + col0 + k) * cs + c];
+  }
+  int W = v_cplx || c_cplx ? 1 : 2;
+  for (int j = 0; j < m && W == 2; ++j)
+    if ((uintptr_t)v[j] & 15) W = 1;
+  for (int k = 0; k < ncol; ++k) {
+    p.y[k] = y[k];
+    if ((uintptr_t)y[k] & 15) W = 1;
+  }
+  int grid = cv_grid_for(ctx, (n + W - 1) / W, CV_BLOCK);
+  double *out_norm = norm_slot >= 0 ? ctx->scalars + norm_slot : nullptr;
+  int rc;
+  if (!v_cplx && !c_cplx) {
+    if (W == 2)
+      rc = norm_slot >= 0 ? launch_lincomb_nc<double, double, double, 2, true>(ctx, p, ncol, grid, out_norm, st)
+                          : launch_lincomb_nc<double, double, double, 2, false>(ctx, p, ncol, grid, out_norm, st);
+    else
+      rc = norm_slot >= 0 ? launch_lincomb_nc<double, double, double, 1, true>(ctx, p, ncol, grid, out_norm, st)
+                          : launch_lincomb_nc<double, double, double, 1, false>(ctx, p, ncol, grid, out_norm, st);
+  } else if (v_cplx && c_cplx) {
+    rc = norm_slot >= 0 ? launch_lincomb_nc<cplx, cplx, cplx, 1, true>(ctx, p, ncol, grid, out_norm, st)
+                        : launch_lincomb_nc<cplx, cplx, cplx, 1, false>(ctx, p, ncol, grid, out_norm, st);
+  } else if (v_cplx && !c_cplx) {
+    rc = norm_slot >= 0 ? launch_lincomb_nc<cplx, double, cplx, 1, true>(ctx, p, ncol, grid, out_norm, st)
+                        : launch_lincomb_nc<cplx, double, cplx, 1, false>(ctx, p, ncol, grid, out_norm, st);
+  } else {
+    rc = norm_slot >= 0 ? launch_lincomb_nc<double, cplx, cplx, 1, true>(ctx, p, ncol, grid, out_norm, st)
+                        : launch_lincomb_nc<double, cplx, cplx, 1, false>(ctx, p, ncol, grid, out_norm, st);
+  }
+  CV_TRY(rc);
+  if (norm_slot >= 0) CV_TRY(cv_reduce_ranks(ctx, norm_slot, ncol, st));
+  return CV_OK;
+}
+
+extern "C" int cv_lincomb(cv_ctx *ctx, int64_t n, int v_cplx, int c_cplx, int m,
+                          const void *const *v_ptrs, int ncol, const double *coef_host,
+                          void *const *y_ptrs, void *stream) {
+  CV_REQUIRE(ctx && v_ptrs && coef_host && y_ptrs, "cv_lincomb: null argument");
+  CV_REQUIRE(m >= 1 && m <= CV_MAX_PTRS, "cv_lincomb: m=%d outside 1..%d", m, CV_MAX_PTRS);
+  CV_REQUIRE(ncol >= 1 && n >= 0, "cv_lincomb: bad shape");
+  if (n == 0) return CV_OK;
+  const int cs = c_cplx ? 2 : 1;
+  int chunk = 4;
+  while (chunk > 1 && m * chunk * cs > CV_MAX_COEF) chunk >>= 1;
+  CV_REQUIRE(m * chunk * cs <= CV_MAX_COEF, "cv_lincomb: too many coefficients");
+  for (int c0 = 0; c0 < ncol; c0 += chunk) {
+    int nc = ncol - c0 < chunk ? ncol - c0 : chunk;
+    CV_TRY(cv_lincomb_launch(ctx, n, v_cplx, c_cplx, m, v_ptrs, nc, coef_host, ncol, c0, y_ptrs + c0,
+                             -1, (cudaStream_t)stream));
+  }
+  return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// tall-skinny product into ctx->scalars[slot ...): layout ((i*b + k)*NRED + c)
+// ------------------------------------------------------------------------------------------
+template <typename T, int W, bool CONJ>
+static int launch_tsdot(cv_ctx *ctx, const TsParams &p, int slot, cudaStream_t st) {
+  constexpr int NR = Num<T>::NRED;
+  const int64_t np = (p.n + W - 1) / W;
+  double *out = ctx->scalars + slot;
+  // MI vectors per CTA slab: 16 for a single right-hand side, 8 for 2, 4 for 3..4
+  int MI = p.b == 1 ? 16 : (p.b == 2 ? 8 : 4);
+  int ny = (p.m + MI - 1) / MI;
+  int gx = cv_grid_for(ctx, np, CV_BLOCK);
+  // keep (gx * values) inside the partials area and the whole grid near one wave
+  int64_t per_slab = (int64_t)MI * p.b * NR;
+  while ((int64_t)gx * per_slab * ny > (int64_t)CV_N_PARTIALS && gx > 1) gx >>= 1;
+  if (ny > 1) {
+    int cap = (ctx->sms * CV_CTAS_PER_SM * 2) / ny;
+    if (cap < 1) cap = 1;
+    if (gx > cap) gx = cap;
+  }
+  dim3 grid(gx, ny);
+#define TSD(MI_, B_) \
+  k_tsdot<T, W, CONJ, MI_, B_><<<grid, CV_BLOCK, 0, st>>>(p, ctx->partials, ctx->counters, out)
+  switch (p.b) {
+    case 1: TSD(16, 1); break;
+    case 2: TSD(8, 2); break;
+    case 3: TSD(4, 3); break;
+    case 4: TSD(4, 4); break;
+    default:
+      cv_set_error("tsdot: b=%d outside 1..4", p.b);
+      return CV_ERR_ARG;
+  }
+#undef TSD
+  CV_TRY(cv_check_launch(ctx, "tsdot"));
+  return cv_reduce_ranks(ctx, slot, p.m * p.b * NR, st);
+}
+
+int cv_tsdot_dev(cv_ctx *ctx, int64_t n, int cplx_, int conj, int m, const void *const *v, int b,
+                 const void *const *w, int slot, cudaStream_t st) {
+  CV_REQUIRE(m >= 1 && m <= CV_MAX_PTRS && b >= 1 && b <= 4, "tsdot: m=%d b=%d out of range", m, b);
+  CV_REQUIRE(m * b * (cplx_ ? 2 : 1) <= CV_MAX_RED, "tsdot: too many values");
+  CV_REQUIRE(CV_MAX_PTRS / 4 <= (int)CV_N_COUNTERS, "tsdot: counters");
+  TsParams p;
+  p.m = m;
+  p.b = b;
+  p.n = n;
+  int W = cplx_ ? 1 : 2;
+  for (int i = 0; i < m; ++i) {
+    p.v[i] = v[i];
+    if ((uintptr_t)v[i] & 15) W = 1;
+  }
+  for (int k = 0; k < b; ++k) {
+    p.w[k] = w[k];
+    if ((uintptr_t)w[k] & 15) W = 1;
+  }
+  if (cplx_) return conj ? launch_tsdot<cplx, 1, true>(ctx, p, slot, st) : launch_tsdot<cplx, 1, false>(ctx, p, slot, st);
+  // real: conjugation is the identity
+  return W == 2 ? launch_tsdot<double, 2, false>(ctx, p, slot, st) : launch_tsdot<double, 1, false>(ctx, p, slot, st);
+}
+
+extern "C" int cv_tsdot(cv_ctx *ctx, int64_t n, int cplx_, int conj, int m, const void *const *v_ptrs,
+                        int b, const void *const *w_ptrs, double *out_host, void *stream) {
+  CV_REQUIRE(ctx && v_ptrs && w_ptrs && out_host && n >= 0, "cv_tsdot: bad argument");
+  CV_REQUIRE(m >= 1 && m <= CV_MAX_PTRS && b >= 1, "cv_tsdot: m=%d b=%d out of range", m, b);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nr = cplx_ ? 2 : 1;
+  // chunk the right-hand sides by 4; results are assembled as out[(i*b + k)*nr + c]
+  for (int k0 = 0; k0 < b; k0 += 4) {
+    int bb = b - k0 < 4 ? b - k0 : 4;
+    CV_TRY(cv_tsdot_dev(ctx, n, cplx_, conj, m, v_ptrs, bb, w_ptrs + k0, CV_S_TS, st));
+    CV_TRY(cv_fetch_scalars(ctx, CV_S_TS, m * bb * nr, st));
+    for (int i = 0; i < m; ++i)
+      for (int k = 0; k < bb; ++k)
+        for (int c = 0; c < nr; ++c)
+          out_host[((size_t)i * b + k0 + k) * nr + c] = ctx->mailbox[CV_S_TS + (i * bb + k) * nr + c];
+  }
+  return CV_OK;
+}
+
+// w -= V h  (h = ctx->scalars[h_slot ..)), optional |w|^2 into norm_slot
+int cv_tsupdate_dev(cv_ctx *ctx, int64_t n, int cplx_, int m, const void *const *v, int h_slot,
+                    void *w, int norm_slot, cudaStream_t st) {
+  CV_REQUIRE(m >= 1 && m <= CV_MAX_PTRS, "tsupdate: m=%d out of range", m);
+  TsParams p;
+  p.m = m;
+  p.b = 1;
+  p.n = n;
+  int W = cplx_ ? 1 : 2;
+  for (int i = 0; i < m; ++i) {
+    p.v[i] = v[i];
+    if ((uintptr_t)v[i] & 15) W = 1;
+  }
+  if ((uintptr_t)w & 15) W = 1;
+  int grid = cv_grid_for(ctx, (n + W - 1) / W, CV_BLOCK);
+  const double *h = ctx->scalars + h_slot;
+  double *on = norm_slot >= 0 ? ctx->scalars + norm_slot : nullptr;
+  size_t sh = sizeof(double) * m * (cplx_ ? 2 : 1);
+#define TSU(T, WW, NM) \
+  k_tsupdate<T, WW, NM><<<grid, CV_BLOCK, sh, st>>>(p, h, (T *)w, ctx->partials, ctx->counters, on)
+  if (cplx_) {
+    if (on) TSU(cplx, 1, true); else TSU(cplx, 1, false);
+  } else if (W == 2) {
+    if (on) TSU(double, 2, true); else TSU(double, 2, false);
+  } else {
+    if (on) TSU(double, 1, true); else TSU(double, 1, false);
+  }
+#undef TSU
+  CV_TRY(cv_check_launch(ctx, "tsupdate"));
+  if (on) CV_TRY(cv_reduce_ranks(ctx, norm_slot, 1, st));
+  return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Gram-Schmidt against a set (reference semantics, numpyVector.py:121-145)
+// ------------------------------------------------------------------------------------------
+template <typename T, int W>
+static int gs_chain(cv_ctx *ctx, int64_t n, const T *x_in, int m, const void *const *q, T *x_out,
+                    cudaStream_t st) {
+  constexpr int NR = Num<T>::NRED;
+  int grid = cv_grid_for(ctx, (n + W - 1) / W, CV_BLOCK);
+  // step i: subtract projection on q[i-1] (coefficients from slot i-1), dots with q[i]
+  for (int i = 0; i <= m; ++i) {
+    const T *src = (i == 0) ? x_in : x_out;
+    const T *qp = (i == 0) ? nullptr : static_cast<const T *>(q[i - 1]);
+    const T *qc = (i == m) ? nullptr : static_cast<const T *>(q[i]);
+    const double *tprev = ctx->scalars + CV_S_GS + 2 * NR * (i > 0 ? i - 1 : 0);
+    double *tout = ctx->scalars + CV_S_GS + 2 * NR * i;
+    k_mgs_step<T, W><<<grid, CV_BLOCK, 0, st>>>(n, src, x_out, qp, tprev, qc, ctx->partials,
+                                                ctx->counters, tout);
+    CV_TRY(cv_check_launch(ctx, "mgs_step"));
+    CV_TRY(cv_reduce_ranks(ctx, CV_S_GS + 2 * NR * i, 2 * NR, st));
+  }
+  return CV_OK;
+}
+
+extern "C" int cv_gs_against_set(cv_ctx *ctx, int64_t n, int cplx_, const void *x_in, int m,
+                                 const void *const *q_ptrs, double lindep, void *x_out, int *status,
+                                 double *innerprod_host, void *stream) {
+  CV_REQUIRE(ctx && x_in && x_out && status && innerprod_host, "cv_gs_against_set: null argument");
+  CV_REQUIRE(m >= 0 && m < CV_MAX_PTRS, "cv_gs_against_set: m=%d out of range", m);
+  CV_REQUIRE(m == 0 || q_ptrs, "cv_gs_against_set: null q_ptrs");
+  CV_REQUIRE(x_in != x_out, "cv_gs_against_set: out of place only");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int NR = cplx_ ? 2 : 1;
+  int W = cplx_ ? 1 : 2;
+  if (((uintptr_t)x_in | (uintptr_t)x_out) & 15) W = 1;
+  for (int i = 0; i < m; ++i)
+    if ((uintptr_t)q_ptrs[i] & 15) W = 1;
+  if (cplx_)
+    CV_TRY((gs_chain<cplx, 1>(ctx, n, (const cplx *)x_in, m, q_ptrs, (cplx *)x_out, st)));
+  else if (W == 2)
+    CV_TRY((gs_chain<double, 2>(ctx, n, (const double *)x_in, m, q_ptrs, (double *)x_out, st)));
+  else
+    CV_TRY((gs_chain<double, 1>(ctx, n, (const double *)x_in, m, q_ptrs, (double *)x_out, st)));
+  const int slot = CV_S_GS + 2 * NR * m;  // innerprod = x.x
+  CV_TRY(cv_fetch_scalars(ctx, slot, NR, st));
+  innerprod_host[0] = ctx->mailbox[slot];
+  innerprod_host[1] = cplx_ ? ctx->mailbox[slot + 1] : 0.0;
+  // numpyVector.py:141: `innerprod > lindep` (for complex data numpy compares lexicographically;
+  // the real part decides unless it ties)
+  bool ok = innerprod_host[0] > lindep || (innerprod_host[0] == lindep && innerprod_host[1] > 0.0);
+  if (!ok) {
+    *status = 1;
+    return CV_OK;
+  }
+  *status = 0;
+  if (cplx_) {
+    k_div_csqrt<<<cv_grid_for(ctx, n, CV_BLOCK), CV_BLOCK, 0, st>>>(n, (cplx *)x_out, ctx->scalars + slot);
+    return cv_check_launch(ctx, "div_csqrt");
+  }
+  return cv_scale_dev(ctx, n, 0, x_out, nullptr, slot, 0, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// operator
+// ------------------------------------------------------------------------------------------
+extern "C" int cv_op_create_csr(cv_ctx *ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                                const int64_t *indptr_dev, const int32_t *indices_dev,
+                                const double *data_dev, cv_op **out) {
+  CV_REQUIRE(ctx && out && indptr_dev, "cv_op_create_csr: null argument");
+  CV_REQUIRE(n_rows >= 0 && n_cols >= 0 && nnz >= 0, "cv_op_create_csr: negative size");
+  CV_REQUIRE(n_cols < ((int64_t)1 << 31), "cv_op_create_csr: column indices are int32");
+  CV_REQUIRE(nnz == 0 || (indices_dev && data_dev), "cv_op_create_csr: null arrays");
+  cv_op *op = new cv_op();
+  op->n_rows = n_rows;
+  op->n_cols = n_cols;
+  op->nnz = nnz;
+  op->indptr = indptr_dev;
+  op->indices = indices_dev;
+  op->data = data_dev;
+  op->fmt = CV_FMT_CSR;
+  double mean = n_rows ? (double)nnz / (double)n_rows : 0.0;
+  op->csr_group = mean <= 4 ? 2 : mean <= 8 ? 4 : mean <= 16 ? 8 : mean <= 48 ? 16 : 32;
+  *out = op;
+  return CV_OK;
+}
+
+extern "C" int cv_op_destroy(cv_op *op) {
+  delete op;
+  return CV_OK;
+}
+
+extern "C" int cv_op_sell_widths(cv_ctx *ctx, cv_op *op, int32_t *widths_dev, void *stream) {
+  CV_REQUIRE(ctx && op && widths_dev, "cv_op_sell_widths: null argument");
+  int64_t ns = (op->n_rows + 31) / 32;
+  if (ns == 0) return CV_OK;
+  k_sell_widths<<<cv_grid_for(ctx, ns, CV_WARPS), CV_BLOCK, 0, (cudaStream_t)stream>>>(
+      op->n_rows, ns, op->indptr, widths_dev);
+  return cv_check_launch(ctx, "sell_widths");
+}
+
+extern "C" int cv_op_attach_sell(cv_ctx *ctx, cv_op *op, const int64_t *slice_ptr_dev,
+                                 int64_t padded_nnz, int32_t *sell_col_dev, double *sell_val_dev,
+                                 void *stream) {
+  CV_REQUIRE(ctx && op && slice_ptr_dev, "cv_op_attach_sell: null argument");
+  CV_REQUIRE(padded_nnz == 0 || (sell_col_dev && sell_val_dev), "cv_op_attach_sell: null storage");
+  int64_t ns = (op->n_rows + 31) / 32;
+  op->n_slices = ns;
+  op->slice_ptr = slice_ptr_dev;
+  op->sell_col = sell_col_dev;
+  op->sell_val = sell_val_dev;
+  op->padded_nnz = padded_nnz;
+  if (ns > 0) {
+    k_sell_fill<<<cv_grid_for(ctx, ns, CV_WARPS), CV_BLOCK, 0, (cudaStream_t)stream>>>(
+        op->n_rows, op->n_cols, ns, op->indptr, op->indices, op->data, slice_ptr_dev, sell_col_dev,
+        sell_val_dev);
+    CV_TRY(cv_check_launch(ctx, "sell_fill"));
+  }
+  op->fmt = CV_FMT_SELL;
+  return CV_OK;
+}
+
+extern "C" int cv_op_set_format(cv_op *op, int fmt) {
+  CV_REQUIRE(op, "cv_op_set_format: null operator");
+  CV_REQUIRE(fmt == CV_FMT_CSR || (fmt == CV_FMT_SELL && op->slice_ptr), "cv_op_set_format: format %d not available", fmt);
+  op->fmt = fmt;
+  return CV_OK;
+}
+
+extern "C" int cv_op_info(cv_op *op, int64_t *n_rows, int64_t *nnz, int64_t *padded_nnz, int *fmt) {
+  CV_REQUIRE(op, "cv_op_info: null operator");
+  if (n_rows) *n_rows = op->n_rows;
+  if (nnz) *nnz = op->nnz;
+  if (padded_nnz) *padded_nnz = op->padded_nnz;
+  if (fmt) *fmt = op->fmt;
+  return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// SpMV dispatch
+// ------------------------------------------------------------------------------------------
+template <typename T, bool HALO, bool EPI, bool DOTS>
+static int launch_spmv_fmt(cv_ctx *ctx, cv_op *op, const SpmvArgs<T> &a, cudaStream_t st) {
+  if (op->fmt == CV_FMT_SELL) {
+    int grid = cv_grid_for(ctx, op->n_slices, CV_WARPS);
+    k_spmv_sell<T, HALO, EPI, DOTS><<<grid, CV_BLOCK, 0, st>>>(a);
+  } else {
+#define CSR(G)                                                    \
+  {                                                               \
+    int grid = cv_grid_for(ctx, op->n_rows, CV_BLOCK / G);        \
+    k_spmv_csr<T, G, HALO, EPI, DOTS><<<grid, CV_BLOCK, 0, st>>>(a); \
+  }
+    switch (op->csr_group) {
+      case 2: CSR(2); break;
+      case 4: CSR(4); break;
+      case 8: CSR(8); break;
+      case 16: CSR(16); break;
+      default: CSR(32); break;
+    }
+#undef CSR
+  }
+  return cv_check_launch(ctx, "spmv");
+}
+
+template <typename T>
+static int launch_spmv_t(cv_ctx *ctx, cv_op *op, int mode, T sigma, const T *x, T *y, double alpha,
+                         double beta1, const T *u1, bool epi, int dots_slot, cudaStream_t st) {
+  SpmvArgs<T> a;
+  a.n_rows = op->n_rows;
+  a.n_slices = op->n_slices;
+  a.slice_ptr = op->slice_ptr;
+  a.sell_col = op->sell_col;
+  a.sell_val = op->sell_val;
+  a.indptr = op->indptr;
+  a.indices = op->indices;
+  a.data = op->data;
+  a.x = x;
+  a.halo = static_cast<const T *>(op->halobuf);
+  a.n_local_cols = op->n_halo > 0 ? op->n_cols - op->n_halo : op->n_cols;
+  a.y = y;
+  a.mode = mode;
+  a.sigma = sigma;
+  a.alpha = alpha;
+  a.beta1 = beta1;
+  a.u1 = u1;
+  a.partials = ctx->partials;
+  a.counter = ctx->counters;
+  a.out = dots_slot >= 0 ? ctx->scalars + dots_slot : nullptr;
+  const bool halo = op->n_halo > 0;
+  const bool dots = dots_slot >= 0;
+  if (halo) CV_TRY(cv_halo_exchange(ctx, op, sizeof(T) == 16, x, st));
+  int rc;
+#define GO(H, E, D) rc = launch_spmv_fmt<T, H, E, D>(ctx, op, a, st)
+  if (halo) {
+    if (epi) { if (dots) GO(true, true, true); else GO(true, true, false); }
+    else     { if (dots) GO(true, false, true); else GO(true, false, false); }
+  } else {
+    if (epi) { if (dots) GO(false, true, true); else GO(false, true, false); }
+    else     { if (dots) GO(false, false, true); else GO(false, false, false); }
+  }
+#undef GO
+  CV_TRY(rc);
+  if (dots) CV_TRY(cv_reduce_ranks(ctx, dots_slot, Num<T>::NRED + 1, st));
+  return CV_OK;
+}
+
+int cv_spmv_dev(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim, const void *x,
+                void *y, double alpha, double beta1, const void *u1, bool epi, int dots_slot,
+                cudaStream_t st) {
+  CV_REQUIRE(mode >= 0 && mode <= 2, "spmv: mode %d", mode);
+  CV_REQUIRE(x != y, "spmv: x and y must not alias");
+  if (op->n_rows == 0) return CV_OK;
+  if (cplx_)
+    return launch_spmv_t<cplx>(ctx, op, mode, make_cplx(sre, sim), (const cplx *)x, (cplx *)y, alpha,
+                               beta1, (const cplx *)u1, epi, dots_slot, st);
+  CV_REQUIRE(sim == 0.0, "spmv: complex shift needs complex vectors");
+  return launch_spmv_t<double>(ctx, op, mode, sre, (const double *)x, (double *)y, alpha, beta1,
+                               (const double *)u1, epi, dots_slot, st);
+}
+
+extern "C" int cv_spmv(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sigma_re, double sigma_im,
+                       const void *x, void *y, void *stream) {
+  CV_REQUIRE(ctx && op && x && y, "cv_spmv: null argument");
+  return cv_spmv_dev(ctx, op, cplx_, mode, sigma_re, sigma_im, x, y, 1.0, 0.0, nullptr, false, -1,
+                     (cudaStream_t)stream);
+}
+
+extern "C" int cv_spmv_dots(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sigma_re,
+                            double sigma_im, const void *x, void *y, double *out3_host, void *stream) {
+  CV_REQUIRE(ctx && op && x && y, "cv_spmv_dots: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CV_TRY(cv_spmv_dev(ctx, op, cplx_, mode, sigma_re, sigma_im, x, y, 1.0, 0.0, nullptr, false,
+                     CV_S_TMP, st));
+  if (out3_host) {
+    CV_TRY(cv_fetch_scalars(ctx, CV_S_TMP, 3, st));
+    if (cplx_) {
+      out3_host[0] = ctx->mailbox[CV_S_TMP];
+      out3_host[1] = ctx->mailbox[CV_S_TMP + 1];
+      out3_host[2] = ctx->mailbox[CV_S_TMP + 2];
+    } else {
+      out3_host[0] = ctx->mailbox[CV_S_TMP];
+      out3_host[1] = 0.0;
+      out3_host[2] = ctx->mailbox[CV_S_TMP + 1];
+    }
+  }
+  return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// extension of the overlap / operator matrices by one column (numpyVector.py:205-238)
+// ------------------------------------------------------------------------------------------
+extern "C" int cv_extend_columns(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int m,
+                                 const void *const *v_ptrs, void *ket_tmp, double *s_col_host,
+                                 double *h_col_host, void *stream) {
+  CV_REQUIRE(ctx && v_ptrs && m >= 1 && m <= CV_MAX_PTRS, "cv_extend_columns: bad argument");
+  CV_REQUIRE(s_col_host || h_col_host, "cv_extend_columns: nothing to compute");
+  CV_REQUIRE(!h_col_host || (op && ket_tmp), "cv_extend_columns: operator column needs op and ket_tmp");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nr = cplx_ ? 2 : 1;
+  const void *w[2];
+  int b = 0;
+  if (s_col_host) w[b++] = v_ptrs[m - 1];
+  if (h_col_host) {
+    CV_REQUIRE(op->n_rows == n, "cv_extend_columns: operator has %lld rows, vectors %lld", (long long)op->n_rows, (long long)n);
+    CV_TRY(cv_spmv_dev(ctx, op, cplx_, CV_SPMV_PLAIN, 0.0, 0.0, v_ptrs[m - 1], ket_tmp, 1.0, 0.0,
+                       nullptr, false, -1, st));
+    w[b++] = ket_tmp;
+  }
+  CV_TRY(cv_tsdot_dev(ctx, n, cplx_, 1, m, v_ptrs, b, w, CV_S_TS, st));
+  CV_TRY(cv_fetch_scalars(ctx, CV_S_TS, m * b * nr, st));
+  for (int i = 0; i < m; ++i) {
+    int k = 0;
+    if (s_col_host) {
+      for (int c = 0; c < nr; ++c) s_col_host[i * nr + c] = ctx->mailbox[CV_S_TS + (i * b + k) * nr + c];
+      ++k;
+    }
+    if (h_col_host)
+      for (int c = 0; c < nr; ++c) h_col_host[i * nr + c] = ctx->mailbox[CV_S_TS + (i * b + k) * nr + c];
+  }
+  return CV_OK;
+}

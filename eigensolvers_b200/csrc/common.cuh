@@ -1,0 +1,308 @@
+// common.cuh — shared device/host helpers of libcudavec (sm_100a only).
+//
+// Everything on this path is fp64 and HBM-bound, so the helpers here are about
+// three things only: wide coalesced loads with streaming cache hints, deterministic two-stage
+// reductions (warp shuffle -> block -> ordered sum over blocks by the last block to arrive),
+// and a complex type whose memory layout equals numpy's complex128.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include "../../include/cudavec.h"
+
+// ------------------------------------------------------------------------------------------
+// error plumbing (no exceptions across the C ABI)
+// ------------------------------------------------------------------------------------------
+void cv_set_error(const char *fmt, ...);
+
+#define CV_CUDA(call)                                                                     \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      cv_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return CV_ERR_CUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+#define CV_TRY(call)            \
+  do {                          \
+    int rc__ = (call);          \
+    if (rc__ != CV_OK) return rc__; \
+  } while (0)
+
+#define CV_REQUIRE(cond, ...)     \
+  do {                            \
+    if (!(cond)) {                \
+      cv_set_error(__VA_ARGS__);  \
+      return CV_ERR_ARG;          \
+    }                             \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// launch geometry: B200 has 148 SMs; streaming kernels run as persistent grid-stride grids of
+// 148 x 8 CTAs x 256 threads (= 2048 resident threads per SM, one full wave).
+// ------------------------------------------------------------------------------------------
+constexpr int CV_BLOCK = 256;
+constexpr int CV_WARPS = CV_BLOCK / 32;
+constexpr int CV_CTAS_PER_SM = 8;
+constexpr int CV_MAX_GRID = 148 * CV_CTAS_PER_SM * 2;  // upper bound used to size scratch
+constexpr int CV_MAX_PTRS = 128;                       // vectors per tall-skinny call
+constexpr int CV_MAX_COEF = 256;                       // doubles of coefficients per launch
+constexpr int CV_MAX_RED = 1024;                       // reduction values per launch
+
+// scratch layout handed over by the host language (torch tensor), see cv_ctx_create
+constexpr size_t CV_N_COUNTERS = 64;                     // unsigned tickets
+constexpr size_t CV_N_SCALARS = 4096;                    // doubles: reduction results / coefficients
+constexpr size_t CV_N_PARTIALS = (size_t)1 << 21;        // doubles: per-CTA partial sums (16 MiB)
+
+struct cv_comm_state;  // NCCL state, comm.cu
+
+struct cv_ctx {
+  int device;
+  int sms;
+  unsigned *counters;   // device, zeroed
+  double *scalars;      // device
+  double *partials;     // device
+  double *mailbox;      // pinned host mirror of `scalars`
+  uint64_t launches;
+  cv_comm_state *comm;  // null when world == 1
+  int rank, world;
+};
+
+inline int cv_grid_for(const cv_ctx *ctx, int64_t work_items, int items_per_cta) {
+  int64_t need = (work_items + items_per_cta - 1) / items_per_cta;
+  int64_t cap = (int64_t)ctx->sms * CV_CTAS_PER_SM;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+int cv_fetch_scalars(cv_ctx *ctx, int offset, int count, cudaStream_t st);  // D2H + sync
+int cv_reduce_ranks(cv_ctx *ctx, int offset, int count, cudaStream_t st);   // NCCL sum (world>1)
+
+// ------------------------------------------------------------------------------------------
+// complex128 with numpy layout
+// ------------------------------------------------------------------------------------------
+struct __align__(16) cplx {
+  double re, im;
+};
+
+__host__ __device__ inline cplx make_cplx(double r, double i) {
+  cplx c;
+  c.re = r;
+  c.im = i;
+  return c;
+}
+
+template <typename T>
+struct Num;
+
+template <>
+struct Num<double> {
+  static constexpr int NRED = 1;
+  __host__ __device__ static inline double zero() { return 0.0; }
+  __host__ __device__ static inline double make(double r, double) { return r; }
+  __device__ static inline double mul(double a, double b) { return a * b; }
+  __device__ static inline double add(double a, double b) { return a + b; }
+  __device__ static inline double sub(double a, double b) { return a - b; }
+  __device__ static inline double conj(double a) { return a; }
+  __device__ static inline double abs2(double a) { return a * a; }
+  __device__ static inline double scale(double a, double s) { return a * s; }
+  // acc += a*b
+  __device__ static inline void fma(double &acc, double a, double b) { acc = ::fma(a, b, acc); }
+  // acc += conj(a)*b
+  __device__ static inline void fmac(double &acc, double a, double b) { acc = ::fma(a, b, acc); }
+  // acc += s*b with real s
+  __device__ static inline void fmar(double &acc, double s, double b) { acc = ::fma(s, b, acc); }
+  __device__ static inline void to_red(double a, double *out) { out[0] = a; }
+  __device__ static inline double from_red(const double *in) { return in[0]; }
+};
+
+template <>
+struct Num<cplx> {
+  static constexpr int NRED = 2;
+  __host__ __device__ static inline cplx zero() { return make_cplx(0.0, 0.0); }
+  __host__ __device__ static inline cplx make(double r, double i) { return make_cplx(r, i); }
+  __device__ static inline cplx mul(cplx a, cplx b) {
+    return make_cplx(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+  }
+  __device__ static inline cplx add(cplx a, cplx b) { return make_cplx(a.re + b.re, a.im + b.im); }
+  __device__ static inline cplx sub(cplx a, cplx b) { return make_cplx(a.re - b.re, a.im - b.im); }
+  __device__ static inline cplx conj(cplx a) { return make_cplx(a.re, -a.im); }
+  __device__ static inline double abs2(cplx a) { return a.re * a.re + a.im * a.im; }
+  __device__ static inline cplx scale(cplx a, double s) { return make_cplx(a.re * s, a.im * s); }
+  __device__ static inline void fma(cplx &acc, cplx a, cplx b) {
+    acc.re = ::fma(a.re, b.re, acc.re);
+    acc.re = ::fma(-a.im, b.im, acc.re);
+    acc.im = ::fma(a.re, b.im, acc.im);
+    acc.im = ::fma(a.im, b.re, acc.im);
+  }
+  __device__ static inline void fmac(cplx &acc, cplx a, cplx b) {  // conj(a)*b
+    acc.re = ::fma(a.re, b.re, acc.re);
+    acc.re = ::fma(a.im, b.im, acc.re);
+    acc.im = ::fma(a.re, b.im, acc.im);
+    acc.im = ::fma(-a.im, b.re, acc.im);
+  }
+  __device__ static inline void fmar(cplx &acc, double s, cplx b) {
+    acc.re = ::fma(s, b.re, acc.re);
+    acc.im = ::fma(s, b.im, acc.im);
+  }
+  __device__ static inline void to_red(cplx a, double *out) {
+    out[0] = a.re;
+    out[1] = a.im;
+  }
+  __device__ static inline cplx from_red(const double *in) { return make_cplx(in[0], in[1]); }
+};
+
+// mixed helpers used by kernels templated on both a vector type and a coefficient type
+__device__ inline void cfma(double &acc, double c, double v) { acc = ::fma(c, v, acc); }
+__device__ inline void cfma(cplx &acc, double c, cplx v) { Num<cplx>::fmar(acc, c, v); }
+__device__ inline void cfma(cplx &acc, cplx c, cplx v) { Num<cplx>::fma(acc, c, v); }
+__device__ inline void cfma(cplx &acc, cplx c, double v) {
+  acc.re = ::fma(c.re, v, acc.re);
+  acc.im = ::fma(c.im, v, acc.im);
+}
+
+// ------------------------------------------------------------------------------------------
+// cache-hinted loads/stores.  Matrix values/indices and one-shot vector streams bypass L1
+// (ld.global.nc.L1::no_allocate) so that L1 stays available to the gathered x; results that
+// the next kernel re-reads go through the normal path so they can stay in the 126 MB L2.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ld_stream(const double *p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 ld_stream2(const double2 *p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+               : "=d"(v.x), "=d"(v.y)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ cplx ld_stream(const cplx *p) {
+  double2 v = ld_stream2(reinterpret_cast<const double2 *>(p));
+  return make_cplx(v.x, v.y);
+}
+__device__ __forceinline__ int ld_stream(const int *p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int2 ld_stream2(const int2 *p) {
+  int2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];"
+               : "=r"(v.x), "=r"(v.y)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int4 ld_stream4(const int4 *p) {
+  int4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+// gathered x: read-only path, allocate in L1 (neighbouring rows hit the same lines)
+__device__ __forceinline__ double ld_gather(const double *p) { return __ldg(p); }
+__device__ __forceinline__ cplx ld_gather(const cplx *p) {
+  double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+  return make_cplx(v.x, v.y);
+}
+// plain (coherent) loads for data written earlier by other kernels and possibly L2 resident
+__device__ __forceinline__ double ld_plain(const double *p) { return *p; }
+__device__ __forceinline__ cplx ld_plain(const cplx *p) {
+  double2 v = *reinterpret_cast<const double2 *>(p);
+  return make_cplx(v.x, v.y);
+}
+__device__ __forceinline__ void st_plain(double *p, double v) { *p = v; }
+__device__ __forceinline__ void st_plain(cplx *p, cplx v) {
+  *reinterpret_cast<double2 *>(p) = make_double2(v.re, v.im);
+}
+
+// ------------------------------------------------------------------------------------------
+// deterministic grid reduction
+//
+// Each CTA reduces NV doubles (warp shuffles, then across its 8 warps through shared memory),
+// stores them at partials[(v)*nblk + blockIdx.x], fences and takes a ticket.  The CTA that
+// draws the last ticket sums every value over all CTAs in a fixed order (warp w owns values
+// w, w+8, ..; lanes stride over CTAs; xor-shuffle tree) and writes out[v].  The result does
+// not depend on which CTA came last, so repeated runs are bit-identical.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int NV>
+__device__ __forceinline__ void grid_reduce(double (&vals)[NV], double *partials, unsigned *counter,
+                                            double *out, int nblk_total, int blk_linear) {
+  __shared__ double s_red[CV_WARPS][NV];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    double r = warp_sum(vals[v]);
+    if (lane == 0) s_red[warp][v] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double r = 0.0;
+#pragma unroll
+    for (int w = 0; w < CV_WARPS; ++w) r += s_red[w][threadIdx.x];
+    partials[(size_t)threadIdx.x * nblk_total + blk_linear] = r;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(counter, 1u);
+    s_last = (t == (unsigned)nblk_total - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int v = warp; v < NV; v += CV_WARPS) {
+    const double *p = partials + (size_t)v * nblk_total;
+    double r = 0.0;
+    for (int b = lane; b < nblk_total; b += 32) r += __ldcg(p + b);
+    r = warp_sum(r);
+    if (lane == 0) out[v] = r;
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+
+// runtime-sized variant (tall-skinny products): values live in shared memory, s_vals[nv]
+// already summed over the CTA.
+__device__ __forceinline__ void grid_reduce_dyn(const double *s_vals, int nv, double *partials,
+                                                unsigned *counter, double *out, int nblk_total,
+                                                int blk_linear) {
+  __shared__ bool s_last_dyn;
+  for (int v = threadIdx.x; v < nv; v += blockDim.x)
+    partials[(size_t)v * nblk_total + blk_linear] = s_vals[v];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(counter, 1u);
+    s_last_dyn = (t == (unsigned)nblk_total - 1u);
+  }
+  __syncthreads();
+  if (!s_last_dyn) return;
+  __threadfence();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int v = warp; v < nv; v += CV_WARPS) {
+    const double *p = partials + (size_t)v * nblk_total;
+    double r = 0.0;
+    for (int b = lane; b < nblk_total; b += 32) r += __ldcg(p + b);
+    r = warp_sum(r);
+    if (lane == 0) out[v] = r;
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+
+// scalar-slot map inside ctx->scalars (doubles).  Solvers use [CV_S_SOLVER, ...).
+constexpr int CV_S_TMP = 0;        // 16 doubles: dot/norm results of the BLAS-1 entry points
+constexpr int CV_S_GS = 16;        // 4*CV_MAX_PTRS doubles: MGS coefficients
+constexpr int CV_S_TS = 1024;      // CV_MAX_RED doubles: tall-skinny results
+constexpr int CV_S_SOLVER = 2048;  // solver scalars (h columns, norms, ...)

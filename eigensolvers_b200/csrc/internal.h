@@ -1,0 +1,46 @@
+// internal.h — declarations shared by the translation units of libcudavec
+#pragma once
+#include <vector>
+#include "common.cuh"
+#include "kernels_vec.cuh"
+#include "kernels_spmv.cuh"
+
+struct cv_op {
+  int64_t n_rows = 0, n_cols = 0, nnz = 0;
+  // CSR (borrowed device arrays)
+  const int64_t *indptr = nullptr;
+  const int32_t *indices = nullptr;
+  const double *data = nullptr;
+  int csr_group = 8;
+  // SELL-32 (borrowed device arrays)
+  int64_t n_slices = 0, padded_nnz = 0;
+  const int64_t *slice_ptr = nullptr;
+  const int32_t *sell_col = nullptr;
+  const double *sell_val = nullptr;
+  int fmt = CV_FMT_CSR;
+  // row-sharded mode: columns >= n_cols - n_halo address the halo buffer
+  int64_t n_halo = 0;
+  const int32_t *send_idx = nullptr;
+  std::vector<int64_t> send_off, recv_off;
+  void *sendbuf = nullptr, *halobuf = nullptr;
+};
+
+int cv_check_launch(cv_ctx *ctx, const char *what);
+
+// device-resident variants: results land in ctx->scalars[slot ...) (already summed over ranks)
+int cv_dot_dev(cv_ctx *ctx, int64_t n, int cplx_, int conj, const void *x, const void *y, int slot,
+               cudaStream_t st);
+int cv_nrm2sq_dev(cv_ctx *ctx, int64_t n, int cplx_, const void *x, int slot, cudaStream_t st);
+int cv_scale_dev(cv_ctx *ctx, int64_t n, int cplx_, void *x, void *x2, int slot, int mode,
+                 cudaStream_t st);
+int cv_lincomb_launch(cv_ctx *ctx, int64_t n, int v_cplx, int c_cplx, int m, const void *const *v,
+                      int ncol, const double *coef, int ldc, int col0, void *const *y, int norm_slot,
+                      cudaStream_t st);
+int cv_tsdot_dev(cv_ctx *ctx, int64_t n, int cplx_, int conj, int m, const void *const *v, int b,
+                 const void *const *w, int slot, cudaStream_t st);
+int cv_tsupdate_dev(cv_ctx *ctx, int64_t n, int cplx_, int m, const void *const *v, int h_slot,
+                    void *w, int norm_slot, cudaStream_t st);
+int cv_spmv_dev(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim, const void *x,
+                void *y, double alpha, double beta1, const void *u1, bool epi, int dots_slot,
+                cudaStream_t st);
+int cv_halo_exchange(cv_ctx *ctx, cv_op *op, bool cplx_, const void *x, cudaStream_t st);

@@ -1,0 +1,222 @@
+// kernels_spmv.cuh — the fused shifted sparse matrix-vector product
+//
+//     y = alpha * op(x) + beta1 * u1,   op(x) = H x | sigma x - H x | H x - sigma x
+//     d_xy = <x|y>,  d_yy = <y|y>                       (partial dots, same pass)
+//
+// replacing `sigma*x - H@x` / `H@x - sigma*x` / `H@x` (numpyVector.py:152,154,100), the Lanczos
+// three-term update of MINRES (minres.py:215-222) and the w-norm of GCROT's Arnoldi step
+// (_gcrotmk.py:112-114) — each of which is a separate full pass with temporaries in the
+// reference.  H is real (fp64 values, int32 columns); x,y are fp64 or complex128 (FEAST's
+// complex shift: a complex x is two real right-hand sides sharing one pass over H).
+//
+// Algorithmic bytes per launch: 12*nnz + 20*N (fp64) / 12*nnz + 36*N (complex), SURVEY §8d.
+//
+// Two storage formats:
+//   SELL-32  thread-per-row, 32-row slices stored column-major: the val/col streams of a warp
+//            are perfectly coalesced 256 B / 128 B segments, x is gathered through L1/L2
+//            (neighbouring rows of the product-basis / stencil Hamiltonians hit the same lines).
+//   CSR      G threads per row (G = 2..32 by mean row length) with a shuffle reduction; the
+//            general fallback (dense-as-CSR test matrices, irregular rows).
+#pragma once
+#include "common.cuh"
+
+template <typename T>
+struct SpmvArgs {
+  int64_t n_rows;
+  // SELL
+  int64_t n_slices;
+  const int64_t *slice_ptr;
+  const int32_t *sell_col;
+  const double *sell_val;
+  // CSR
+  const int64_t *indptr;
+  const int32_t *indices;
+  const double *data;
+  // vectors
+  const T *x;
+  const T *halo;        // columns >= n_local_cols read halo[c - n_local_cols]
+  int64_t n_local_cols;
+  T *y;
+  int mode;
+  T sigma;
+  double alpha, beta1;
+  const T *u1;
+  // reductions
+  double *partials;
+  unsigned *counter;
+  double *out;  // [0..NRED) = <x|y>, [NRED] = <y|y>
+};
+
+template <typename T, bool HALO>
+__device__ __forceinline__ T spmv_gather(const SpmvArgs<T> &a, int c) {
+  if (HALO && c >= a.n_local_cols) return ld_gather(a.halo + (c - a.n_local_cols));
+  return ld_gather(a.x + c);
+}
+
+// shift + epilogue for one row; returns y_row and accumulates the dots
+template <typename T, bool EPI, bool DOTS>
+__device__ __forceinline__ void spmv_finish_row(const SpmvArgs<T> &a, int64_t row, T hx, T &d_xy,
+                                                double &d_yy) {
+  T xr = Num<T>::zero();
+  if (a.mode != CV_SPMV_PLAIN || DOTS) xr = ld_gather(a.x + row);
+  T r;
+  if (a.mode == CV_SPMV_PLAIN)
+    r = hx;
+  else if (a.mode == CV_SPMV_SHIFT)
+    r = Num<T>::sub(Num<T>::mul(a.sigma, xr), hx);
+  else
+    r = Num<T>::sub(hx, Num<T>::mul(a.sigma, xr));
+  if (EPI) {
+    r = Num<T>::scale(r, a.alpha);
+    if (a.u1) Num<T>::fmar(r, a.beta1, ld_plain(a.u1 + row));
+  }
+  st_plain(a.y + row, r);
+  if (DOTS) {
+    Num<T>::fmac(d_xy, xr, r);
+    d_yy += Num<T>::abs2(r);
+  }
+}
+
+template <typename T, bool DOTS>
+__device__ __forceinline__ void spmv_reduce(const SpmvArgs<T> &a, T d_xy, double d_yy) {
+  if (DOTS) {
+    constexpr int NR = Num<T>::NRED;
+    double vals[NR + 1];
+    Num<T>::to_red(d_xy, vals);
+    vals[NR] = d_yy;
+    grid_reduce<NR + 1>(vals, a.partials, a.counter, a.out, gridDim.x, blockIdx.x);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// SELL-32: one warp per slice, one thread per row, 4-way unrolled so that each thread keeps
+// 8 streaming loads + 4 gathers in flight.
+// ------------------------------------------------------------------------------------------
+template <typename T, bool HALO, bool EPI, bool DOTS>
+__global__ void __launch_bounds__(CV_BLOCK) k_spmv_sell(const __grid_constant__ SpmvArgs<T> a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * CV_WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * CV_WARPS;
+  T d_xy = Num<T>::zero();
+  double d_yy = 0.0;
+  for (int64_t s = warp0; s < a.n_slices; s += nwarps) {
+    const int64_t base = __ldg(a.slice_ptr + s);
+    const int width = (int)((__ldg(a.slice_ptr + s + 1) - base) >> 5);
+    const double *vp = a.sell_val + base + lane;
+    const int32_t *cp = a.sell_col + base + lane;
+    T acc0 = Num<T>::zero(), acc1 = Num<T>::zero();
+    int j = 0;
+    for (; j + 4 <= width; j += 4) {
+      int c0 = ld_stream(cp + (j + 0) * 32), c1 = ld_stream(cp + (j + 1) * 32);
+      int c2 = ld_stream(cp + (j + 2) * 32), c3 = ld_stream(cp + (j + 3) * 32);
+      double v0 = ld_stream(vp + (j + 0) * 32), v1 = ld_stream(vp + (j + 1) * 32);
+      double v2 = ld_stream(vp + (j + 2) * 32), v3 = ld_stream(vp + (j + 3) * 32);
+      T x0 = spmv_gather<T, HALO>(a, c0), x1 = spmv_gather<T, HALO>(a, c1);
+      T x2 = spmv_gather<T, HALO>(a, c2), x3 = spmv_gather<T, HALO>(a, c3);
+      Num<T>::fmar(acc0, v0, x0);
+      Num<T>::fmar(acc1, v1, x1);
+      Num<T>::fmar(acc0, v2, x2);
+      Num<T>::fmar(acc1, v3, x3);
+    }
+    for (; j < width; ++j) {
+      int c0 = ld_stream(cp + j * 32);
+      double v0 = ld_stream(vp + j * 32);
+      Num<T>::fmar(acc0, v0, spmv_gather<T, HALO>(a, c0));
+    }
+    const int64_t row = s * 32 + lane;
+    if (row < a.n_rows) spmv_finish_row<T, EPI, DOTS>(a, row, Num<T>::add(acc0, acc1), d_xy, d_yy);
+  }
+  spmv_reduce<T, DOTS>(a, d_xy, d_yy);
+}
+
+// ------------------------------------------------------------------------------------------
+// CSR: G lanes cooperate on one row.
+// ------------------------------------------------------------------------------------------
+template <typename T, int G, bool HALO, bool EPI, bool DOTS>
+__global__ void __launch_bounds__(CV_BLOCK) k_spmv_csr(const __grid_constant__ SpmvArgs<T> a) {
+  constexpr int RPB = CV_BLOCK / G;
+  const int grp = threadIdx.x / G, gl = threadIdx.x % G;
+  T d_xy = Num<T>::zero();
+  double d_yy = 0.0;
+  for (int64_t row0 = (int64_t)blockIdx.x * RPB; row0 < a.n_rows; row0 += (int64_t)gridDim.x * RPB) {
+    const int64_t row = row0 + grp;
+    const bool valid = row < a.n_rows;
+    T acc = Num<T>::zero();
+    if (valid) {
+      const int64_t rs = __ldg(a.indptr + row), re = __ldg(a.indptr + row + 1);
+      for (int64_t k = rs + gl; k < re; k += G) {
+        int c = ld_stream(a.indices + k);
+        double v = ld_stream(a.data + k);
+        Num<T>::fmar(acc, v, spmv_gather<T, HALO>(a, c));
+      }
+    }
+    // reduce over the G lanes of the group (G divides 32, groups are lane-aligned)
+    double r[Num<T>::NRED];
+    Num<T>::to_red(acc, r);
+#pragma unroll
+    for (int c = 0; c < Num<T>::NRED; ++c)
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) r[c] += __shfl_xor_sync(0xffffffffu, r[c], o);
+    if (valid && gl == 0) spmv_finish_row<T, EPI, DOTS>(a, row, Num<T>::from_red(r), d_xy, d_yy);
+  }
+  spmv_reduce<T, DOTS>(a, d_xy, d_yy);
+}
+
+// ------------------------------------------------------------------------------------------
+// SELL construction (one-time, per operator)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CV_BLOCK)
+    k_sell_widths(int64_t n_rows, int64_t n_slices, const int64_t *__restrict__ indptr,
+                  int32_t *__restrict__ widths) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * CV_WARPS + (threadIdx.x >> 5);
+  for (int64_t s = warp0; s < n_slices; s += (int64_t)gridDim.x * CV_WARPS) {
+    int64_t row = s * 32 + lane;
+    int len = 0;
+    if (row < n_rows) len = (int)(indptr[row + 1] - indptr[row]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if (lane == 0) widths[s] = len;
+  }
+}
+
+__global__ void __launch_bounds__(CV_BLOCK)
+    k_sell_fill(int64_t n_rows, int64_t n_cols, int64_t n_slices, const int64_t *__restrict__ indptr,
+                const int32_t *__restrict__ indices, const double *__restrict__ data,
+                const int64_t *__restrict__ slice_ptr, int32_t *__restrict__ sell_col,
+                double *__restrict__ sell_val) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * CV_WARPS + (threadIdx.x >> 5);
+  for (int64_t s = warp0; s < n_slices; s += (int64_t)gridDim.x * CV_WARPS) {
+    const int64_t base = slice_ptr[s];
+    const int width = (int)((slice_ptr[s + 1] - base) >> 5);
+    const int64_t row = s * 32 + lane;
+    int64_t rs = 0, len = 0;
+    if (row < n_rows) {
+      rs = indptr[row];
+      len = indptr[row + 1] - rs;
+    }
+    // padding points at a column that is certainly valid and already cached by this row
+    int32_t pad_col = (int32_t)(row < n_rows ? (row < n_cols ? row : n_cols - 1) : 0);
+    for (int j = 0; j < width; ++j) {
+      int64_t dst = base + (int64_t)j * 32 + lane;
+      if (j < len) {
+        sell_col[dst] = indices[rs + j];
+        sell_val[dst] = data[rs + j];
+      } else {
+        sell_col[dst] = pad_col;
+        sell_val[dst] = 0.0;
+      }
+    }
+  }
+}
+
+// pack the owned entries a peer needs into a contiguous send buffer (halo exchange)
+template <typename T>
+__global__ void __launch_bounds__(CV_BLOCK)
+    k_pack(int64_t n_send, const int32_t *__restrict__ idx, const T *__restrict__ x,
+           T *__restrict__ sendbuf) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_send; i += stride)
+    st_plain(sendbuf + i, ld_gather(x + idx[i]));
+}

@@ -1,0 +1,507 @@
+// solvers.cu — device-resident restatement of the two iterative solvers NumpyVector.solve
+// delegates to (numpyVector.py:147-178):
+//
+//   * scipy.sparse.linalg.gcrotmk  — flexible GCROT(m,k), Hicken & Zingg 2010
+//       (scipy/sparse/linalg/_isolve/_gcrotmk.py:16-183 `_fgmres`, :187-506 `gcrotmk`)
+//   * scipy.sparse.linalg.minres   — Paige & Saunders 1975 (…/_isolve/minres.py:13-379)
+//
+// All length-N work runs in the fused kernels of kernels_vec.cuh / kernels_spmv.cuh; the host
+// sees only scalars (one pinned-mailbox read per inner iteration) and keeps the tiny
+// Hessenberg QR / Givens recurrences, exactly the split the reference has between SciPy's
+// BLAS-1 calls and its Python control flow.
+//
+// Differences from SciPy that are deliberate:
+//   - GCROT orthogonalises the new Arnoldi vector against [C, V] with classical Gram-Schmidt
+//     applied twice (two tall-skinny passes) instead of (nc+j) sequential dot/axpy pairs; in
+//     exact arithmetic both give the same Hessenberg column, and CGS2 keeps orthogonality to
+//     machine precision.
+//   - unpreconditioned: z_j == v_j, so Z is not stored.
+#include <complex>
+#include <vector>
+#include <limits>
+#include "internal.h"
+
+typedef std::complex<double> zc;
+
+namespace {
+
+constexpr int S_W = CV_S_SOLVER;         // <x|y> (NRED) , <y|y>
+constexpr int S_NRM = CV_S_SOLVER + 4;   // squared norm of the orthogonalised vector
+constexpr int S_CX = CV_S_SOLVER + 5;    // |ux|^2, |cx|^2
+constexpr int S_GAMMA = CV_S_SOLVER + 8; // <cx|r> (NRED)
+constexpr int S_BETA = CV_S_SOLVER + 10; // |r|^2
+constexpr int S_H1 = CV_S_SOLVER + 16;
+constexpr int S_H2 = S_H1 + 2 * CV_MAX_PTRS;
+constexpr int S_END = S_H2 + 2 * CV_MAX_PTRS;
+static_assert(S_END <= (int)CV_N_SCALARS, "solver scalar slots exceed the mailbox");
+
+inline size_t vec_stride_bytes(int64_t n, int cplx_) {
+  size_t b = (size_t)n * (cplx_ ? 16 : 8);
+  return (b + 255) & ~(size_t)255;
+}
+
+struct Workspace {
+  char *base;
+  size_t stride;
+  void *vec(int i) const { return base + stride * (size_t)i; }
+};
+
+// y = a*x with a real host scalar (used for v0 = r/beta)
+int scal_real(cv_ctx *ctx, int64_t n, int cplx_, double a, const void *x, void *y, cudaStream_t st) {
+  return cv_scal(ctx, n, cplx_, cplx_, a, 0.0, x, y, (void *)st);
+}
+
+// ------------------------------------------------------------------------------------------
+// GCROT(m,k)
+// ------------------------------------------------------------------------------------------
+int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim, const void *b,
+            const void *x0, void *x, double rtol, double atol_in, int maxiter, int m, int k,
+            const Workspace &ws, cv_solve_stats *stats, cudaStream_t st) {
+  const int64_t n = op->n_rows;
+  const int NR = cplx_ ? 2 : 1;
+  const size_t ebytes = cplx_ ? 16 : 8;
+  const double eps = std::numeric_limits<double>::epsilon();
+  double *mb = ctx->mailbox;
+
+  // workspace map: r | V[0..m+k] | C ring (k+1) | U ring (k+1)
+  const int nV = m + k + 1;
+  void *r = ws.vec(0);
+  auto V = [&](int i) { return ws.vec(1 + i); };
+  auto Cs = [&](int i) { return ws.vec(1 + nV + i); };
+  auto Us = [&](int i) { return ws.vec(1 + nV + (k + 1) + i); };
+  std::vector<int> cu_slots;  // ring order: oldest first (scipy `CU` list)
+  std::vector<int> free_slots;
+  for (int i = k; i >= 0; --i) free_slots.push_back(i);
+
+  // x = x0 or 0;  r = b - A x
+  if (x0) {
+    if (x0 != x) CV_TRY(cv_copy(ctx, n, cplx_, x0, x, (void *)st));
+    CV_TRY(cv_spmv_dev(ctx, op, cplx_, mode, sre, sim, x, r, -1.0, 1.0, b, true, -1, st));
+    stats->n_matvec++;
+  } else {
+    CV_CUDA(cudaMemsetAsync(x, 0, (size_t)n * ebytes, st));
+    CV_TRY(cv_copy(ctx, n, cplx_, b, r, (void *)st));
+  }
+  CV_TRY(cv_nrm2sq_dev(ctx, n, cplx_, b, S_W, st));
+  CV_TRY(cv_nrm2sq_dev(ctx, n, cplx_, r, S_BETA, st));
+  CV_TRY(cv_fetch_scalars(ctx, S_W, S_BETA - S_W + 1, st));
+  stats->n_sync++;
+  const double b_norm = sqrt(mb[S_W]);
+  double beta = sqrt(mb[S_BETA]);
+  stats->b_norm = b_norm;
+  if (!std::isfinite(b_norm)) {
+    cv_set_error("gcrotmk: RHS must contain only finite numbers");
+    return CV_ERR_ARG;
+  }
+  const double atol = std::max(atol_in, rtol * b_norm);  // _get_atol_rtol
+  if (b_norm == 0.0) {  // _gcrotmk.py:307-309: x = b
+    CV_TRY(cv_copy(ctx, n, cplx_, b, x, (void *)st));
+    stats->info = 0;
+    return CV_OK;
+  }
+
+  const int mlmax = m + k;
+  std::vector<zc> Q((size_t)(mlmax + 2) * (mlmax + 2)), R((size_t)(mlmax + 2) * (mlmax + 1));
+  std::vector<zc> B((size_t)(k + 1) * (mlmax + 1)), y(mlmax + 2), hy(mlmax + 2), by(k + 1), hcur(mlmax + 2);
+  const int ldq = mlmax + 2, ldr = mlmax + 1, ldb = mlmax + 1;
+  std::vector<const void *> basis(CV_MAX_PTRS);
+  std::vector<double> coef(2 * 2 * CV_MAX_PTRS);
+
+  int j_outer = 0;
+  bool converged = false;
+  for (j_outer = 0; j_outer < maxiter; ++j_outer) {
+    const double beta_tol = std::max(atol, rtol * b_norm);
+    if (beta <= beta_tol && (j_outer > 0 || !cu_slots.empty())) {
+      // recompute the residual to avoid rounding error (_gcrotmk.py:384-387)
+      CV_TRY(cv_spmv_dev(ctx, op, cplx_, mode, sre, sim, x, r, -1.0, 1.0, b, true, S_W, st));
+      stats->n_matvec++;
+      CV_TRY(cv_fetch_scalars(ctx, S_W, NR + 1, st));
+      stats->n_sync++;
+      beta = sqrt(mb[S_W + NR]);
+    }
+    stats->resid = beta;
+    if (beta <= beta_tol) {
+      converged = true;
+      break;
+    }
+    const int nc = (int)cu_slots.size();
+    const int ml = m + std::max(k - nc, 0);
+    const double atol_inner = std::max(atol, rtol * b_norm) / beta;
+
+    // ---- FGMRES (Arnoldi with projection against C), _gcrotmk.py:93-168 ----
+    CV_TRY(scal_real(ctx, n, cplx_, 1.0 / beta, r, V(0), st));
+    for (int c = 0; c < nc; ++c) basis[c] = Cs(cu_slots[c]);
+    std::fill(Q.begin(), Q.end(), zc(0));
+    std::fill(R.begin(), R.end(), zc(0));
+    std::fill(B.begin(), B.end(), zc(0));
+    Q[0] = 1.0;
+    int j = 0;
+    bool breakdown = false;
+    double res = NAN;
+    for (j = 0; j < ml; ++j) {
+      void *w = V(j + 1);
+      CV_TRY(cv_spmv_dev(ctx, op, cplx_, mode, sre, sim, V(j), w, 1.0, 0.0, nullptr, false, S_W, st));
+      stats->n_matvec++;
+      basis[nc + j] = V(j);
+      const int nb = nc + j + 1;
+      const void *wp[1] = {w};
+      CV_TRY(cv_tsdot_dev(ctx, n, cplx_, 1, nb, basis.data(), 1, wp, S_H1, st));
+      CV_TRY(cv_tsupdate_dev(ctx, n, cplx_, nb, basis.data(), S_H1, w, -1, st));
+      CV_TRY(cv_tsdot_dev(ctx, n, cplx_, 1, nb, basis.data(), 1, wp, S_H2, st));
+      CV_TRY(cv_tsupdate_dev(ctx, n, cplx_, nb, basis.data(), S_H2, w, S_NRM, st));
+      CV_TRY(cv_scale_dev(ctx, n, cplx_, w, nullptr, S_NRM, 1, st));
+      CV_TRY(cv_fetch_scalars(ctx, S_W, S_H2 + nb * NR - S_W, st));
+      stats->n_sync++;
+      const double w_norm = sqrt(mb[S_W + NR]);
+      for (int i = 0; i < nb; ++i) {
+        zc h = cplx_ ? zc(mb[S_H1 + 2 * i] + mb[S_H2 + 2 * i], mb[S_H1 + 2 * i + 1] + mb[S_H2 + 2 * i + 1])
+                     : zc(mb[S_H1 + i] + mb[S_H2 + i], 0.0);
+        if (i < nc)
+          B[(size_t)i * ldb + j] = h;
+        else
+          hcur[i - nc] = h;
+      }
+      const double hlast = sqrt(mb[S_NRM]);
+      hcur[j + 1] = hlast;
+      if (!(hlast > eps * w_norm)) breakdown = true;
+
+      // ---- insert column j into H = Q R (Givens), _gcrotmk.py:149-157 ----
+      // u = blockdiag(Q,1)^H hcur
+      std::vector<zc> u(j + 2);
+      for (int c = 0; c <= j; ++c) {
+        zc s = 0;
+        for (int i = 0; i <= j; ++i) s += std::conj(Q[(size_t)i * ldq + c]) * hcur[i];
+        u[c] = s;
+      }
+      u[j + 1] = hcur[j + 1];
+      for (int i = 0; i <= j + 1; ++i) Q[(size_t)i * ldq + (j + 1)] = 0, Q[(size_t)(j + 1) * ldq + i] = 0;
+      Q[(size_t)(j + 1) * ldq + (j + 1)] = 1.0;
+      {
+        const zc a = u[j], bb = u[j + 1];
+        const double na = std::abs(a), nbb = std::abs(bb);
+        const double rho = std::hypot(na, nbb);
+        double c;
+        zc s;
+        if (rho == 0.0 || !std::isfinite(rho)) {
+          c = 1.0;
+          s = 0.0;
+        } else if (na == 0.0) {
+          c = 0.0;
+          s = std::conj(bb) / nbb;
+        } else {
+          c = na / rho;
+          s = (a / na) * std::conj(bb) / rho;
+        }
+        const zc rjj = c * a + s * bb;
+        for (int i = 0; i < j; ++i) R[(size_t)i * ldr + j] = u[i];
+        R[(size_t)j * ldr + j] = rjj;
+        R[(size_t)(j + 1) * ldr + j] = 0.0;
+        for (int i = 0; i <= j + 1; ++i) {
+          zc qa = Q[(size_t)i * ldq + j], qb = Q[(size_t)i * ldq + j + 1];
+          Q[(size_t)i * ldq + j] = qa * c + qb * std::conj(s);
+          Q[(size_t)i * ldq + j + 1] = -qa * s + qb * c;
+        }
+      }
+      res = std::abs(Q[j + 1]);  // |Q[0,-1]|
+      if (res < atol_inner || breakdown) break;
+    }
+    if (j == ml) j = ml - 1;  // python's loop variable after a full sweep
+    if (!std::isfinite(R[(size_t)j * ldr + j].real()) || !std::isfinite(R[(size_t)j * ldr + j].imag())) {
+      // scipy raises LinAlgError inside _fgmres and gcrotmk breaks out reporting failure
+      break;
+    }
+    const int ncol = j + 1;
+    // y = lstsq(R[:ncol,:ncol], conj(Q[0,:ncol])) * beta  — triangular solve, zero pivots give 0
+    for (int i = ncol - 1; i >= 0; --i) {
+      zc s = std::conj(Q[i]);
+      for (int c = i + 1; c < ncol; ++c) s -= R[(size_t)i * ldr + c] * y[c];
+      zc d = R[(size_t)i * ldr + i];
+      y[i] = (std::abs(d) > 0.0) ? s / d : zc(0);
+    }
+    for (int i = 0; i < ncol; ++i) y[i] *= beta;
+    // by = B y ; hy = Q (R y)
+    for (int c = 0; c < nc; ++c) {
+      zc s = 0;
+      for (int i = 0; i < ncol; ++i) s += B[(size_t)c * ldb + i] * y[i];
+      by[c] = s;
+    }
+    std::vector<zc> ry(ncol + 1);
+    for (int i = 0; i <= ncol; ++i) {
+      zc s = 0;
+      for (int c = 0; c < ncol; ++c) s += R[(size_t)i * ldr + c] * y[c];
+      ry[i] = s;
+    }
+    for (int i = 0; i <= ncol; ++i) {
+      zc s = 0;
+      for (int c = 0; c <= ncol; ++c) s += Q[(size_t)i * ldq + c] * ry[c];
+      hy[i] = s;
+    }
+    // ux = Z y - U by,  cx = V hy  in ONE pass over [V_0..V_ncol, U_0..U_nc-1] (_gcrotmk.py:430-447)
+    CV_REQUIRE(!free_slots.empty(), "gcrotmk: CU ring exhausted");
+    const int slot_new = free_slots.back();
+    {
+      const int mt = ncol + 1 + nc;
+      std::vector<const void *> src(mt);
+      const int cs = cplx_ ? 2 : 1;
+      std::fill(coef.begin(), coef.end(), 0.0);
+      for (int i = 0; i <= ncol; ++i) {
+        src[i] = V(i);
+        zc cu = (i < ncol) ? y[i] : zc(0);
+        coef[(i * 2 + 0) * cs] = cu.real();
+        coef[(i * 2 + 1) * cs] = hy[i].real();
+        if (cplx_) {
+          coef[(i * 2 + 0) * cs + 1] = cu.imag();
+          coef[(i * 2 + 1) * cs + 1] = hy[i].imag();
+        }
+      }
+      for (int c = 0; c < nc; ++c) {
+        src[ncol + 1 + c] = Us(cu_slots[c]);
+        coef[((ncol + 1 + c) * 2 + 0) * cs] = -by[c].real();
+        if (cplx_) coef[((ncol + 1 + c) * 2 + 0) * cs + 1] = -by[c].imag();
+      }
+      void *outs[2] = {Us(slot_new), Cs(slot_new)};
+      CV_TRY(cv_lincomb_launch(ctx, n, cplx_, cplx_, mt, src.data(), 2, coef.data(), 2, 0, outs, S_CX, st));
+    }
+    CV_TRY(cv_fetch_scalars(ctx, S_CX, 2, st));
+    stats->n_sync++;
+    const double cx_norm = sqrt(mb[S_CX + 1]);
+    const double alpha = 1.0 / cx_norm;
+    if (!std::isfinite(alpha)) continue;  // cannot update, skip (_gcrotmk.py:451-456)
+    // cx, ux *= alpha; gamma = <cx|r>; r -= gamma cx; x += gamma ux; beta = |r|
+    {
+      const int W = cplx_ ? 1 : 2;
+      int grid = cv_grid_for(ctx, (n + W - 1) / W, CV_BLOCK);
+      if (cplx_) {
+        k_gcrot_scale_dot<cplx, 1><<<grid, CV_BLOCK, 0, st>>>(n, ctx->scalars + S_CX + 1, (cplx *)Cs(slot_new),
+                                                             (cplx *)Us(slot_new), (const cplx *)r,
+                                                             ctx->partials, ctx->counters, ctx->scalars + S_GAMMA);
+      } else {
+        k_gcrot_scale_dot<double, 2><<<grid, CV_BLOCK, 0, st>>>(n, ctx->scalars + S_CX + 1, (double *)Cs(slot_new),
+                                                               (double *)Us(slot_new), (const double *)r,
+                                                               ctx->partials, ctx->counters, ctx->scalars + S_GAMMA);
+      }
+      CV_TRY(cv_check_launch(ctx, "gcrot_scale_dot"));
+      CV_TRY(cv_reduce_ranks(ctx, S_GAMMA, NR, st));
+      if (cplx_) {
+        k_gcrot_update<cplx, 1><<<grid, CV_BLOCK, 0, st>>>(n, ctx->scalars + S_GAMMA, (const cplx *)Cs(slot_new),
+                                                          (const cplx *)Us(slot_new), (cplx *)r, (cplx *)x,
+                                                          ctx->partials, ctx->counters, ctx->scalars + S_BETA);
+      } else {
+        k_gcrot_update<double, 2><<<grid, CV_BLOCK, 0, st>>>(n, ctx->scalars + S_GAMMA, (const double *)Cs(slot_new),
+                                                            (const double *)Us(slot_new), (double *)r, (double *)x,
+                                                            ctx->partials, ctx->counters, ctx->scalars + S_BETA);
+      }
+      CV_TRY(cv_check_launch(ctx, "gcrot_update"));
+      CV_TRY(cv_reduce_ranks(ctx, S_BETA, 1, st));
+    }
+    // truncate oldest, append the new pair (_gcrotmk.py:463-499)
+    free_slots.pop_back();
+    while ((int)cu_slots.size() >= k && !cu_slots.empty()) {
+      free_slots.push_back(cu_slots.front());
+      cu_slots.erase(cu_slots.begin());
+    }
+    cu_slots.push_back(slot_new);
+    CV_TRY(cv_fetch_scalars(ctx, S_BETA, 1, st));
+    stats->n_sync++;
+    beta = sqrt(mb[S_BETA]);
+  }
+  stats->n_outer = converged ? j_outer : std::min(j_outer + 1, maxiter);
+  stats->info = converged ? 0 : (j_outer >= maxiter ? maxiter : j_outer + 1);
+  return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// MINRES (real symmetric), minres.py:98-379 with shift = 0, M = I, check = False
+// ------------------------------------------------------------------------------------------
+int minres(cv_ctx *ctx, cv_op *op, int mode, double sigma, const double *b, const double *x0,
+           double *x, double rtol, int maxiter, const Workspace &ws, cv_solve_stats *stats,
+           cudaStream_t st) {
+  const int64_t n = op->n_rows;
+  const double eps = std::numeric_limits<double>::epsilon();
+  double *mb = ctx->mailbox;
+  double *rbuf[3] = {(double *)ws.vec(0), (double *)ws.vec(1), (double *)ws.vec(2)};
+  double *wbuf[2] = {(double *)ws.vec(3), (double *)ws.vec(4)};
+  const int W = ((uintptr_t)x & 15) ? 1 : 2;
+  const int grid = cv_grid_for(ctx, (n + W - 1) / W, CV_BLOCK);
+
+  double *r1 = rbuf[0], *r2 = rbuf[0], *ynew = rbuf[1], *spare = rbuf[2];
+  if (x0) {
+    if (x0 != x) CV_TRY(cv_copy(ctx, n, 0, x0, x, (void *)st));
+    CV_TRY(cv_spmv_dev(ctx, op, 0, mode, sigma, 0.0, x, r1, -1.0, 1.0, b, true, -1, st));
+    stats->n_matvec++;
+  } else {
+    CV_CUDA(cudaMemsetAsync(x, 0, (size_t)n * 8, st));
+    CV_TRY(cv_copy(ctx, n, 0, b, r1, (void *)st));
+  }
+  CV_TRY(cv_nrm2sq_dev(ctx, n, 0, r1, S_W, st));
+  CV_TRY(cv_nrm2sq_dev(ctx, n, 0, b, S_W + 1, st));
+  CV_TRY(cv_fetch_scalars(ctx, S_W, 2, st));
+  stats->n_sync++;
+  double beta1 = mb[S_W];
+  const double bnorm = sqrt(mb[S_W + 1]);
+  stats->b_norm = bnorm;
+  stats->info = 0;
+  if (beta1 == 0.0) return CV_OK;  // x is x0 (minres.py:171-172)
+  if (bnorm == 0.0) {
+    CV_TRY(cv_copy(ctx, n, 0, b, x, (void *)st));
+    return CV_OK;
+  }
+  beta1 = sqrt(beta1);
+  CV_CUDA(cudaMemsetAsync(wbuf[0], 0, (size_t)n * 8, st));
+  CV_CUDA(cudaMemsetAsync(wbuf[1], 0, (size_t)n * 8, st));
+  double *w_older = wbuf[0], *w_old = wbuf[1];  // scipy's (w2, w) before the update
+
+  double oldb = 0, beta = beta1, dbar = 0, epsln = 0, phibar = beta1, rhs1 = beta1, rhs2 = 0;
+  double tnorm2 = 0, gmax = 0, gmin = std::numeric_limits<double>::max(), cs = -1, sn = 0;
+  double qrnorm = beta1, Anorm = 0, Acond = 0, rnorm = 0, ynorm = 0;
+  int istop = 0, itn = 0;
+  (void)rhs1; (void)rhs2; (void)qrnorm; (void)Acond; (void)rnorm;
+
+  while (itn < maxiter) {
+    itn++;
+    const double s = 1.0 / beta;
+    // y = A (s r2) - (beta/oldb) r1 ; alfa = v.y = s <r2|y>       (minres.py:212-222)
+    CV_TRY(cv_spmv_dev(ctx, op, 0, mode, sigma, 0.0, r2, ynew, s, itn >= 2 ? -(beta / oldb) : 0.0,
+                       itn >= 2 ? r1 : nullptr, true, S_W, st));
+    stats->n_matvec++;
+    CV_TRY(cv_fetch_scalars(ctx, S_W, 2, st));
+    stats->n_sync++;
+    const double alfa = s * mb[S_W];
+    // y -= (alfa/beta) r2 ; beta_new^2 = y.y                         (:223-228)
+    if (W == 2)
+      k_axpy_norm<double, 2, true><<<grid, CV_BLOCK, 0, st>>>(n, -(alfa / beta), r2, ynew, ctx->partials,
+                                                             ctx->counters, ctx->scalars + S_NRM);
+    else
+      k_axpy_norm<double, 1, true><<<grid, CV_BLOCK, 0, st>>>(n, -(alfa / beta), r2, ynew, ctx->partials,
+                                                             ctx->counters, ctx->scalars + S_NRM);
+    CV_TRY(cv_check_launch(ctx, "axpy_norm"));
+    CV_TRY(cv_reduce_ranks(ctx, S_NRM, 1, st));
+    CV_TRY(cv_fetch_scalars(ctx, S_NRM, 1, st));
+    stats->n_sync++;
+    // rotate: r1 = r2; r2 = y
+    double *vsrc = r2;  // v = s * vsrc, needed by the direction update below
+    if (itn == 1) {
+      r1 = r2;
+      r2 = ynew;
+      ynew = spare;  // rbuf[2]; rbuf[0] still holds r1
+    } else {
+      double *dead = r1;
+      r1 = r2;
+      r2 = ynew;
+      ynew = dead;
+    }
+    oldb = beta;
+    const double beta_sq = mb[S_NRM];
+    if (beta_sq < 0) {
+      cv_set_error("minres: non-symmetric matrix");
+      return CV_ERR_NUMERIC;
+    }
+    beta = sqrt(beta_sq);
+    tnorm2 += alfa * alfa + oldb * oldb + beta * beta;
+    if (itn == 1 && beta / beta1 <= 10 * eps) istop = -1;
+
+    // plane rotation (:242-257)
+    const double oldeps = epsln;
+    const double delta = cs * dbar + sn * alfa;
+    const double gbar = sn * dbar - cs * alfa;
+    epsln = sn * beta;
+    dbar = -cs * beta;
+    const double root = std::hypot(gbar, dbar);
+    double gamma = std::hypot(gbar, beta);
+    gamma = std::max(gamma, eps);
+    cs = gbar / gamma;
+    sn = beta / gamma;
+    const double phi = cs * phibar;
+    phibar = sn * phibar;
+
+    // w = (v - oldeps w1 - delta w2)/gamma ; x += phi w ; ynorm = |x|   (:259-265, 278)
+    const double denom = 1.0 / gamma;
+    if (W == 2)
+      k_minres_update<2><<<grid, CV_BLOCK, 0, st>>>(n, s, oldeps, delta, denom, phi, vsrc, w_older, w_old, x,
+                                                   ctx->partials, ctx->counters, ctx->scalars + S_W);
+    else
+      k_minres_update<1><<<grid, CV_BLOCK, 0, st>>>(n, s, oldeps, delta, denom, phi, vsrc, w_older, w_old, x,
+                                                   ctx->partials, ctx->counters, ctx->scalars + S_W);
+    CV_TRY(cv_check_launch(ctx, "minres_update"));
+    CV_TRY(cv_reduce_ranks(ctx, S_W, 1, st));
+    std::swap(w_older, w_old);  // new w sits in the former w_older buffer
+    CV_TRY(cv_fetch_scalars(ctx, S_W, 1, st));
+    stats->n_sync++;
+    ynorm = sqrt(mb[S_W]);
+
+    gmax = std::max(gmax, gamma);
+    gmin = std::min(gmin, gamma);
+    const double z = rhs1 / gamma;
+    rhs1 = rhs2 - delta * z;
+    rhs2 = -epsln * z;
+
+    // norms and stopping tests (:270-328)
+    Anorm = sqrt(tnorm2);
+    const double epsx = Anorm * ynorm * eps;
+    qrnorm = phibar;
+    rnorm = qrnorm;
+    const double test1 = (ynorm == 0 || Anorm == 0) ? INFINITY : rnorm / (Anorm * ynorm);
+    const double test2 = (Anorm == 0) ? INFINITY : root / Anorm;
+    Acond = gmax / gmin;
+    if (istop == 0) {
+      const double t1 = 1 + test1, t2 = 1 + test2;
+      if (t2 <= 1) istop = 2;
+      if (t1 <= 1) istop = 1;
+      if (itn >= maxiter) istop = 6;
+      if (Acond >= 0.1 / eps) istop = 4;
+      if (epsx >= beta1) istop = 3;
+      if (test2 <= rtol) istop = 2;
+      if (test1 <= rtol) istop = 1;
+    }
+    stats->resid = rnorm;
+    if (istop != 0) break;
+  }
+  stats->n_outer = itn;
+  stats->info = (istop == 6) ? maxiter : 0;
+  return CV_OK;
+}
+
+}  // namespace
+
+extern "C" size_t cv_solve_workspace_bytes(int64_t n, int cplx_, int solver, int m, int k) {
+  size_t stride = vec_stride_bytes(n, cplx_);
+  if (solver == CV_SOLVER_MINRES) return stride * 5;
+  return stride * (size_t)(1 + (m + k + 1) + 2 * (k + 1));
+}
+
+extern "C" int cv_solve(cv_ctx *ctx, cv_op *op, int cplx_, int solver, int reverse, double sigma_re,
+                        double sigma_im, const void *b, const void *x0, void *x_out, double rtol,
+                        double atol, int maxiter, int m, int k, void *work_dev, size_t work_bytes,
+                        cv_solve_stats *stats, void *stream) {
+  CV_REQUIRE(ctx && op && b && x_out && work_dev && stats, "cv_solve: null argument");
+  CV_REQUIRE(op->n_rows == op->n_cols - op->n_halo, "cv_solve: operator must be square");
+  CV_REQUIRE(maxiter >= 0 && rtol >= 0, "cv_solve: bad tolerances");
+  CV_REQUIRE(((uintptr_t)work_dev & 255) == 0, "cv_solve: workspace must be 256-byte aligned");
+  CV_REQUIRE(((uintptr_t)b & 15) == 0 && ((uintptr_t)x_out & 15) == 0 && (!x0 || ((uintptr_t)x0 & 15) == 0),
+             "cv_solve: vectors must be 16-byte aligned");
+  memset(stats, 0, sizeof(*stats));
+  const int mode = reverse ? CV_SPMV_RSHIFT : CV_SPMV_SHIFT;
+  Workspace ws{static_cast<char *>(work_dev), vec_stride_bytes(op->n_rows, cplx_)};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (solver == CV_SOLVER_GCROTMK) {
+    if (m <= 0) m = 20;
+    if (k <= 0) k = m;
+    CV_REQUIRE(atol >= 0, "cv_solve: gcrotmk called with invalid atol=%g", atol);
+    CV_REQUIRE(m + 2 * k + 2 <= CV_MAX_PTRS, "cv_solve: GCROT(m=%d,k=%d) exceeds %d basis vectors", m, k, CV_MAX_PTRS);
+    CV_REQUIRE(work_bytes >= cv_solve_workspace_bytes(op->n_rows, cplx_, solver, m, k),
+               "cv_solve: workspace too small");
+    return gcrotmk(ctx, op, cplx_, mode, sigma_re, sigma_im, b, x0, x_out, rtol, atol, maxiter, m, k, ws,
+                   stats, st);
+  }
+  if (solver == CV_SOLVER_MINRES) {
+    if (cplx_ || sigma_im != 0.0) {
+      cv_set_error("cv_solve: MINRES is implemented for real symmetric systems only");
+      return CV_ERR_UNSUPPORTED;
+    }
+    CV_REQUIRE(work_bytes >= cv_solve_workspace_bytes(op->n_rows, 0, solver, 0, 0), "cv_solve: workspace too small");
+    return minres(ctx, op, mode, sigma_re, (const double *)b, (const double *)x0, (double *)x_out, rtol,
+                  maxiter, ws, stats, st);
+  }
+  cv_set_error("cv_solve: unknown solver %d", solver);
+  return CV_ERR_ARG;
+}

@@ -1,0 +1,444 @@
+"""CudaVector — the B200 back-end of the ``AbstractVector`` plug-in interface.
+
+Drop-in for the reference's ``NumpyVector`` (numpyVector.py:23-238): same constructor, the same
+attributes (``array``, ``options``, ``size``, ``shape``), the same methods with the same
+argument meaning and the same error behaviour, so ``inexactLanczosDiagonalization`` and
+``feastDiagonalization`` run unchanged.  Every length-N operation executes in libcudavec
+(hand-written sm_100a CUDA reached through ctypes); the vector's storage is a torch tensor used
+only as the device-memory holder.  There is no CPU fallback.
+
+Each method cites the reference lines it replaces.
+"""
+import ctypes as C
+import warnings
+
+import numpy as np
+
+from . import _lib
+from .runtime import Runtime
+from .vector_api import AbstractVector, LINDEP_DEFAULT_VALUE
+
+
+def _is_complex_scalar(s):
+    return isinstance(s, (complex, np.complexfloating))
+
+
+class _NpzCheckpoint:
+    """Stand-in for ``vector.ttns`` so the driver's default checkpoint call
+    ``Ylist[i].ttns.saveToHDF5(filename, additionalInformation=...)`` (inexact_Lanczos.py:384-393)
+    works for plain vectors; h5py is not required — the data goes to ``<filename>.npz``."""
+
+    def __init__(self, vec):
+        self._vec = vec
+
+    def saveToHDF5(self, filename, additionalInformation=None):
+        info = additionalInformation or {}
+        payload = {"array": self._vec.array}
+        for key in ("eigencoefficients", "eigenvalues"):
+            if key in info:
+                payload[key] = np.asarray(info[key])
+        np.savez(str(filename) + ".npz", **payload)
+
+
+class CudaVector(AbstractVector):
+    """Device-resident dense vector (float64 or complex128)."""
+
+    # ------------------------------------------------------------------ construction
+    def __init__(self, array, options=dict()):  # noqa: B006 - shared default as in numpyVector.py:25
+        rt = Runtime.get()
+        t = rt.torch
+        if isinstance(array, t.Tensor):
+            if array.device != rt.device or array.dtype not in (t.float64, t.complex128):
+                raise TypeError("device tensors must be float64/complex128 on the runtime's GPU")
+            self._t = array.contiguous().reshape(-1)
+            self._n_global = int(array.numel()) if rt.world == 1 else None
+        else:
+            a = np.asarray(array)
+            if a.ndim != 1:
+                a = a.reshape(-1)
+            cplx = np.iscomplexobj(a)
+            self._n_global = a.shape[0]
+            if rt.world > 1:  # keep this rank's row block
+                r0, r1 = rt.local_range(a.shape[0])
+                a = a[r0:r1]
+            self._t = rt.upload(a, dtype=np.complex128 if cplx else np.float64)
+        self._finish_init(options)
+
+    def _finish_init(self, options):
+        n = self._n_global
+        self.size = n
+        self.shape = (n,)
+        # numpyVector.py:28-36 — note: fills the CALLER's linearSystemArgs dict in place
+        self.options = dict()
+        opt = options.get("linearSystemArgs", dict())
+        opt["linearSolver"] = opt.get("linearSolver", "minres")
+        opt["linearIter"] = opt.get("linearIter", 1000)
+        opt["linear_tol"] = opt.get("linear_tol", 1e-4)
+        opt["linear_atol"] = opt.get("linear_atol", 1e-4)
+        self.options["linearSystemArgs"] = opt
+
+    @classmethod
+    def _wrap(cls, tensor, options, n_global):
+        """New vector around a device tensor this class just produced (no copy)."""
+        obj = cls.__new__(cls)
+        obj._t = tensor
+        obj._n_global = n_global
+        obj._finish_init(options)
+        return obj
+
+    # ------------------------------------------------------------------ small helpers
+    @property
+    def _cplx(self):
+        return int(self._t.is_complex())
+
+    @property
+    def _nloc(self):
+        return int(self._t.numel())
+
+    @property
+    def _ptr(self):
+        return self._t.data_ptr()
+
+    def _like(self, cplx=None):
+        rt = Runtime.get()
+        return rt.empty(self._nloc, self._cplx if cplx is None else cplx)
+
+    def _as_complex_tensor(self):
+        """complex128 copy of a real vector (rare mixed-type paths)."""
+        rt = Runtime.get()
+        if self._cplx:
+            return self._t
+        out = rt.empty(self._nloc, 1)
+        _lib.check(rt.lib.cv_scal(rt.ctx, self._nloc, 0, 1, 1.0, 0.0, self._ptr, out.data_ptr(), rt.stream))
+        return out
+
+    # ------------------------------------------------------------------ attributes
+    @property
+    def array(self):
+        """Host copy (numpy) of the full vector; gathers the row blocks in sharded mode."""
+        rt = Runtime.get()
+        if rt.world == 1:
+            return self._t.cpu().numpy()
+        import torch.distributed as dist
+        off = rt.offsets_for(self._n_global)
+        sizes = [int(off[p + 1] - off[p]) for p in range(rt.world)]
+        parts = [rt.empty(s, self._cplx) for s in sizes]
+        dist.all_gather(parts, self._t)
+        return rt.torch.cat(parts).cpu().numpy()
+
+    @property
+    def ttns(self):
+        return _NpzCheckpoint(self)
+
+    @property
+    def hasExactAddition(self):  # numpyVector.py:38-46
+        return True
+
+    @property
+    def dtype(self):  # numpyVector.py:48-50
+        return np.dtype(np.complex128 if self._cplx else np.float64)
+
+    @property
+    def maxD(self):  # numpyVector.py:52-55
+        return 0
+
+    def __len__(self):  # numpyVector.py:73-74
+        return self._n_global
+
+    # ------------------------------------------------------------------ scalar algebra
+    def _scaled(self, factor):
+        rt = Runtime.get()
+        fc = _is_complex_scalar(factor) or self._cplx
+        out = self._like(cplx=1 if fc else 0)
+        f = complex(factor)
+        _lib.check(rt.lib.cv_scal(rt.ctx, self._nloc, self._cplx, 1 if fc else 0, f.real, f.imag,
+                                  self._ptr, out.data_ptr(), rt.stream))
+        return CudaVector._wrap(out, self.options, self._n_global)
+
+    def __mul__(self, other):  # numpyVector.py:57-58
+        return self._scaled(other)
+
+    def __rmul__(self, other):  # numpyVector.py:60-61
+        return self._scaled(other)
+
+    def __truediv__(self, other):  # numpyVector.py:63-64
+        return self._scaled(1.0 / other)
+
+    def __imul__(self, other):  # numpyVector.py:66-67
+        raise NotImplementedError
+
+    def __itruediv__(self, other):  # numpyVector.py:69-70
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ BLAS-1
+    def normalize(self):  # numpyVector.py:76-78 (in place, returns self)
+        rt = Runtime.get()
+        _lib.check(rt.lib.cv_normalize(rt.ctx, self._nloc, self._cplx, self._ptr, None, rt.stream))
+        return self
+
+    def norm(self):  # numpyVector.py:80-81
+        rt = Runtime.get()
+        out = C.c_double()
+        _lib.check(rt.lib.cv_nrm2(rt.ctx, self._nloc, self._cplx, self._ptr, C.byref(out), rt.stream))
+        return np.float64(out.value)
+
+    def real(self):  # numpyVector.py:83-84
+        rt = Runtime.get()
+        if not self._cplx:
+            return self.copy()
+        out = self._like(cplx=0)
+        _lib.check(rt.lib.cv_real(rt.ctx, self._nloc, self._ptr, out.data_ptr(), rt.stream))
+        return CudaVector._wrap(out, self.options, self._n_global)
+
+    def conjugate(self):  # numpyVector.py:86-87
+        rt = Runtime.get()
+        if not self._cplx:
+            return self.copy()
+        out = self._like()
+        _lib.check(rt.lib.cv_conj(rt.ctx, self._nloc, self._ptr, out.data_ptr(), rt.stream))
+        return CudaVector._wrap(out, self.options, self._n_global)
+
+    def vdot(self, other, conjugate=True):  # numpyVector.py:89-93
+        rt = Runtime.get()
+        if len(other) != len(self):
+            raise ValueError("vdot: size mismatch")
+        cplx = self._cplx or other._cplx
+        a = self._as_complex_tensor() if cplx else self._t
+        b = other._as_complex_tensor() if cplx else other._t
+        out = _lib.dbl_array(2)
+        _lib.check(rt.lib.cv_dot(rt.ctx, self._nloc, int(cplx), int(bool(conjugate)), a.data_ptr(),
+                                 b.data_ptr(), out, rt.stream))
+        return np.complex128(complex(out[0], out[1])) if cplx else np.float64(out[0])
+
+    def copy(self):  # numpyVector.py:95-96
+        rt = Runtime.get()
+        out = self._like()
+        _lib.check(rt.lib.cv_copy(rt.ctx, self._nloc, self._cplx, self._ptr, out.data_ptr(), rt.stream))
+        return CudaVector._wrap(out, self.options, self._n_global)
+
+    def applyOp(self, other):  # numpyVector.py:98-100: other @ self.array
+        rt = Runtime.get()
+        op = rt.operator_for(other)
+        if op.shape[1] != len(self):
+            raise ValueError(f"operator of shape {op.shape} cannot act on a vector of length {len(self)}")
+        out = self._like()
+        _lib.check(rt.lib.cv_spmv(rt.ctx, op.handle, self._cplx, _lib.CV_SPMV_PLAIN, 0.0, 0.0, self._ptr,
+                                  out.data_ptr(), rt.stream))
+        return CudaVector._wrap(out, self.options, self._n_global)
+
+    def compress(self):  # numpyVector.py:102-103
+        return self
+
+    # ------------------------------------------------------------------ list algebra
+    @staticmethod
+    def _common(vectors):
+        n = vectors[0]._nloc
+        for v in vectors:
+            if v._nloc != n:
+                raise ValueError("vectors of different length")
+        return n
+
+    def linearCombination(vectors, coeffs):  # numpyVector.py:105-119
+        """c1*v1 + ... + cn*vn; result dtype is that of vectors[0] (complex terms on a real
+        accumulator raise, as numpy's in-place add does in the reference)."""
+        assert len(vectors) == len(coeffs)
+        out = CudaVector.linearCombinationBlock(vectors, np.asarray(coeffs).reshape(len(coeffs), 1))
+        return out[0]
+
+    def linearCombinationBlock(vectors, coeffMatrix):
+        """All columns of ``coeffMatrix`` (m x k) at once: Y_k = sum_j C[j,k] v_j, one pass over the
+        inputs per four outputs.  Batched form of the per-column calls of basisTransformation
+        (util_funcs.py:208-231)."""
+        rt = Runtime.get()
+        coeffMatrix = np.asarray(coeffMatrix)
+        m, k = coeffMatrix.shape
+        assert m == len(vectors)
+        n = CudaVector._common(vectors)
+        out_cplx = vectors[0]._cplx
+        c_cplx = np.iscomplexobj(coeffMatrix)
+        if not out_cplx and (c_cplx or any(v._cplx for v in vectors)):
+            raise TypeError("Cannot cast ufunc 'add' output from dtype('complex128') to "
+                            "dtype('float64') with casting rule 'same_kind'")
+        tens = [v._as_complex_tensor() if out_cplx else v._t for v in vectors]
+        coef = np.ascontiguousarray(coeffMatrix, dtype=np.complex128 if c_cplx else np.float64)
+        outs = [rt.empty(n, out_cplx) for _ in range(k)]
+        vp, _k1 = _lib.ptr_array([t.data_ptr() for t in tens])
+        yp, _k2 = _lib.ptr_array([t.data_ptr() for t in outs])
+        # chunks of <= 128 inputs: accumulate by feeding the partial result back as an input
+        if m > 120:
+            raise NotImplementedError("linear combinations of more than 120 vectors")
+        _lib.check(rt.lib.cv_lincomb(rt.ctx, n, int(out_cplx), int(c_cplx), m, vp, k,
+                                     coef.ctypes.data_as(C.POINTER(C.c_double)), yp, rt.stream))
+        opts, ng = vectors[0].options, vectors[0]._n_global
+        return [CudaVector._wrap(t, opts, ng) for t in outs]
+
+    def orthogonalize_against_set(x, qs, lindep=LINDEP_DEFAULT_VALUE):  # numpyVector.py:121-145
+        """Sequential Gram-Schmidt with unconjugated products and division by q.q; returns the
+        normalised vector or None when x.x <= lindep after projection."""
+        rt = Runtime.get()
+        cplx = x._cplx or any(q._cplx for q in qs)
+        xin = x._as_complex_tensor() if cplx else x._t
+        qts = [q._as_complex_tensor() if cplx else q._t for q in qs]
+        out = rt.empty(x._nloc, cplx)
+        status = C.c_int()
+        inner = _lib.dbl_array(2)
+        qp, _keep = _lib.ptr_array([t.data_ptr() for t in qts]) if qts else (None, None)
+        _lib.check(rt.lib.cv_gs_against_set(rt.ctx, x._nloc, int(cplx), xin.data_ptr(), len(qts), qp,
+                                            float(lindep), out.data_ptr(), C.byref(status), inner,
+                                            rt.stream))
+        if status.value != 0:
+            return None
+        return CudaVector._wrap(out, x.options, x._n_global)
+
+    @staticmethod
+    def solve(H, b, sigma, x0=None, opType="her", reverseGF=False):  # numpyVector.py:147-178
+        """Approximate solution of (sigma*I - H) x = b (reverseGF: (H - sigma*I) x = b) with the
+        device GCROT(20,20) or MINRES; raises like the reference when the solver does not converge."""
+        rt = Runtime.get()
+        op = rt.operator_for(H)
+        n = op.shape[0]
+        if len(b) != n:
+            raise ValueError("solve: shape mismatch between operator and right-hand side")
+        cplx = bool(np.issubdtype(np.result_type(sigma, op.dtype, b.dtype), np.complexfloating))
+        options = b.options["linearSystemArgs"]
+        tol, atol, maxiter = options["linear_tol"], options["linear_atol"], options["linearIter"]
+        name = options["linearSolver"]
+        if name == "gcrotmk":
+            solver = _lib.CV_SOLVER_GCROTMK
+        elif name == "minres":
+            solver = _lib.CV_SOLVER_MINRES
+        elif name == "pardiso":
+            raise NotImplementedError('linearSolver "pardiso" (dense host spsolve, numpyVector.py:164-171, '
+                                      "used only to compare with Fortran FEAST) has no device counterpart")
+        else:
+            raise Exception("Got linear solver other than gcrotmk, minres and pardiso!")
+        bt = b._as_complex_tensor() if cplx else b._t
+        x0t = None
+        if x0 is not None:
+            x0t = x0._as_complex_tensor() if cplx else x0._t
+        m_in, k_in = int(options.get("gcrot_m", 20)), int(options.get("gcrot_k", 0))
+        nloc = b._nloc
+        wbytes = rt.lib.cv_solve_workspace_bytes(nloc, int(cplx), solver, m_in, k_in if k_in else m_in)
+        work = rt.workspace(wbytes)
+        out = rt.empty(nloc, cplx)
+        stats = _lib.SolveStats()
+        s = complex(sigma)
+        _lib.check(rt.lib.cv_solve(rt.ctx, op.handle, int(cplx), solver, int(bool(reverseGF)), s.real, s.imag,
+                                   bt.data_ptr(), None if x0t is None else x0t.data_ptr(), out.data_ptr(),
+                                   float(tol), float(atol), int(maxiter), m_in, k_in, work.data_ptr(),
+                                   work.numel(), C.byref(stats), rt.stream))
+        rt.stats["solves"] += 1
+        rt.stats["matvecs"] += stats.n_matvec
+        rt.stats["syncs"] += stats.n_sync
+        rt.stats["outer"] += stats.n_outer
+        rt.last_solve = stats
+        if stats.info != 0:  # numpyVector.py:175-177 (turns the warning into an exception)
+            warnings.simplefilter('error', UserWarning)
+            warnings.warn("Warning:: Iterative solver is not converged ")
+        return CudaVector._wrap(out, b.options, b._n_global)
+
+    # ------------------------------------------------------------------ small matrices
+    @staticmethod
+    def _tsdot(vs, ws, conj=True):
+        """host ndarray C[i,k] = <v_i|w_k> for lists of CudaVectors."""
+        rt = Runtime.get()
+        cplx = any(v._cplx for v in vs) or any(w._cplx for w in ws)
+        vt = [v._as_complex_tensor() if cplx else v._t for v in vs]
+        wt = [w._as_complex_tensor() if cplx else w._t for w in ws]
+        m, b = len(vt), len(wt)
+        out = _lib.dbl_array(m * b * (2 if cplx else 1))
+        res = np.empty((m, b), dtype=np.complex128 if cplx else np.float64)
+        for i0 in range(0, m, 120):
+            chunk = vt[i0:i0 + 120]
+            vp, _k1 = _lib.ptr_array([t.data_ptr() for t in chunk])
+            wp, _k2 = _lib.ptr_array([t.data_ptr() for t in wt])
+            _lib.check(rt.lib.cv_tsdot(rt.ctx, vt[0].numel(), int(cplx), int(bool(conj)), len(chunk), vp, b,
+                                       wp, out, rt.stream))
+            flat = np.ctypeslib.as_array(out)[:len(chunk) * b * (2 if cplx else 1)]
+            if cplx:
+                flat = flat.view(np.complex128)
+            res[i0:i0 + len(chunk), :] = flat.reshape(len(chunk), b)
+        return res
+
+    def matrixRepresentation(operator, vectors):  # numpyVector.py:180-190
+        """M[i,j] = <v_i | H v_j>, lower triangle computed and mirrored by conjugation."""
+        rt = Runtime.get()
+        m = len(vectors)
+        dtype = vectors[0].dtype
+        qtAq = np.zeros((m, m), dtype=dtype)
+        for j0 in range(0, m, 4):
+            kets = [vectors[j].applyOp(operator) for j in range(j0, min(j0 + 4, m))]
+            block = CudaVector._tsdot(vectors, kets)
+            for jj in range(len(kets)):
+                j = j0 + jj
+                for i in range(j, m):
+                    qtAq[i, j] = block[i, jj]
+                    qtAq[j, i] = qtAq[i, j].conj()
+        return qtAq
+
+    def overlapMatrix(vectors):  # numpyVector.py:192-203
+        """S[i,j] = <v_i|v_j>, upper triangle computed and mirrored by conjugation."""
+        m = len(vectors)
+        dtype = vectors[0].dtype
+        Smat = np.zeros((m, m), dtype=dtype)
+        block = CudaVector._tsdot(vectors, vectors)
+        for i in range(m):
+            for j in range(i, m):
+                Smat[i, j] = block[i, j]
+                Smat[j, i] = Smat[i, j].conj()
+        return Smat
+
+    @staticmethod
+    def _new_columns(operator, vectors, want_s, want_h):
+        rt = Runtime.get()
+        m = len(vectors)
+        cplx = any(v._cplx for v in vectors)
+        vt = [v._as_complex_tensor() if cplx else v._t for v in vectors]
+        n = vt[0].numel()
+        nr = 2 if cplx else 1
+        vp, _keep = _lib.ptr_array([t.data_ptr() for t in vt])
+        s_col = _lib.dbl_array(m * nr) if want_s else None
+        h_col = _lib.dbl_array(m * nr) if want_h else None
+        op_handle, ket = None, None
+        if want_h:
+            op_handle = rt.operator_for(operator).handle
+            ket = rt.tmp_vector("ket", n, cplx).data_ptr()
+        _lib.check(rt.lib.cv_extend_columns(rt.ctx, op_handle, n, int(cplx), m, vp, ket, s_col, h_col, rt.stream))
+
+        def to_np(buf):
+            a = np.ctypeslib.as_array(buf).copy()
+            return a.view(np.complex128) if cplx else a
+        return (to_np(s_col) if want_s else None), (to_np(h_col) if want_h else None)
+
+    def extendMatrixRepresentation(operator, vectors, opMat):  # numpyVector.py:205-221
+        m = len(vectors)
+        dtype = vectors[0].dtype
+        elems = np.empty((1, m), dtype=dtype)
+        _, h = CudaVector._new_columns(operator, vectors, False, True)
+        elems[0, :] = h
+        opMat = np.append(opMat, elems[:, :-1].conj(), axis=0)
+        opMat = np.append(opMat, elems.T, axis=1)
+        return opMat
+
+    def extendOverlapMatrix(vectors, overlap):  # numpyVector.py:223-238
+        m = len(vectors)
+        dtype = vectors[0].dtype
+        elems = np.empty((1, m), dtype=dtype)
+        s, _ = CudaVector._new_columns(None, vectors, True, False)
+        elems[0, :] = s
+        overlap = np.append(overlap, elems[:, :-1].conj(), axis=0)
+        overlap = np.append(overlap, elems.T, axis=1)
+        return overlap
+
+    def extendBoth(operator, vectors, overlap, opMat):
+        """Fused form of the two extend* calls the Lanczos driver makes back to back
+        (inexact_Lanczos.py:349-350): one SpMV and ONE pass over the Krylov list."""
+        m = len(vectors)
+        dtype = vectors[0].dtype
+        s, h = CudaVector._new_columns(operator, vectors, True, True)
+        es = np.empty((1, m), dtype=dtype)
+        eh = np.empty((1, m), dtype=dtype)
+        es[0, :], eh[0, :] = s, h
+        overlap = np.append(np.append(overlap, es[:, :-1].conj(), axis=0), es.T, axis=1)
+        opMat = np.append(np.append(opMat, eh[:, :-1].conj(), axis=0), eh.T, axis=1)
+        return overlap, opMat

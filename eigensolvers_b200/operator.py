@@ -1,0 +1,175 @@
+"""Device-resident Hamiltonian: CSR uploaded once, optionally re-laid out as sliced ELL
+(32-row slices, column-major inside a slice) by a device kernel.  Replaces the host objects the
+reference applies with ``H @ x`` (numpyVector.py:100,152,154): scipy.sparse matrices and dense
+ndarrays (stored as CSR with every entry).
+
+Layout in HBM (single GPU, N rows, nnz non-zeros, P padded non-zeros):
+    indptr  int64[N+1]   indices int32[nnz]   data float64[nnz]          (CSR)
+    slice_ptr int64[N/32+1]   sell_col int32[P]   sell_val float64[P]    (SELL-32)
+In row-sharded mode each rank holds rows [r_p, r_{p+1}) with columns renumbered to
+[0, n_loc) (owned) ++ [n_loc, n_loc + n_halo) (halo, sorted by global column = grouped by owner).
+"""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+
+
+class DeviceOperator:
+    """Handle to a cv_op plus the torch tensors that own its device arrays."""
+
+    dtype = np.dtype(np.float64)
+
+    def __init__(self, runtime, shape):
+        self.rt = runtime
+        self.shape = tuple(int(s) for s in shape)  # GLOBAL shape
+        self.handle = C.c_void_p()
+        self._keep = []  # tensors owning device memory
+        self.nnz = 0
+        self.padded_nnz = 0
+        self.n_local = self.shape[0]
+        self.n_halo = 0
+        self.format = "csr"
+        self.halo_cols = None
+        self.send_idx = None
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.rt.lib.cv_op_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------------------------------
+    @staticmethod
+    def _as_csr(H):
+        if sp.issparse(H):
+            A = H.tocsr()
+        elif isinstance(H, np.ndarray):
+            if H.ndim != 2:
+                raise ValueError("operator must be a 2-D matrix")
+            A = sp.csr_matrix(H)
+        else:
+            raise TypeError(
+                f"CudaVector cannot apply an operator of type {type(H).__name__}: pass a "
+                "scipy.sparse matrix, a dense ndarray or a DeviceOperator (an opaque "
+                "LinearOperator has no device representation)")
+        if np.iscomplexobj(A):
+            raise NotImplementedError("complex-valued Hamiltonians are not supported yet (real "
+                                      "symmetric H with real or complex vectors is)")
+        if A.shape[1] >= 2 ** 31:
+            raise ValueError("column indices must fit int32")
+        if not A.has_sorted_indices:
+            A = A.sorted_indices()
+        return A
+
+    @classmethod
+    def from_host(cls, H, runtime=None, fmt="auto"):
+        """Upload (this rank's row block of) ``H``.  ``fmt``: 'auto' | 'csr' | 'sell'."""
+        from .runtime import Runtime
+        rt = runtime or Runtime.get()
+        A = cls._as_csr(H)
+        op = cls(rt, A.shape)
+        indptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(A.indices, dtype=np.int32)
+        data = np.ascontiguousarray(A.data, dtype=np.float64)
+        if rt.world > 1:
+            indptr, indices, data = op._shard(indptr, indices, data)
+        n_rows = len(indptr) - 1
+        n_cols = op.shape[1] if rt.world == 1 else op.n_local + op.n_halo
+        op.nnz = int(indptr[-1])
+        t = rt.torch
+        d_indptr = rt.upload(indptr)
+        d_indices = rt.upload(indices) if op.nnz else t.empty(0, dtype=t.int32, device=rt.device)
+        d_data = rt.upload(data) if op.nnz else t.empty(0, dtype=t.float64, device=rt.device)
+        op._keep += [d_indptr, d_indices, d_data]
+        _lib.check(rt.lib.cv_op_create_csr(rt.ctx, n_rows, n_cols, op.nnz, d_indptr.data_ptr(),
+                                           d_indices.data_ptr(), d_data.data_ptr(),
+                                           C.byref(op.handle)))
+        if rt.world > 1:
+            op._register_halo()
+        if fmt in ("auto", "sell") and n_rows > 0 and op.nnz > 0:
+            op._build_sell(force=(fmt == "sell"))
+        return op
+
+    # ---------------------------------------------------------------------------------------
+    def _build_sell(self, force=False):
+        rt, t = self.rt, self.rt.torch
+        n_rows = self.n_local
+        n_slices = (n_rows + 31) // 32
+        widths = t.empty(n_slices, dtype=t.int32, device=rt.device)
+        _lib.check(rt.lib.cv_op_sell_widths(rt.ctx, self.handle, widths.data_ptr(), rt.stream))
+        w = widths.cpu().numpy().astype(np.int64)
+        slice_ptr = np.zeros(n_slices + 1, dtype=np.int64)
+        np.cumsum(w * 32, out=slice_ptr[1:])
+        padded = int(slice_ptr[-1])
+        # SELL pays off for short, regular rows; keep CSR when padding would cost > 25 % traffic
+        # or the matrix is tiny (dense test matrices)
+        if not force and (padded > 1.25 * self.nnz or n_rows < 1024):
+            return
+        d_ptr = rt.upload(slice_ptr)
+        d_col = t.empty(padded, dtype=t.int32, device=rt.device)
+        d_val = t.empty(padded, dtype=t.float64, device=rt.device)
+        _lib.check(rt.lib.cv_op_attach_sell(rt.ctx, self.handle, d_ptr.data_ptr(), padded,
+                                            d_col.data_ptr(), d_val.data_ptr(), rt.stream))
+        self._keep += [d_ptr, d_col, d_val]
+        self.padded_nnz = padded
+        self.format = "sell"
+
+    def set_format(self, fmt):
+        code = {"csr": _lib.CV_FMT_CSR, "sell": _lib.CV_FMT_SELL}[fmt]
+        if fmt == "sell" and self.padded_nnz == 0:
+            self._build_sell(force=True)
+        _lib.check(self.rt.lib.cv_op_set_format(self.handle, code))
+        self.format = fmt
+
+    # -- row-sharded mode --------------------------------------------------------------------
+    def _shard(self, indptr, indices, data):
+        """Slice this rank's row block and renumber columns (cv_halo_build, comm.cu)."""
+        rt = self.rt
+        off = rt.offsets_for(self.shape[0])
+        r0, r1 = int(off[rt.rank]), int(off[rt.rank + 1])
+        nloc = r1 - r0
+        n_halo = C.c_int64()
+        _lib.check(rt.lib.cv_halo_count(indptr.ctypes.data, indices.ctypes.data, r0, r1,
+                                        C.byref(n_halo)))
+        nh = n_halo.value
+        nnz_loc = int(indptr[r1] - indptr[r0])
+        halo_cols = np.empty(nh, dtype=np.int32)
+        halo_owner = np.empty(nh, dtype=np.int32)
+        loc_indptr = np.empty(nloc + 1, dtype=np.int64)
+        loc_indices = np.empty(nnz_loc, dtype=np.int32)
+        _lib.check(rt.lib.cv_halo_build(indptr.ctypes.data, indices.ctypes.data, r0, r1,
+                                        off.ctypes.data, rt.world, nh, halo_cols.ctypes.data,
+                                        halo_owner.ctypes.data, loc_indptr.ctypes.data,
+                                        loc_indices.ctypes.data))
+        self.n_local, self.n_halo = nloc, nh
+        self.halo_cols, self.halo_owner = halo_cols, halo_owner
+        self.row0 = r0
+        return loc_indptr, loc_indices, np.ascontiguousarray(data[indptr[r0]:indptr[r1]])
+
+    def _register_halo(self):
+        """Exchange the halo request lists once (host, torch.distributed) and register the plan."""
+        from .partition import exchange_plan
+        rt, t = self.rt, self.rt.torch
+        send_idx, send_off, recv_off = exchange_plan(self.halo_cols, self.halo_owner,
+                                                     rt.offsets_for(self.shape[0]), rt.rank, rt.world)
+        self.send_idx = send_idx
+        d_send = rt.upload(send_idx) if len(send_idx) else t.empty(0, dtype=t.int32, device=rt.device)
+        cap = max(len(send_idx), self.n_halo, 1)
+        sendbuf = t.empty(2 * cap, dtype=t.float64, device=rt.device)
+        halobuf = t.zeros(2 * cap, dtype=t.float64, device=rt.device)
+        self._keep += [d_send, sendbuf, halobuf]
+        self._send_off = np.ascontiguousarray(send_off, dtype=np.int64)
+        self._recv_off = np.ascontiguousarray(recv_off, dtype=np.int64)
+        _lib.check(rt.lib.cv_op_set_halo(rt.ctx, self.handle, self.n_halo, d_send.data_ptr(),
+                                         self._send_off.ctypes.data, self._recv_off.ctypes.data,
+                                         sendbuf.data_ptr(), halobuf.data_ptr()))
+
+    # -- roofline bookkeeping ----------------------------------------------------
+    def algorithmic_bytes(self, cplx=False):
+        """Compulsory traffic of one shifted SpMV: 12*nnz + 20*N (fp64), 12*nnz + 36*N (complex)."""
+        return 12 * self.nnz + (36 if cplx else 20) * self.n_local

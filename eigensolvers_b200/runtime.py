@@ -1,0 +1,144 @@
+"""Process-wide device runtime: the cv_ctx handle, its scratch memory (a torch tensor — torch is
+used only as the device-memory holder and for streams / torch.distributed plumbing), the
+operator cache and the solver workspaces.
+
+One process drives one GPU.  In row-sharded mode (``init_distributed``) every rank runs the same
+host code on its row block; all scalar results are summed over ranks inside libcudavec, so every
+rank takes identical control-flow decisions.
+"""
+import ctypes as C
+import os
+import weakref
+
+import numpy as np
+
+from . import _lib
+
+
+class Runtime:
+    _instance = None
+
+    def __init__(self):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("eigensolvers_b200 needs a CUDA device (B200, sm_100a); "
+                               "there is no CPU fallback")
+        self.torch = torch
+        self.lib = _lib.load()
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.device_index = local_rank if local_rank < torch.cuda.device_count() else 0
+        torch.cuda.set_device(self.device_index)
+        self.device = torch.device("cuda", self.device_index)
+        nbytes = self.lib.cv_ctx_scratch_bytes()
+        self.scratch = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        handle = C.c_void_p()
+        _lib.check(self.lib.cv_ctx_create(self.device_index, self.scratch.data_ptr(), nbytes,
+                                          C.byref(handle)))
+        self.ctx = handle
+        self.rank, self.world = 0, 1
+        self.offsets = None  # row partition in distributed mode (world+1 int64)
+        self._workspaces = {}
+        self._op_cache = {}
+        self._tmp = {}
+        self.stats = {"solves": 0, "matvecs": 0, "syncs": 0, "outer": 0}
+
+    # -- singletons ---------------------------------------------------------------------------
+    @classmethod
+    def get(cls):
+        if cls._instance is None:
+            cls._instance = Runtime()
+        return cls._instance
+
+    @classmethod
+    def reset(cls):
+        inst = cls._instance
+        if inst is not None:
+            inst._op_cache.clear()
+            inst._workspaces.clear()
+            inst.lib.cv_ctx_destroy(inst.ctx)
+        cls._instance = None
+
+    # -- helpers --------------------------------------------------------------------------------
+    @property
+    def stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def launch_count(self):
+        n = C.c_uint64()
+        _lib.check(self.lib.cv_ctx_launch_count(self.ctx, C.byref(n)))
+        return n.value
+
+    def empty(self, n, cplx):
+        t = self.torch
+        return t.empty(int(n), dtype=t.complex128 if cplx else t.float64, device=self.device)
+
+    def upload(self, host_array, dtype=None):
+        """Host ndarray -> device tensor through pinned staging (counted by bench.py's e2e)."""
+        t = self.torch
+        a = np.ascontiguousarray(host_array, dtype=dtype)
+        src = t.from_numpy(a)
+        if a.nbytes >= (1 << 20):
+            src = src.pin_memory()
+        return src.to(self.device, non_blocking=False)
+
+    def workspace(self, nbytes):
+        """Solver workspace, grown on demand and reused across solves."""
+        t = self.torch
+        cur = self._workspaces.get("solve")
+        if cur is None or cur.numel() < nbytes:
+            self._workspaces.pop("solve", None)
+            cur = t.empty(int(nbytes), dtype=t.uint8, device=self.device)
+            self._workspaces["solve"] = cur
+        return cur
+
+    def tmp_vector(self, key, n, cplx):
+        cur = self._tmp.get((key, cplx))
+        if cur is None or cur.numel() != n:
+            cur = self.empty(n, cplx)
+            self._tmp[(key, cplx)] = cur
+        return cur
+
+    # -- row-sharded mode ----------------------------------------------------------------------
+    def init_distributed(self):
+        """Join the NCCL communicator of an already initialised torch.distributed group."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return self
+        if self.world > 1:
+            return self
+        rank, world = dist.get_rank(), dist.get_world_size()
+        uid = (C.c_char * 128)()
+        if rank == 0:
+            _lib.check(self.lib.cv_comm_unique_id(uid))
+        box = [bytes(uid)]
+        dist.broadcast_object_list(box, src=0)
+        uid = (C.c_char * 128).from_buffer_copy(box[0])
+        _lib.check(self.lib.cv_comm_init(self.ctx, uid, rank, world))
+        self.rank, self.world = rank, world
+        return self
+
+    def offsets_for(self, n):
+        from .partition import row_offsets
+        return row_offsets(n, self.world)
+
+    def local_range(self, n):
+        off = self.offsets_for(n)
+        return int(off[self.rank]), int(off[self.rank + 1])
+
+    # -- operator cache -------------------------------------------------------------------------
+    def operator_for(self, H):
+        """Device operator for a host matrix, cached by object identity."""
+        from .operator import DeviceOperator
+        if isinstance(H, DeviceOperator):
+            return H
+        key = id(H)
+        hit = self._op_cache.get(key)
+        if hit is not None and hit[0]() is H:
+            return hit[1]
+        op = DeviceOperator.from_host(H, runtime=self)
+        try:
+            ref = weakref.ref(H, lambda _r, k=key, cache=self._op_cache: cache.pop(k, None))
+        except TypeError:  # object without weakref support: keep it alive with the cache entry
+            ref = (lambda obj: (lambda: obj))(H)
+        self._op_cache[key] = (ref, op)
+        return op

@@ -1,0 +1,192 @@
+/*
+ * cudavec.h — C ABI of libcudavec.so, the B200 (sm_100a) device back-end behind
+ * `CudaVector`, the drop-in replacement for the reference's NumpyVector hot path.
+ *
+ * The reference (chem-rano/eigensolvers) has no FFI: its plugin boundary is the Python
+ * ABC `AbstractVector` (abstractVector.py:15-169).  Every entry point below is the
+ * device-side body of one call site of that ABC as implemented by numpyVector.py; the
+ * Python class eigensolvers_b200/cudaVector.py binds them with ctypes (INTEGRATION.md
+ * shows the binding a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain C types only; every function returns CV_OK (0) or a CV_ERR_* code and
+ *     cv_last_error() then holds a message.  No exceptions cross the ABI.
+ *   - all `*_dev` / vector pointers are DEVICE pointers (torch.Tensor.data_ptr()); the
+ *     library never allocates vector memory, the host language owns lifetimes.
+ *   - `cplx` flags: 0 = float64, 1 = complex128 stored interleaved (re,im) like numpy.
+ *   - `n` counts ELEMENTS (complex elements when cplx=1).
+ *   - scalar results are returned to HOST pointers; such calls synchronise `stream`.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - distributed mode (cv_comm_*): vectors are the local row shard; every scalar result
+ *     is summed over ranks before it is returned, so all ranks see identical scalars.
+ */
+#ifndef CUDAVEC_H
+#define CUDAVEC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CV_ABI_VERSION 1
+
+#define CV_OK 0
+#define CV_ERR_CUDA 1        /* a CUDA runtime call failed                              */
+#define CV_ERR_ARG 2         /* invalid argument                                        */
+#define CV_ERR_UNSUPPORTED 3 /* combination not implemented                             */
+#define CV_ERR_NUMERIC 4     /* non-finite value met inside a solver (scipy LinAlgError) */
+#define CV_ERR_COMM 5        /* NCCL failure                                            */
+
+/* spmv modes */
+#define CV_SPMV_PLAIN 0   /* y = H x            numpyVector.py:98-100 (applyOp)          */
+#define CV_SPMV_SHIFT 1   /* y = sigma x - H x  numpyVector.py:152 (solve, Green's fn)   */
+#define CV_SPMV_RSHIFT 2  /* y = H x - sigma x  numpyVector.py:154 (reverseGF)           */
+
+/* operator storage formats */
+#define CV_FMT_CSR 0
+#define CV_FMT_SELL 1     /* sliced ELL, slice height 32 */
+
+/* linear solvers (numpyVector.py:160-163) */
+#define CV_SOLVER_GCROTMK 0
+#define CV_SOLVER_MINRES 1
+
+typedef struct cv_ctx cv_ctx; /* per-device context: reduction scratch, pinned mailbox, counters */
+typedef struct cv_op cv_op;   /* device-resident Hamiltonian                                     */
+
+int cv_abi_version(void);
+const char *cv_last_error(void);
+
+/* ---- context ------------------------------------------------------------------------ */
+/* Bytes of device scratch the caller must hand to cv_ctx_create (partial sums, scalars). */
+size_t cv_ctx_scratch_bytes(void);
+int cv_ctx_create(int device, void *scratch_dev, size_t scratch_bytes, cv_ctx **out);
+int cv_ctx_destroy(cv_ctx *ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int cv_ctx_launch_count(cv_ctx *ctx, uint64_t *count);
+int cv_ctx_sm_count(cv_ctx *ctx, int *sms);
+
+/* ---- distributed mode (row-sharded H) -------------------------------------- */
+/* 128-byte NCCL unique id, created on rank 0 and broadcast by the host language. */
+int cv_comm_unique_id(void *id128);
+int cv_comm_init(cv_ctx *ctx, const void *id128, int rank, int world);
+int cv_comm_finalize(cv_ctx *ctx);
+/* Sum `count` doubles in place over all ranks (device buffer); no-op for world 1. */
+int cv_comm_allreduce(cv_ctx *ctx, double *buf_dev, int count, void *stream);
+
+/* Host-side integer routines (bit-exact vs. the scipy slicing oracle).
+ * cv_partition_rows: offsets[p] = floor(p*n/P), p = 0..P.
+ * cv_halo_count / cv_halo_build: for the row block [row0,row1) of a CSR matrix with GLOBAL
+ * column indices, the sorted unique off-block columns (the halo), their owner rank, and the
+ * local CSR whose columns are renumbered to [0,nloc) (owned) ++ [nloc, nloc+nhalo) (halo).   */
+int cv_partition_rows(int64_t n, int world, int64_t *offsets /* world+1 */);
+int cv_halo_count(const int64_t *indptr, const int32_t *indices, int64_t row0, int64_t row1,
+                  int64_t *n_halo);
+int cv_halo_build(const int64_t *indptr, const int32_t *indices, int64_t row0, int64_t row1,
+                  const int64_t *offsets, int world, int64_t n_halo,
+                  int32_t *halo_cols /* n_halo, sorted global ids */,
+                  int32_t *halo_owner /* n_halo */,
+                  int64_t *local_indptr /* row1-row0+1 */,
+                  int32_t *local_indices /* nnz of the block */);
+/* Register the exchange plan of this rank's operator: for each peer the owned local rows to
+ * send (device int32 list, concatenated, send_off[world+1]) and the halo slots received
+ * (contiguous per owner, recv_off[world+1]).                                               */
+int cv_op_set_halo(cv_ctx *ctx, cv_op *op, int64_t n_halo, const int32_t *send_idx_dev,
+                   const int64_t *send_off /* host, world+1 */,
+                   const int64_t *recv_off /* host, world+1 */, void *sendbuf_dev,
+                   void *halobuf_dev /* each 16*max(n_send,n_halo) bytes */);
+
+/* ---- operator ------------------------------------------------------------------------- */
+/* Borrow a CSR matrix already resident on the device (int64 indptr, int32 column indices,
+ * float64 values; numpyVector.py:100 takes scipy.sparse / ndarray H).                      */
+int cv_op_create_csr(cv_ctx *ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                     const int64_t *indptr_dev, const int32_t *indices_dev,
+                     const double *data_dev, cv_op **out);
+int cv_op_destroy(cv_op *op);
+/* sliced-ELL: (1) per-slice widths (max row length of each 32-row slice) into widths_dev,
+ * (2) caller scans them into slice_ptr (int64, n_slices+1, element offsets) and supplies
+ * storage, (3) the fill kernel lays the matrix out column-major inside each slice.          */
+int cv_op_sell_widths(cv_ctx *ctx, cv_op *op, int32_t *widths_dev, void *stream);
+int cv_op_attach_sell(cv_ctx *ctx, cv_op *op, const int64_t *slice_ptr_dev, int64_t padded_nnz,
+                      int32_t *sell_col_dev, double *sell_val_dev, void *stream);
+int cv_op_set_format(cv_op *op, int fmt);
+int cv_op_info(cv_op *op, int64_t *n_rows, int64_t *nnz, int64_t *padded_nnz, int *fmt);
+
+/* y = H x | sigma x - H x | H x - sigma x  (numpyVector.py:100,152,154).  H real; x,y real
+ * or complex (FEAST: complex sigma and x, feast.py:90).                                     */
+int cv_spmv(cv_ctx *ctx, cv_op *op, int cplx, int mode, double sigma_re, double sigma_im,
+            const void *x, void *y, void *stream);
+/* Same pass, plus the partial dots the Krylov solvers need: out[0..1] = <x|y> (conjugated),
+ * out[2] = <y|y>.  This is the "fused shifted SpMV" of the headline metric.                 */
+int cv_spmv_dots(cv_ctx *ctx, cv_op *op, int cplx, int mode, double sigma_re, double sigma_im,
+                 const void *x, void *y, double *out3_host, void *stream);
+
+/* ---- BLAS-1 family (numpyVector.py:57-96) -------------------------------------------- */
+int cv_copy(cv_ctx *ctx, int64_t n, int cplx, const void *x, void *y, void *stream);
+/* y = a x.  x real & a real -> y real; x real & a complex (y_cplx=1) -> y complex; x complex
+ * -> y complex.  __mul__/__rmul__/__truediv__ (numpyVector.py:57-64).                        */
+int cv_scal(cv_ctx *ctx, int64_t n, int x_cplx, int y_cplx, double a_re, double a_im,
+            const void *x, void *y, void *stream);
+int cv_real(cv_ctx *ctx, int64_t n, const void *x_cplx, double *y, void *stream); /* :83-84 */
+int cv_conj(cv_ctx *ctx, int64_t n, const void *x_cplx, void *y_cplx, void *stream); /* :86-87 */
+/* out[0..1] = sum conj?(x) * y  (np.vdot / np.dot, numpyVector.py:89-93).                   */
+int cv_dot(cv_ctx *ctx, int64_t n, int cplx, int conj, const void *x, const void *y,
+           double *out2_host, void *stream);
+int cv_nrm2(cv_ctx *ctx, int64_t n, int cplx, const void *x, double *out_host, void *stream);
+/* in place x /= ||x||  (numpyVector.py:76-78); returns the norm that was divided out.       */
+int cv_normalize(cv_ctx *ctx, int64_t n, int cplx, void *x, double *norm_host, void *stream);
+
+/* ---- linear combinations / tall-skinny products ---------------------------------------- */
+/* Y_k = sum_j coef[j*ncol + k] V_j, k < ncol: one pass over the m inputs for all outputs
+ * (linearCombination numpyVector.py:105-119 as driven by basisTransformation
+ * util_funcs.py:208-231).  coef is a HOST array, row-major m x ncol, interleaved re/im when
+ * c_cplx.  Outputs must not alias inputs.                                                  */
+int cv_lincomb(cv_ctx *ctx, int64_t n, int v_cplx, int c_cplx, int m, const void *const *v_ptrs,
+               int ncol, const double *coef_host, void *const *y_ptrs, void *stream);
+/* C[i*b + k] = sum conj?(V_i) W_k : overlapMatrix / matrixRepresentation / pick
+ * (numpyVector.py:180-203, util_funcs.py:321-322).  out is HOST, re/im interleaved if cplx. */
+int cv_tsdot(cv_ctx *ctx, int64_t n, int cplx, int conj, int m, const void *const *v_ptrs,
+             int b, const void *const *w_ptrs, double *out_host, void *stream);
+
+/* Sequential modified Gram-Schmidt of x against qs with UNCONJUGATED products and division by
+ * q.q, then the LINDEP test x.x > lindep and normalisation (numpyVector.py:121-145).
+ * status: 0 = ok (x_out normalised), 1 = linearly dependent (reference returns None).
+ * innerprod_host[0..1] = x.x after projection.                                             */
+int cv_gs_against_set(cv_ctx *ctx, int64_t n, int cplx, const void *x_in, int m,
+                      const void *const *q_ptrs, double lindep, void *x_out, int *status,
+                      double *innerprod_host, void *stream);
+
+/* New column of the overlap and operator matrices when v_last joins the list
+ * (extendOverlapMatrix :223-238, extendMatrixRepresentation :205-221):
+ * s_col[i] = <v_i|v_last>, h_col[i] = <v_i|H v_last>, i < m (v_ptrs includes v_last as its
+ * last entry).  ket_tmp is caller scratch of n elements.  One SpMV + one pass over V.       */
+int cv_extend_columns(cv_ctx *ctx, cv_op *op, int64_t n, int cplx, int m,
+                      const void *const *v_ptrs, void *ket_tmp, double *s_col_host,
+                      double *h_col_host, void *stream);
+
+/* ---- approximate shifted solve (numpyVector.py:147-178) ------------------------------- */
+typedef struct cv_solve_stats {
+  int info;          /* scipy's second return value: 0 converged, >0 not converged          */
+  int n_matvec;      /* operator applications                                               */
+  int n_outer;       /* GCROT outer iterations / MINRES iterations                          */
+  int n_sync;        /* host synchronisations                                               */
+  double resid;      /* last residual norm estimate                                         */
+  double b_norm;
+} cv_solve_stats;
+
+size_t cv_solve_workspace_bytes(int64_t n, int cplx, int solver, int m, int k);
+/* Solve (sigma I - H) x = b (reverse: (H - sigma I) x = b) with the device restatement of
+ * scipy.sparse.linalg.gcrotmk (GCROT(m,k), _gcrotmk.py:187-506) or minres (minres.py:13-379).
+ * x0 may be NULL.  maxiter counts GCROT outer iterations / MINRES iterations exactly as the
+ * reference passes `linearIter`.  Non-convergence is reported through stats->info; the host
+ * layer raises like numpyVector.py:175-177.                                                */
+int cv_solve(cv_ctx *ctx, cv_op *op, int cplx, int solver, int reverse, double sigma_re,
+             double sigma_im, const void *b, const void *x0, void *x_out, double rtol,
+             double atol, int maxiter, int m, int k, void *work_dev, size_t work_bytes,
+             cv_solve_stats *stats, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUDAVEC_H */
