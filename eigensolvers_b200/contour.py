@@ -1,0 +1,140 @@
+"""FEAST contour-integral subspace iteration (Polizzi, PRB 79, 115112 (2009)) — host control
+flow over the vector plug-in, with the call signature, status dictionary, return values and
+quirks of the reference's ``feastDiagonalization`` (feast.py:126-244):
+
+  per FEAST iteration, for each retained quadrature node k and each of the m0 subspace vectors:
+  solve (z_k I - A) Qe = Y, accumulate Re[-1/2 w_k r (f cos(theta) + i sin(theta)) Qe] into Q;
+  then Rayleigh-Ritz on Q in the Loewdin basis and Y <- Q uSH; stop when the relative change of
+  the eigenvalues inside [eMin, eMax] drops below eConv.
+
+`positiveHalf=True` keeps the Legendre nodes with g_k > 0 only, i.e. nc/2 nodes in the upper
+right quadrant of the contour — kept as is, it is the parity target.
+
+All (node, vector) solves of one iteration are independent.  With `distribute="nodes"` and a
+torch.distributed group, node k is owned by rank k % world: the owner solves, the others skip,
+and the m0 accumulated vectors are summed over ranks once per iteration (H replicated).
+"""
+import math
+import time
+import warnings
+
+import numpy as np
+
+from .hostmath import (basisTransformation, diagonalizeHamiltonian, eigenvalueResidual,
+                       lowdinOrthoMatrix, quadraturePointsWeights)
+from .runlog import FeastRunLog
+
+
+def _getStatus(status, guess):
+    """feast.py:16-43."""
+    out = {"flagAddition": guess[0].hasExactAddition, "outerIter": 0, "quadrature": 0,
+           "isConverged": False, "phase": 1, "residual": None,
+           "startTime": time.time(), "runTime": 0.0}
+    if status is not None:
+        out.update(status)
+    return out
+
+
+def calculateQuadrature(Amat, guess_b, z, radius, angle, weight, contourEllipseFactor):
+    """Contribution of one contour point to the filtered vector (feast.py:45-103).
+
+    Exact-addition vectors need one complex solve: Re[mult * (zI-A)^-1 b]; others need the
+    solves at z and conj(z) and a fitted sum (Polizzi eq. 12)."""
+    b = guess_b
+    typeClass = b.__class__
+    if abs(z.imag) < 1e-15:  # contour point on the real axis
+        opType = "her"
+        z = z.real
+    else:
+        opType = "gen"
+    c, s = contourEllipseFactor * math.cos(angle), math.sin(angle)
+    if b.hasExactAddition:
+        Qe = typeClass.solve(Amat, b, z, opType=opType)
+        mult = -0.50 * weight * radius * (c + s * 1j)
+        return typeClass.real(mult * Qe)
+    mult = -0.25 * weight * radius
+    part1 = typeClass.solve(Amat, b, z, opType=opType)
+    part2 = typeClass.solve(Amat, b, z.conj(), opType=opType)
+    return typeClass.linearCombination([part1, part2], [mult * (c + s * 1j), mult * (c - s * 1j)])
+
+
+def updateQ(Q, im0, Qquad_k, k):
+    """Q[im0] (+)= Qquad_k (feast.py:105-121)."""
+    typeClass = Qquad_k.__class__
+    if k == 0:
+        Q[im0] = Qquad_k
+    else:
+        Q[im0] = typeClass.linearCombination([Q[im0], Qquad_k], [1.0, 1.0])
+    return Q
+
+
+def feastDiagonalization(A, Y, nc, quad, eMin, eMax, eConv, maxit, contourEllipseFactor=1.0,
+                         writeOut=True, eShift=0.0, convertUnit="au", outFileName=None,
+                         summaryFileName=None, distribute=None):
+    """Eigenpairs of the Hermitian A inside [eMin, eMax] from the m0 = len(Y) guess vectors.
+    Returns (ev, Y, status) with ALL m0 (or fewer, after a rank drop) Ritz pairs."""
+    typeClass = type(Y[0])
+    N_SUBSPACE = len(Y)
+    assert eMax > eMin
+    eRadius = (eMax - eMin) * 0.5
+    gk, wk = quadraturePointsWeights(nc, quad, positiveHalf=True)
+
+    status = _getStatus(None, Y)  # the reference ignores a user status here (feast.py:178)
+    printObj = FeastRunLog(Y, nc, quad, eMin, eMax, eConv, maxit, writeOut, eShift, convertUnit,
+                           status, outFileName, summaryFileName)
+    printObj.fileHeader()
+    rank, world = 0, 1
+    if distribute == "nodes":
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(), dist.get_world_size()
+
+    ev = None
+    ref_ev = None
+    for it in range(maxit):
+        status["outerIter"] = it
+        Q = [None] * N_SUBSPACE
+        first = True
+        for k in range(len(gk)):
+            status["quadrature"] = k
+            if world > 1 and k % world != rank:
+                continue
+            theta = -(np.pi * 0.5) * (gk[k] - 1)  # Polizzi (13)
+            z = (eMin + eMax) * 0.5 + eRadius * (math.cos(theta) + contourEllipseFactor * 1.0j * math.sin(theta))
+            for im0 in range(N_SUBSPACE):
+                Qk = calculateQuadrature(A, Y[im0], z, eRadius, theta, wk[k], contourEllipseFactor)
+                Q = updateQ(Q, im0, Qk, 0 if first else 1)
+            first = False
+        if world > 1:
+            Q = typeClass.sumOverRanks(Q, like=Y)
+
+        Smat = typeClass.overlapMatrix(Q)
+        Hmat = typeClass.matrixRepresentation(A, Q)
+        printObj.writeFile("iteration", status)
+        printObj.writeFile("overlap", Smat)
+        status, uS = lowdinOrthoMatrix(Smat, status)
+        ev, uv = diagonalizeHamiltonian(uS, Hmat, printObj)
+        uSH = uS @ uv
+        Y = basisTransformation(Q, uSH)
+        del Q
+
+        if it != 0:
+            if len(ref_ev) > len(ev):
+                nearest = np.argmin(np.abs(ref_ev[:, None] - ev[None, :]), axis=0)
+                ref_ev = ref_ev[nearest]
+            elif len(ref_ev) < len(ev):
+                raise RuntimeError(f"{ref_ev=} but {ev=}. Enlarged space?")
+            residual = eigenvalueResidual(ev, ref_ev, [eMin, eMax])
+            status["runTime"] = time.time() - status["startTime"]
+            status["residual"] = residual
+            printObj.writeFile("summary", ev, residual, status)
+            if residual < eConv:
+                break
+        if N_SUBSPACE != len(Y):
+            warnings.warn(f"Alert! Got {N_SUBSPACE - len(Y)} dependent vectors")
+        N_SUBSPACE = len(Y)
+        ref_ev = ev
+
+    printObj.writeFile("results", ev)
+    printObj.fileFooter()
+    return ev, Y, status

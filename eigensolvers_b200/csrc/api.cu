@@ -44,6 +44,7 @@ extern "C" int cv_ctx_create(int device, void *scratch_dev, size_t scratch_bytes
   CV_CUDA(cudaMemset(scratch_dev, 0, CV_N_COUNTERS * sizeof(unsigned) + CV_N_SCALARS * sizeof(double)));
   CV_CUDA(cudaMallocHost(&c->mailbox, CV_N_SCALARS * sizeof(double)));
   c->launches = 0;
+  c->prof = nullptr;
   c->comm = nullptr;
   c->rank = 0;
   c->world = 1;
@@ -55,6 +56,14 @@ extern "C" int cv_ctx_destroy(cv_ctx *ctx) {
   if (!ctx) return CV_OK;
   if (ctx->comm) cv_comm_finalize(ctx);
   if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
+  if (ctx->prof) {
+    if (ctx->prof->created)
+      for (int i = 0; i < CV_PROF_POOL; ++i) {
+        cudaEventDestroy(ctx->prof->start[i]);
+        cudaEventDestroy(ctx->prof->stop[i]);
+      }
+    delete ctx->prof;
+  }
   delete ctx;
   return CV_OK;
 }
@@ -68,6 +77,65 @@ extern "C" int cv_ctx_launch_count(cv_ctx *ctx, uint64_t *count) {
 extern "C" int cv_ctx_sm_count(cv_ctx *ctx, int *sms) {
   CV_REQUIRE(ctx && sms, "cv_ctx_sm_count: null argument");
   *sms = ctx->sms;
+  return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel-class timing (CUDA events on the launching stream)
+// ------------------------------------------------------------------------------------------
+static void prof_drain(cv_prof_state *p) {
+  for (int i = 0; i < p->used; ++i) {
+    cudaEventSynchronize(p->stop[i]);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p->start[i], p->stop[i]) == cudaSuccess) {
+      p->ms[p->cls[i]] += ms;
+      p->count[p->cls[i]]++;
+    }
+  }
+  p->used = 0;
+}
+
+cv_prof_scope::cv_prof_scope(cv_ctx *c, int cls, cudaStream_t s) : ctx(c), st(s), slot(-1) {
+  cv_prof_state *p = c->prof;
+  if (!p || !p->enabled) return;
+  if (p->used == CV_PROF_POOL) prof_drain(p);
+  slot = p->used++;
+  p->cls[slot] = cls;
+  cudaEventRecord(p->start[slot], st);
+}
+
+cv_prof_scope::~cv_prof_scope() {
+  if (slot >= 0) cudaEventRecord(ctx->prof->stop[slot], st);
+}
+
+extern "C" int cv_ctx_profile(cv_ctx *ctx, int enable) {
+  CV_REQUIRE(ctx, "cv_ctx_profile: null context");
+  if (!ctx->prof) ctx->prof = new cv_prof_state();
+  cv_prof_state *p = ctx->prof;
+  if (enable && !p->created) {
+    for (int i = 0; i < CV_PROF_POOL; ++i) {
+      CV_CUDA(cudaEventCreate(&p->start[i]));
+      CV_CUDA(cudaEventCreate(&p->stop[i]));
+    }
+    p->created = true;
+  }
+  if (!enable && p->enabled) prof_drain(p);
+  p->enabled = enable != 0;
+  return CV_OK;
+}
+
+extern "C" int cv_ctx_profile_read(cv_ctx *ctx, double *ms4, uint64_t *count4) {
+  CV_REQUIRE(ctx && ms4 && count4, "cv_ctx_profile_read: null argument");
+  for (int i = 0; i < CV_PROF_CLASSES; ++i) ms4[i] = 0.0, count4[i] = 0;
+  cv_prof_state *p = ctx->prof;
+  if (!p) return CV_OK;
+  prof_drain(p);
+  for (int i = 0; i < CV_PROF_CLASSES; ++i) {
+    ms4[i] = p->ms[i];
+    count4[i] = p->count[i];
+    p->ms[i] = 0.0;
+    p->count[i] = 0;
+  }
   return CV_OK;
 }
 
@@ -257,6 +325,10 @@ static int launch_lincomb_nc(cv_ctx *ctx, const LcParams &p, int ncol, int grid,
     case 2: LC(2); break;
     case 3: LC(3); break;
     case 4: LC(4); break;
+    case 5: LC(5); break;
+    case 6: LC(6); break;
+    case 7: LC(7); break;
+    case 8: LC(8); break;
     default:
       cv_set_error("lincomb: internal chunk of %d columns", ncol);
       return CV_ERR_ARG;
@@ -319,7 +391,7 @@ extern "C" int cv_lincomb(cv_ctx *ctx, int64_t n, int v_cplx, int c_cplx, int m,
   CV_REQUIRE(ncol >= 1 && n >= 0, "cv_lincomb: bad shape");
   if (n == 0) return CV_OK;
   const int cs = c_cplx ? 2 : 1;
-  int chunk = 4;
+  int chunk = c_cplx || v_cplx ? 4 : 8;  // outputs per pass over the inputs
   while (chunk > 1 && m * chunk * cs > CV_MAX_COEF) chunk >>= 1;
   CV_REQUIRE(m * chunk * cs <= CV_MAX_COEF, "cv_lincomb: too many coefficients");
   for (int c0 = 0; c0 < ncol; c0 += chunk) {
@@ -334,7 +406,7 @@ extern "C" int cv_lincomb(cv_ctx *ctx, int64_t n, int v_cplx, int c_cplx, int m,
 // tall-skinny product into ctx->scalars[slot ...): layout ((i*b + k)*NRED + c)
 // ------------------------------------------------------------------------------------------
 template <typename T, int W, bool CONJ>
-static int launch_tsdot(cv_ctx *ctx, const TsParams &p, int slot, cudaStream_t st) {
+static int launch_tsdot(cv_ctx *ctx, const TsParams &p, int slot, const double *gate, cudaStream_t st) {
   constexpr int NR = Num<T>::NRED;
   const int64_t np = (p.n + W - 1) / W;
   double *out = ctx->scalars + slot;
@@ -351,24 +423,28 @@ static int launch_tsdot(cv_ctx *ctx, const TsParams &p, int slot, cudaStream_t s
     if (gx > cap) gx = cap;
   }
   dim3 grid(gx, ny);
+  {
+    cv_prof_scope prof(ctx, 1, st);
 #define TSD(MI_, B_) \
-  k_tsdot<T, W, CONJ, MI_, B_><<<grid, CV_BLOCK, 0, st>>>(p, ctx->partials, ctx->counters, out)
-  switch (p.b) {
-    case 1: TSD(16, 1); break;
-    case 2: TSD(8, 2); break;
-    case 3: TSD(4, 3); break;
-    case 4: TSD(4, 4); break;
-    default:
-      cv_set_error("tsdot: b=%d outside 1..4", p.b);
-      return CV_ERR_ARG;
-  }
+  k_tsdot<T, W, CONJ, MI_, B_><<<grid, CV_BLOCK, 0, st>>>(p, gate, ctx->partials, ctx->counters, out)
+    switch (p.b) {
+      case 1: TSD(16, 1); break;
+      case 2: TSD(8, 2); break;
+      case 3: TSD(4, 3); break;
+      case 4: TSD(4, 4); break;
+      default:
+        cv_set_error("tsdot: b=%d outside 1..4", p.b);
+        return CV_ERR_ARG;
+    }
 #undef TSD
+  }
   CV_TRY(cv_check_launch(ctx, "tsdot"));
   return cv_reduce_ranks(ctx, slot, p.m * p.b * NR, st);
 }
 
 int cv_tsdot_dev(cv_ctx *ctx, int64_t n, int cplx_, int conj, int m, const void *const *v, int b,
-                 const void *const *w, int slot, cudaStream_t st) {
+                 const void *const *w, int slot, cudaStream_t st, int gate_slot) {
+  const double *gate = gate_slot >= 0 ? ctx->scalars + gate_slot : nullptr;
   CV_REQUIRE(m >= 1 && m <= CV_MAX_PTRS && b >= 1 && b <= 4, "tsdot: m=%d b=%d out of range", m, b);
   CV_REQUIRE(m * b * (cplx_ ? 2 : 1) <= CV_MAX_RED, "tsdot: too many values");
   CV_REQUIRE(CV_MAX_PTRS / 4 <= (int)CV_N_COUNTERS, "tsdot: counters");
@@ -385,9 +461,9 @@ int cv_tsdot_dev(cv_ctx *ctx, int64_t n, int cplx_, int conj, int m, const void 
     p.w[k] = w[k];
     if ((uintptr_t)w[k] & 15) W = 1;
   }
-  if (cplx_) return conj ? launch_tsdot<cplx, 1, true>(ctx, p, slot, st) : launch_tsdot<cplx, 1, false>(ctx, p, slot, st);
+  if (cplx_) return conj ? launch_tsdot<cplx, 1, true>(ctx, p, slot, gate, st) : launch_tsdot<cplx, 1, false>(ctx, p, slot, gate, st);
   // real: conjugation is the identity
-  return W == 2 ? launch_tsdot<double, 2, false>(ctx, p, slot, st) : launch_tsdot<double, 1, false>(ctx, p, slot, st);
+  return W == 2 ? launch_tsdot<double, 2, false>(ctx, p, slot, gate, st) : launch_tsdot<double, 1, false>(ctx, p, slot, gate, st);
 }
 
 extern "C" int cv_tsdot(cv_ctx *ctx, int64_t n, int cplx_, int conj, int m, const void *const *v_ptrs,
@@ -411,7 +487,8 @@ extern "C" int cv_tsdot(cv_ctx *ctx, int64_t n, int cplx_, int conj, int m, cons
 
 // w -= V h  (h = ctx->scalars[h_slot ..)), optional |w|^2 into norm_slot
 int cv_tsupdate_dev(cv_ctx *ctx, int64_t n, int cplx_, int m, const void *const *v, int h_slot,
-                    void *w, int norm_slot, cudaStream_t st) {
+                    void *w, int norm_slot, cudaStream_t st, int gate_slot) {
+  const double *gate = gate_slot >= 0 ? ctx->scalars + gate_slot : nullptr;
   CV_REQUIRE(m >= 1 && m <= CV_MAX_PTRS, "tsupdate: m=%d out of range", m);
   TsParams p;
   p.m = m;
@@ -427,16 +504,19 @@ int cv_tsupdate_dev(cv_ctx *ctx, int64_t n, int cplx_, int m, const void *const 
   const double *h = ctx->scalars + h_slot;
   double *on = norm_slot >= 0 ? ctx->scalars + norm_slot : nullptr;
   size_t sh = sizeof(double) * m * (cplx_ ? 2 : 1);
+  {
+    cv_prof_scope prof(ctx, 2, st);
 #define TSU(T, WW, NM) \
-  k_tsupdate<T, WW, NM><<<grid, CV_BLOCK, sh, st>>>(p, h, (T *)w, ctx->partials, ctx->counters, on)
-  if (cplx_) {
-    if (on) TSU(cplx, 1, true); else TSU(cplx, 1, false);
-  } else if (W == 2) {
-    if (on) TSU(double, 2, true); else TSU(double, 2, false);
-  } else {
-    if (on) TSU(double, 1, true); else TSU(double, 1, false);
-  }
+  k_tsupdate<T, WW, NM><<<grid, CV_BLOCK, sh, st>>>(p, h, gate, (T *)w, ctx->partials, ctx->counters, on)
+    if (cplx_) {
+      if (on) TSU(cplx, 1, true); else TSU(cplx, 1, false);
+    } else if (W == 2) {
+      if (on) TSU(double, 2, true); else TSU(double, 2, false);
+    } else {
+      if (on) TSU(double, 1, true); else TSU(double, 1, false);
+    }
 #undef TSU
+  }
   CV_TRY(cv_check_launch(ctx, "tsupdate"));
   if (on) CV_TRY(cv_reduce_ranks(ctx, norm_slot, 1, st));
   return CV_OK;
@@ -583,6 +663,7 @@ extern "C" int cv_op_info(cv_op *op, int64_t *n_rows, int64_t *nnz, int64_t *pad
 // ------------------------------------------------------------------------------------------
 template <typename T, bool HALO, bool EPI, bool DOTS>
 static int launch_spmv_fmt(cv_ctx *ctx, cv_op *op, const SpmvArgs<T> &a, cudaStream_t st) {
+  cv_prof_scope prof(ctx, 0, st);
   if (op->fmt == CV_FMT_SELL) {
     int grid = cv_grid_for(ctx, op->n_slices, CV_WARPS);
     k_spmv_sell<T, HALO, EPI, DOTS><<<grid, CV_BLOCK, 0, st>>>(a);
@@ -642,7 +723,7 @@ static int launch_spmv_t(cv_ctx *ctx, cv_op *op, int mode, T sigma, const T *x, 
   }
 #undef GO
   CV_TRY(rc);
-  if (dots) CV_TRY(cv_reduce_ranks(ctx, dots_slot, Num<T>::NRED + 1, st));
+  if (dots) CV_TRY(cv_reduce_ranks(ctx, dots_slot, 3, st));
   return CV_OK;
 }
 
@@ -675,15 +756,7 @@ extern "C" int cv_spmv_dots(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double 
                      CV_S_TMP, st));
   if (out3_host) {
     CV_TRY(cv_fetch_scalars(ctx, CV_S_TMP, 3, st));
-    if (cplx_) {
-      out3_host[0] = ctx->mailbox[CV_S_TMP];
-      out3_host[1] = ctx->mailbox[CV_S_TMP + 1];
-      out3_host[2] = ctx->mailbox[CV_S_TMP + 2];
-    } else {
-      out3_host[0] = ctx->mailbox[CV_S_TMP];
-      out3_host[1] = 0.0;
-      out3_host[2] = ctx->mailbox[CV_S_TMP + 1];
-    }
+    for (int i = 0; i < 3; ++i) out3_host[i] = ctx->mailbox[CV_S_TMP + i];
   }
   return CV_OK;
 }

@@ -59,6 +59,19 @@ constexpr size_t CV_N_PARTIALS = (size_t)1 << 21;        // doubles: per-CTA par
 
 struct cv_comm_state;  // NCCL state, comm.cu
 
+// optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline)
+constexpr int CV_PROF_CLASSES = 4;  // 0 spmv, 1 tsdot, 2 tsupdate, 3 other vector kernels
+constexpr int CV_PROF_POOL = 2048;  // event pairs kept in flight before they are drained
+struct cv_prof_state {
+  bool enabled = false;
+  cudaEvent_t start[CV_PROF_POOL], stop[CV_PROF_POOL];
+  int cls[CV_PROF_POOL];
+  int used = 0;
+  bool created = false;
+  double ms[CV_PROF_CLASSES] = {0, 0, 0, 0};
+  uint64_t count[CV_PROF_CLASSES] = {0, 0, 0, 0};
+};
+
 struct cv_ctx {
   int device;
   int sms;
@@ -69,6 +82,16 @@ struct cv_ctx {
   uint64_t launches;
   cv_comm_state *comm;  // null when world == 1
   int rank, world;
+  cv_prof_state *prof;
+};
+
+// RAII bracket: records an event pair around the launches issued inside its scope
+struct cv_prof_scope {
+  cv_ctx *ctx;
+  cudaStream_t st;
+  int slot;
+  cv_prof_scope(cv_ctx *c, int cls, cudaStream_t s);
+  ~cv_prof_scope();
 };
 
 inline int cv_grid_for(const cv_ctx *ctx, int64_t work_items, int items_per_cta) {

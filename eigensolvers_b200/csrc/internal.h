@@ -37,9 +37,9 @@ int cv_lincomb_launch(cv_ctx *ctx, int64_t n, int v_cplx, int c_cplx, int m, con
                       int ncol, const double *coef, int ldc, int col0, void *const *y, int norm_slot,
                       cudaStream_t st);
 int cv_tsdot_dev(cv_ctx *ctx, int64_t n, int cplx_, int conj, int m, const void *const *v, int b,
-                 const void *const *w, int slot, cudaStream_t st);
+                 const void *const *w, int slot, cudaStream_t st, int gate_slot = -1);
 int cv_tsupdate_dev(cv_ctx *ctx, int64_t n, int cplx_, int m, const void *const *v, int h_slot,
-                    void *w, int norm_slot, cudaStream_t st);
+                    void *w, int norm_slot, cudaStream_t st, int gate_slot = -1);
 int cv_spmv_dev(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim, const void *x,
                 void *y, double alpha, double beta1, const void *u1, bool epi, int dots_slot,
                 cudaStream_t st);

@@ -44,7 +44,7 @@ struct SpmvArgs {
   // reductions
   double *partials;
   unsigned *counter;
-  double *out;  // [0..NRED) = <x|y>, [NRED] = <y|y>
+  double *out;  // {Re<x|y>, Im<x|y>, <y|y>}
 };
 
 template <typename T, bool HALO>
@@ -80,11 +80,10 @@ __device__ __forceinline__ void spmv_finish_row(const SpmvArgs<T> &a, int64_t ro
 template <typename T, bool DOTS>
 __device__ __forceinline__ void spmv_reduce(const SpmvArgs<T> &a, T d_xy, double d_yy) {
   if (DOTS) {
-    constexpr int NR = Num<T>::NRED;
-    double vals[NR + 1];
+    // uniform layout for real and complex data: out = {Re<x|y>, Im<x|y>, <y|y>}
+    double vals[3] = {0.0, 0.0, d_yy};
     Num<T>::to_red(d_xy, vals);
-    vals[NR] = d_yy;
-    grid_reduce<NR + 1>(vals, a.partials, a.counter, a.out, gridDim.x, blockIdx.x);
+    grid_reduce<3>(vals, a.partials, a.counter, a.out, gridDim.x, blockIdx.x);
   }
 }
 

@@ -248,12 +248,20 @@ struct TsParams {
 
 template <typename T, int W, bool CONJ, int MI, int B>
 __global__ void __launch_bounds__(CV_BLOCK)
-    k_tsdot(const __grid_constant__ TsParams p, double *partials, unsigned *counters,
-            double *out /* [m*B*NRED] as ((i*B + k)*NRED + c) */) {
+    k_tsdot(const __grid_constant__ TsParams p, const double *__restrict__ gate, double *partials,
+            unsigned *counters, double *out /* [m*B*NRED] as ((i*B + k)*NRED + c) */) {
   constexpr int NR = Num<T>::NRED;
   const int64_t n = p.n;
   const int i0 = blockIdx.y * MI;
   const int mi = min(MI, p.m - i0);
+  // Selective re-orthogonalisation (Daniel-Gragg-Kaufman-Stewart): gate = {|w|^2 before,
+  // |w'|^2 after the first projection}.  If the first pass removed less than half of the
+  // squared norm there was no cancellation and the second pass is skipped: result = 0.
+  if (gate && __ldcg(gate + 1) >= 0.5 * __ldcg(gate)) {
+    if (blockIdx.x == 0)
+      for (int v = threadIdx.x; v < mi * B * NR; v += blockDim.x) out[(size_t)i0 * B * NR + v] = 0.0;
+    return;
+  }
   T acc[MI][B];
 #pragma unroll
   for (int i = 0; i < MI; ++i)
@@ -316,10 +324,15 @@ __global__ void __launch_bounds__(CV_BLOCK)
 // ------------------------------------------------------------------------------------------
 template <typename T, int W, bool NORM>
 __global__ void __launch_bounds__(CV_BLOCK)
-    k_tsupdate(const __grid_constant__ TsParams p, const double *__restrict__ h, T *__restrict__ wvec,
-               double *partials, unsigned *counter, double *out_norm) {
+    k_tsupdate(const __grid_constant__ TsParams p, const double *__restrict__ h,
+               const double *__restrict__ gate, T *__restrict__ wvec, double *partials,
+               unsigned *counter, double *out_norm) {
   extern __shared__ double s_h[];  // m * NRED doubles
   constexpr int NR = Num<T>::NRED;
+  if (gate && __ldcg(gate + 1) >= 0.5 * __ldcg(gate)) {  // second pass skipped (see k_tsdot)
+    if (NORM && blockIdx.x == 0 && threadIdx.x == 0) out_norm[0] = __ldcg(gate + 1);
+    return;
+  }
   for (int j = threadIdx.x; j < p.m * NR; j += blockDim.x) s_h[j] = __ldcg(h + j);
   __syncthreads();
   const int64_t n = p.n;

@@ -25,7 +25,8 @@ typedef std::complex<double> zc;
 
 namespace {
 
-constexpr int S_W = CV_S_SOLVER;         // <x|y> (NRED) , <y|y>
+constexpr int S_W = CV_S_SOLVER;         // {Re<x|y>, Im<x|y>, <y|y>} of the fused SpMV
+constexpr int S_GATE = CV_S_SOLVER + 2;  // {|w|^2, |w'|^2}: gate of the second projection pass
 constexpr int S_NRM = CV_S_SOLVER + 4;   // squared norm of the orthogonalised vector
 constexpr int S_CX = CV_S_SOLVER + 5;    // |ux|^2, |cx|^2
 constexpr int S_GAMMA = CV_S_SOLVER + 8; // <cx|r> (NRED)
@@ -115,9 +116,9 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
       // recompute the residual to avoid rounding error (_gcrotmk.py:384-387)
       CV_TRY(cv_spmv_dev(ctx, op, cplx_, mode, sre, sim, x, r, -1.0, 1.0, b, true, S_W, st));
       stats->n_matvec++;
-      CV_TRY(cv_fetch_scalars(ctx, S_W, NR + 1, st));
+      CV_TRY(cv_fetch_scalars(ctx, S_W, 3, st));
       stats->n_sync++;
-      beta = sqrt(mb[S_W + NR]);
+      beta = sqrt(mb[S_W + 2]);
     }
     stats->resid = beta;
     if (beta <= beta_tol) {
@@ -145,14 +146,16 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
       basis[nc + j] = V(j);
       const int nb = nc + j + 1;
       const void *wp[1] = {w};
+      // classical Gram-Schmidt against [C, V]; the second pass runs only if the first one
+      // cancelled more than half of |w|^2 (decided on the device, no host round trip)
       CV_TRY(cv_tsdot_dev(ctx, n, cplx_, 1, nb, basis.data(), 1, wp, S_H1, st));
-      CV_TRY(cv_tsupdate_dev(ctx, n, cplx_, nb, basis.data(), S_H1, w, -1, st));
-      CV_TRY(cv_tsdot_dev(ctx, n, cplx_, 1, nb, basis.data(), 1, wp, S_H2, st));
-      CV_TRY(cv_tsupdate_dev(ctx, n, cplx_, nb, basis.data(), S_H2, w, S_NRM, st));
+      CV_TRY(cv_tsupdate_dev(ctx, n, cplx_, nb, basis.data(), S_H1, w, S_GATE + 1, st));
+      CV_TRY(cv_tsdot_dev(ctx, n, cplx_, 1, nb, basis.data(), 1, wp, S_H2, st, S_GATE));
+      CV_TRY(cv_tsupdate_dev(ctx, n, cplx_, nb, basis.data(), S_H2, w, S_NRM, st, S_GATE));
       CV_TRY(cv_scale_dev(ctx, n, cplx_, w, nullptr, S_NRM, 1, st));
       CV_TRY(cv_fetch_scalars(ctx, S_W, S_H2 + nb * NR - S_W, st));
       stats->n_sync++;
-      const double w_norm = sqrt(mb[S_W + NR]);
+      const double w_norm = sqrt(mb[S_W + 2]);
       for (int i = 0; i < nb; ++i) {
         zc h = cplx_ ? zc(mb[S_H1 + 2 * i] + mb[S_H2 + 2 * i], mb[S_H1 + 2 * i + 1] + mb[S_H2 + 2 * i + 1])
                      : zc(mb[S_H1 + i] + mb[S_H2 + i], 0.0);
@@ -364,7 +367,7 @@ int minres(cv_ctx *ctx, cv_op *op, int mode, double sigma, const double *b, cons
     CV_TRY(cv_spmv_dev(ctx, op, 0, mode, sigma, 0.0, r2, ynew, s, itn >= 2 ? -(beta / oldb) : 0.0,
                        itn >= 2 ? r1 : nullptr, true, S_W, st));
     stats->n_matvec++;
-    CV_TRY(cv_fetch_scalars(ctx, S_W, 2, st));
+    CV_TRY(cv_fetch_scalars(ctx, S_W, 1, st));
     stats->n_sync++;
     const double alfa = s * mb[S_W];
     // y -= (alfa/beta) r2 ; beta_new^2 = y.y                         (:223-228)

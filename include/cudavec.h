@@ -66,6 +66,12 @@ int cv_ctx_destroy(cv_ctx *ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int cv_ctx_launch_count(cv_ctx *ctx, uint64_t *count);
 int cv_ctx_sm_count(cv_ctx *ctx, int *sms);
+/* Optional kernel timing with CUDA events on the launching stream, per kernel class
+ * (0 = fused SpMV, 1 = tall-skinny dot, 2 = tall-skinny update, 3 = other vector kernels).
+ * cv_ctx_profile_read synchronises, returns accumulated milliseconds and launch counts
+ * (arrays of 4) and resets the accumulators.                                               */
+int cv_ctx_profile(cv_ctx *ctx, int enable);
+int cv_ctx_profile_read(cv_ctx *ctx, double *ms4, uint64_t *count4);
 
 /* ---- distributed mode (row-sharded H) -------------------------------------- */
 /* 128-byte NCCL unique id, created on rank 0 and broadcast by the host language. */

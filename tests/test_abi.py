@@ -1,0 +1,55 @@
+"""The C-ABI library loads on a CPU-only machine and exports exactly what include/cudavec.h
+declares; the ctypes table (eigensolvers_b200/_lib.py) lists the same symbols.  No compute calls."""
+import ctypes
+import os
+import re
+
+import numpy as np
+
+from eigensolvers_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "cudavec.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cv_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_ctypes_table_agree():
+    assert header_symbols() == sorted(_lib.SIGNATURES)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    for name in header_symbols():
+        assert hasattr(lib, name), name
+    assert lib.cv_abi_version() == 1
+    assert lib.cv_ctx_scratch_bytes() > 0
+    assert isinstance(lib.cv_last_error(), bytes)
+
+
+def test_host_side_partition_routine_runs_without_gpu():
+    lib = _lib.load()
+    off = np.empty(4, dtype=np.int64)
+    _lib.check(lib.cv_partition_rows(10, 3, off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))))
+    assert list(off) == [0, 3, 6, 10]
+    assert lib.cv_partition_rows(-1, 3, off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))) != 0
+    assert b"cv_partition_rows" in lib.cv_last_error()
+
+
+def test_product_has_no_cpu_fallback():
+    """The product package never imports the oracle, and constructing a vector without a GPU
+    fails loudly instead of computing on the CPU."""
+    import torch
+    pkg = os.path.join(ROOT, "eigensolvers_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn
+    if not torch.cuda.is_available():
+        import pytest
+        from eigensolvers_b200 import CudaVector
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            CudaVector(np.ones(3))

@@ -1,0 +1,214 @@
+"""GPU parity of the complete drivers on CudaVector against (a) golden results of the UNMODIFIED
+reference (tests/golden, made by oracle/ref_harness/make_golden.py) and (b) the CPU oracle run in
+the same test on the same seeded inputs.
+
+Bar (north_star): converged eigenvalues within max(eConv, 1e-10 relative) of the reference's on
+the same inputs; eigenvector overlaps |<v_ref|v>| >= 1 - 1e-8 (projector trace for degenerate
+targets, unittests/test_lanczosBlock.py:58-61).  Where the inner solves are inexact (rtol 1e-4)
+both runs are only defined up to the eigenvalue-change criterion eConv, which is the tolerance used.
+"""
+import json
+import os
+import warnings
+
+import numpy as np
+import pytest
+import scipy.linalg as la
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def gold(name):
+    return np.load(os.path.join(GOLD, name + ".npz"))
+
+
+def summary():
+    with open(os.path.join(GOLD, "summary.json")) as fh:
+        return json.load(fh)
+
+
+def opts(solver="gcrotmk", tol=1e-4, it=1000):
+    return {"linearSystemArgs": {"linearSolver": solver, "linearIter": it, "linear_tol": tol}}
+
+
+@pytest.fixture(autouse=True)
+def _reset_warning_filters():
+    yield
+    warnings.resetwarnings()
+
+
+def _run(H, guess, sigma, L, maxit, eConv, pick=None):
+    from eigensolvers_b200.lanczos import inexactLanczosDiagonalization
+    with warnings.catch_warnings():
+        warnings.simplefilter("default")
+        return inexactLanczosDiagonalization(H, guess, sigma, L, maxit, eConv, pick=pick, writeOut=False)
+
+
+def _overlap(a, b):
+    return abs(np.vdot(a, b)) / (np.linalg.norm(a) * np.linalg.norm(b))
+
+
+def test_c1_driver_example(rt):
+    """BASELINE config 1 on the GPU vs the reference's run (golden) — same number of Krylov steps."""
+    from eigensolvers_b200 import CudaVector
+    g = gold("lanczos_c1")
+    ev, vecs, st = _run(g["A"], CudaVector(g["Y0"].copy(), opts()), 30, 6, 4, 1e-8)
+    ref = summary()["lanczos_c1"]
+    assert st["isConverged"] and st["cumIter"] == ref["cumIter"]
+    assert isinstance(ev, np.ndarray) and isinstance(vecs, list) and isinstance(vecs[0], CudaVector)
+    i, j = np.argmin(abs(ev - 30)), np.argmin(abs(g["ev"] - 30))
+    assert abs(ev[i] - g["ev"][j]) <= max(1e-8, 1e-10) * abs(g["ev"][j])
+    assert abs(ev[i] - 31.2020202020202) < 1e-7
+    assert _overlap(vecs[i].array, g["vecs"][j]) >= 1 - 1e-8
+    S = CudaVector.overlapMatrix(vecs)
+    np.testing.assert_allclose(S, np.eye(len(vecs)), atol=1e-5)       # unittests/test_lanczos.py:55
+
+
+def test_reference_unit_test_lanczos(rt):
+    """unittests/test_lanczos.py on CudaVector: every assertion of the reference test."""
+    from eigensolvers_b200 import CudaVector
+    from eigensolvers_b200.hostmath import (diagonalizeHamiltonian, find_nearest,
+                                            get_pick_function_close_to_sigma, lowdinOrthoMatrix)
+    g = gold("lanczos_t1")
+    A = g["A"]
+    evE, uvE = np.linalg.eigh(A)
+    ev, vecs, st = _run(A, CudaVector(g["Y0"].copy(), opts()), 30, 6, 4, 1e-6, pick=get_pick_function_close_to_sigma(30))
+    assert st["cumIter"] == summary()["lanczos_t1"]["cumIter"]
+    S = CudaVector.overlapMatrix(vecs)
+    np.testing.assert_allclose(S, np.eye(S.shape[0]), atol=1e-5)
+    Hm = CudaVector.matrixRepresentation(A, vecs)
+    uS = lowdinOrthoMatrix(S, st)[1]
+    _, uv = diagonalizeHamiltonian(uS, Hm)
+    uSH = uS @ uv
+    np.testing.assert_allclose(uSH.T.conj() @ S @ uSH, np.eye(S.shape[0]), atol=1e-5)
+    S1 = CudaVector.overlapMatrix(vecs[:-1])
+    np.testing.assert_allclose(CudaVector.extendOverlapMatrix(vecs, S1), S, atol=1e-9)
+    H1 = CudaVector.matrixRepresentation(A, vecs[:-1])
+    np.testing.assert_allclose(CudaVector.extendMatrixRepresentation(A, vecs, H1), Hm, atol=1e-9)
+    assert abs(find_nearest(ev, 30)[1] - find_nearest(g["exact"], 30)[1]) <= 1e-4
+    iE, iT = find_nearest(evE, 30)[0], find_nearest(ev, 30)[0]
+    exact, mine = uvE[:, iE], vecs[iT].array
+    ov = np.vdot(exact, mine)
+    np.testing.assert_allclose(abs(ov), 1, rtol=1e-5)
+    np.testing.assert_allclose(exact, mine * ov, rtol=1e-5, atol=1e-4)
+    # against the reference's own converged numbers
+    np.testing.assert_allclose(np.sort(ev), np.sort(g["ev"]), rtol=1e-6)
+
+
+def test_reference_unit_test_block(rt):
+    """unittests/test_lanczosBlock.py on CudaVector (3-fold degenerate target)."""
+    from eigensolvers_b200 import CudaVector
+    from eigensolvers_b200.hostmath import get_pick_function_close_to_sigma
+    g = gold("lanczos_blk")
+    sigma = float(g["sigma"])
+    guess = [CudaVector(g["Ys"][:, i].copy(), opts()) for i in range(3)]
+    ev, vecs, st = _run(g["A"], guess, sigma, 6, 4, 1e-6, pick=get_pick_function_close_to_sigma(sigma))
+    assert st["isConverged"]
+    np.testing.assert_allclose(ev[:3], g["exact"][5:8], rtol=1e-6)
+    evE, uvE = np.linalg.eigh(g["A"])
+    mine = np.vstack([vecs[i].array for i in range(3)]).T
+    trace = np.abs(la.eigvals(mine.T.conj() @ uvE[:, 5:8])).sum()
+    assert abs(trace - 3) < 1e-6
+    ref3 = g["vecs"][:3].T                                           # reference's converged subspace
+    assert abs(np.abs(la.eigvals(mine.T.conj() @ ref3)).sum() - 3) < 1e-6
+
+
+def test_state_following(rt):
+    """unittests/test_stateFollowingHO.py (max-overlap pick) on CudaVector."""
+    from eigensolvers_b200 import CudaVector
+    from eigensolvers_b200.hostmath import get_pick_function_maxOvlp
+    g = gold("lanczos_ho")
+    o = opts("gcrotmk", 1e-4, 30000)
+    pick = get_pick_function_maxOvlp(CudaVector(g["ovlpRef"].copy(), o))
+    ev, vecs, st = _run(g["H"], CudaVector(g["Y0"].copy(), o), float(g["sigma"]), 16, 200, 1e-10, pick=pick)
+    assert st["isConverged"]
+    assert abs(ev[0] - g["energyRef"]) / abs(g["energyRef"]) <= 1e-4
+    assert abs(ev[0] - g["ev"][0]) <= 1e-8 * abs(g["ev"][0])
+    np.testing.assert_allclose(_overlap(vecs[0].array, g["ovlpRef"]), 1, rtol=1e-2)
+
+
+def test_sparse_generators_vs_oracle(rt):
+    """C2/C3 generators at small N: GPU run vs the CPU oracle run here on the same inputs, and vs
+    the reference golden (osc_1).  Includes the reference's LINDEP abort on the block case."""
+    from eigensolvers_b200 import CudaVector, hamiltonians as hm
+    from oracle.numpy_vector import NumpyVectorOracle as NV
+    o = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 1000, "linear_tol": 1e-4, "linear_atol": 1e-4}}
+    g = gold("osc_1")
+    H, om = hm.coupled_oscillators((6, 5, 5, 4), coupling=0.1, seed=1)
+    ev, vecs, st = _run(H, CudaVector(g["y0"].copy(), dict(o)), float(g["sigma"]), 8, 20, 1e-10)
+    ev_o, vecs_o, st_o = _run(H, NV(g["y0"].copy(), dict(o)), float(g["sigma"]), 8, 20, 1e-10)
+    assert st["isConverged"] and st_o["isConverged"]
+    assert abs(st["cumIter"] - st_o["cumIter"]) <= 1
+    assert abs(ev[0] - ev_o[0]) <= 1e-10 * abs(ev_o[0])
+    assert abs(ev[0] - g["ev"][0]) <= 1e-10 * abs(g["ev"][0])
+    assert _overlap(vecs[0].array, vecs_o[0].array) >= 1 - 1e-8
+    assert _overlap(vecs[0].array, g["vecs"][0]) >= 1 - 1e-8
+    x = vecs[0].array
+    assert np.linalg.norm(H @ x - ev[0] * x) < 1e-5                 # true residual
+
+    # block start that converges without restart (L=10), vs the oracle
+    H = hm.laplacian3d(12, seed=2, W=1.0)
+    evs = np.linalg.eigvalsh(H.toarray())
+    from eigensolvers_b200.hostmath import calculateTarget
+    sigma = calculateTarget(evs, 10)
+    guess = hm.orthonormal_block(H.shape[0], 4, seed=3)
+    ev, vecs, st = _run(H, [CudaVector(v.copy(), dict(o)) for v in guess], sigma, 10, 20, 1e-8)
+    ev_o, vecs_o, st_o = _run(H, [NV(v.copy(), dict(o)) for v in guess], sigma, 10, 20, 1e-8)
+    assert st["isConverged"] == st_o["isConverged"]
+    if st["isConverged"]:
+        np.testing.assert_allclose(np.sort(ev[:4]), np.sort(ev_o[:4]), rtol=1e-8)
+        near = np.sort(evs[np.argsort(abs(evs - sigma))[:4]])
+        np.testing.assert_allclose(np.sort(ev[:4]), near, rtol=1e-6)
+    # the reference aborts this configuration at L=6 with a linear dependency: NaN results
+    gl = gold("lap_blk")
+    ev, vecs, st = _run(H, [CudaVector(v.copy(), dict(o)) for v in guess], float(gl["sigma"]), 6, 20, 1e-8)
+    assert np.all(np.isnan(ev)) and not st["isConverged"]
+    assert st["cumIter"] == summary()["lap_blk"]["cumIter"] and len(vecs) == len(gl["ev"])
+
+
+def test_feast(rt):
+    """unittests/test_feast.py on CudaVector + the reference's converged numbers."""
+    from eigensolvers_b200 import CudaVector
+    from eigensolvers_b200.contour import feastDiagonalization
+    from eigensolvers_b200.hostmath import find_nearest
+    g = gold("feast_t1")
+    Y = [CudaVector(g["Y1"][:, i].copy(), opts("gcrotmk", 1e-2)) for i in range(6)]
+    ev, vecs, st = feastDiagonalization(g["A"], Y, 8, "legendre", 160.0, 166.0, 1e-10, 20, writeOut=False)
+    assert isinstance(ev, np.ndarray) and isinstance(vecs[0], CudaVector)
+    inside = [e for e in g["exact"] if 160.0 <= e <= 166.0]
+    assert len(inside) <= len(ev)
+    for e in inside:
+        assert abs(find_nearest(ev, e)[1] - e) <= 1e-4
+        assert abs(find_nearest(ev, e)[1] - find_nearest(g["ev"], e)[1]) <= 1e-6
+    S = CudaVector.overlapMatrix(vecs)
+    np.testing.assert_allclose(S, np.eye(S.shape[0]), atol=1e-5)
+    evE, uvE = np.linalg.eigh(g["A"])
+    for e in inside:
+        iE, iT = find_nearest(evE, e)[0], find_nearest(ev, e)[0]
+        np.testing.assert_allclose(_overlap(uvE[:, iE], vecs[iT].array), 1, rtol=1e-2)
+
+
+def test_fortran_golden_through_gpu(rt):
+    """Polizzi's Fortran FEAST numbers (unittests/data_fortranCode.out) through the GPU path: the
+    exact solve is replaced by the device GCROT at rtol 1e-13 (no dense direct solver on device)."""
+    import math
+    from eigensolvers_b200 import CudaVector
+    from eigensolvers_b200.contour import calculateQuadrature, updateQ
+    from eigensolvers_b200.hostmath import quadraturePointsWeights
+    g = gold("fortran")
+    order = list(g["order"])
+    gk, wk = quadraturePointsWeights(8, "legendre", positiveHalf=False)
+    theta = np.array([-(np.pi * 0.5) * (x - 1) for x in gk])[order]
+    wko = wk[order]
+    tight = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 100, "linear_tol": 1e-13, "linear_atol": 0.0}}
+    Y = [CudaVector(g["guess"][i].copy(), tight) for i in range(3)]
+    Q = [None] * 3
+    for k in range(8):
+        z = 4.0 + math.cos(theta[k]) + 0.3 * 1.0j * math.sin(theta[k])
+        Qe = np.array([CudaVector.solve(g["amat"], Y[i], z).array for i in range(3)])
+        np.testing.assert_allclose(Qe, g["Qe"][k], rtol=1e-5, atol=0)
+        for i in range(3):
+            Q = updateQ(Q, i, calculateQuadrature(g["amat"], Y[i], z, 1.0, theta[k], wko[k], 0.3), k)
+        np.testing.assert_allclose(np.array([Q[i].array for i in range(3)]), g["Q"][k], rtol=1e-5, atol=0)
