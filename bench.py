@@ -44,13 +44,19 @@ WORKLOADS = {
 MATVECS_TO_ECONV = {"c3": 6800, "c3mid": 6800, "c3small": 6800, "c2": 9000, "c2small": 3000}
 
 
-def build_workload(name):
+def build_workload(name, rank=0, world=1):
+    """Host-side synthetic inputs.  With world > 1 only this rank's row block of H is built
+    (w["H"] has n_local rows and GLOBAL column indices)."""
     from eigensolvers_b200 import hamiltonians as hm
     from eigensolvers_b200.hostmath import calculateTarget
+    from eigensolvers_b200.partition import row_offsets
     w = dict(WORKLOADS[name])
     t0 = time.time()
     if w["kind"] == "osc":
-        H, omega = hm.coupled_oscillators(w["dims"], coupling=0.1, seed=1)
+        Nglob = int(np.prod(w["dims"]))
+        off = row_offsets(Nglob, world)
+        rows = None if world == 1 else (int(off[rank]), int(off[rank + 1]))
+        H, omega = hm.coupled_oscillators(w["dims"], coupling=0.1, seed=1, rows=rows)
         levels = hm.oscillator_levels(omega, 0.1, 40, max_quanta=6)
         w["sigma"] = float(calculateTarget(levels, w["level"]))
         w["label"] = f"coupled-oscillator product basis dims={w['dims']}"
@@ -67,13 +73,16 @@ def build_workload(name):
             else:
                 w["sigma"] = pinned[w["n"]]
         w["label"] = f"3-D Laplacian {w['n']}^3 + random potential"
-    N = H.shape[0]
+    N = H.shape[1]
+    if world > 1 and H.shape[0] == N:  # generators without a row-block mode: slice
+        off = row_offsets(N, world)
+        H = H[int(off[rank]):int(off[rank + 1])].tocsr()
     rng = np.random.default_rng(4)
     if w["nBlock"] == 1:
         guesses = [rng.standard_normal(N)]
     else:
         guesses = hm.orthonormal_block(N, w["nBlock"], seed=3)
-    w.update(H=H, N=N, nnz=int(H.nnz), guesses=guesses, gen_seconds=time.time() - t0)
+    w.update(H=H, N=N, nnz=int(H.nnz), guesses=guesses, gen_seconds=time.time() - t0, world=world)
     return w
 
 
@@ -187,7 +196,7 @@ def run_reference_arm(args, w):
 
 
 def config_dict(args, w):
-    return {"workload": f"{args.workload}: {w['label']}, N={w['N']}, nnz={w['nnz']}, nBlock={w['nBlock']}, "
+    return {"workload": f"{args.workload}: {w['label']}, N={w['N']}, nnz(rank0)={w['nnz']}, nBlock={w['nBlock']}, "
                         f"sigma={w['sigma']:.6f}, L={w['L']}, maxit={w['maxit']}, eConv={w['eConv']:g}, "
                         f"gcrotmk rtol={w['tol']:g}",
             "format": "sell32", "parallelism": f"row-shard x{args.gpus}",
@@ -220,6 +229,11 @@ def run_ours(args, w):
     Hp = sp.csr_matrix((pinned(H.data), pinned(H.indices.astype(np.int32)), pinned(H.indptr.astype(np.int64))),
                        shape=H.shape, copy=False)
     Hp.has_sorted_indices = True
+
+    def make_operator():
+        if world > 1:
+            return DeviceOperator.from_local_rows(Hp, w["N"], runtime=rt)
+        return DeviceOperator.from_host(Hp, runtime=rt)
     guesses_p = [pinned(g) for g in w["guesses"]]
     flush = torch.zeros(48 * 1024 * 1024, dtype=torch.float64, device=rt.device)  # 384 MB > L2
 
@@ -239,7 +253,7 @@ def run_ours(args, w):
         return ev, Y, st
 
     # ---- resident leg: operator and guesses already in HBM
-    op = DeviceOperator.from_host(Hp, runtime=rt)
+    op = make_operator()
     guess_dev = [CudaVector(g, dict(opts))._t for g in guesses_p]
     for _ in range(args.warmup):
         flush.add_(1.0)
@@ -297,15 +311,19 @@ def run_ours(args, w):
                                "tsupdate": ms4[2] / (t_prof * 1e3)}}
 
     # ---- end-to-end leg: host buffers in, host eigenvectors out, every step
-    h2d = int(H.nnz) * 12 + (w["N"] + 1) * 8 + w["nBlock"] * w["N"] * 8
-    d2h = w["nBlock"] * w["N"] * 8
+    nnz_total = torch.tensor([float(H.nnz)], dtype=torch.float64, device=rt.device)
+    if world > 1:
+        dist.all_reduce(nnz_total)
+    nnz_total = int(nnz_total.item())
+    h2d = nnz_total * 12 + (w["N"] + world) * 8 + w["nBlock"] * w["N"] * 8   # all ranks together
+    d2h = w["nBlock"] * w["N"] * 8 * world                                     # every rank reads the full vectors
     del op
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for _ in range(args.steps):
         flush.add_(1.0)
-        op2 = DeviceOperator.from_host(Hp, runtime=rt)                      # H2D of the Hamiltonian
+        op2 = make_operator()                                                # H2D of the Hamiltonian
         gd = [CudaVector(g, dict(opts))._t for g in guesses_p]               # H2D of the guesses
         ev2, Y2, st2 = one_run(op2, gd)
         host_vecs = [Y2[i].array for i in range(w["nBlock"])]                # D2H of the eigenvectors
@@ -317,7 +335,7 @@ def run_ours(args, w):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e_value = float(tt.item()) / args.steps * 1e-3 / w["nBlock"]
     x = host_vecs[0]
-    true_res = float(np.linalg.norm(H @ x - ev2[0] * x)) if rank == 0 else None
+    true_res = float(np.linalg.norm(H @ x - ev2[0] * x)) if world == 1 else None
 
     # ---- CPU baseline (rank 0, N = 1 only)
     cpu = None
@@ -369,7 +387,8 @@ def main():
         w = build_workload(args.workload)
         run_reference_arm(args, w)
         return
-    w = build_workload(args.workload)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    w = build_workload(args.workload, rank, world)
     run_ours(args, w)
 
 

@@ -122,9 +122,15 @@ class CudaVector(AbstractVector):
         import torch.distributed as dist
         off = rt.offsets_for(self._n_global)
         sizes = [int(off[p + 1] - off[p]) for p in range(rt.world)]
-        parts = [rt.empty(s, self._cplx) for s in sizes]
-        dist.all_gather(parts, self._t)
-        return rt.torch.cat(parts).cpu().numpy()
+        width = max(sizes)  # NCCL all_gather needs equal contributions: pad to the largest block
+        mine = rt.empty(width, self._cplx)
+        mine[:self._nloc] = self._t
+        if width > self._nloc:
+            mine[self._nloc:] = 0
+        gathered = rt.empty(width * rt.world, self._cplx)
+        dist.all_gather_into_tensor(gathered, mine)
+        host = gathered.cpu().numpy().reshape(rt.world, width)
+        return np.concatenate([host[p, :sizes[p]] for p in range(rt.world)])
 
     @property
     def ttns(self):

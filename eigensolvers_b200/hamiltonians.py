@@ -41,21 +41,25 @@ def oscillator_frequencies(D, seed=1):
     return 1.0 + 0.37 * np.arange(D) / D + 0.05 * rng.random(D)
 
 
-def coupled_oscillators(dims, coupling=0.1, seed=1, dtype_index=np.int32):
+def coupled_oscillators(dims, coupling=0.1, seed=1, dtype_index=np.int32, rows=None):
     """H = sum_i w_i (n_i + 1/2) + coupling * sum_i q_i q_{i+1} in the product number basis.
 
     Last mode is the fastest index.  Assembled directly in CSR order: the column offsets
     {0, +-stride_i +- stride_{i+1}} are the same for every row, so visiting them in ascending
     order yields sorted rows without a COO sort (N = 2e7 needs ~25 passes over N-vectors).
+    `rows=(r0, r1)` builds only that row block (global column indices), which is what a rank of
+    the row-sharded mode needs; the result equals H[r0:r1] of the full matrix.
     """
     dims = [int(d) for d in dims]
     D = len(dims)
     N = int(np.prod(dims))
+    r0, r1 = (0, N) if rows is None else (int(rows[0]), int(rows[1]))
+    nloc = r1 - r0
     omega = oscillator_frequencies(D, seed)
     strides = [int(np.prod(dims[i + 1:])) for i in range(D)]
-    idx = np.arange(N, dtype=np.int64)
+    idx = np.arange(r0, r1, dtype=np.int64)
     occ = [((idx // strides[i]) % dims[i]).astype(np.int16) for i in range(D)]
-    diag = np.zeros(N)
+    diag = np.zeros(nloc)
     for i in range(D):
         diag += omega[i] * (occ[i] + 0.5)
 
@@ -67,7 +71,7 @@ def coupled_oscillators(dims, coupling=0.1, seed=1, dtype_index=np.int32):
             for sj in (-1, 1):
                 off = si * strides[i] + sj * strides[j]
                 ni, nj = occ[i], occ[j]
-                mask = np.ones(N, dtype=bool)
+                mask = np.ones(nloc, dtype=bool)
                 mask &= (ni + si >= 0) & (ni + si < dims[i])
                 mask &= (nj + sj >= 0) & (nj + sj < dims[j])
                 # <n+1|q|n> = sqrt((n+1)/2), <n-1|q|n> = sqrt(n/2)
@@ -75,10 +79,10 @@ def coupled_oscillators(dims, coupling=0.1, seed=1, dtype_index=np.int32):
                 fj = np.sqrt(((nj + 1) if sj > 0 else nj) / 2.0)
                 terms.append((off, mask, coupling * fi * fj))
     terms.sort(key=lambda t: t[0])
-    counts = np.zeros(N, dtype=np.int64)
+    counts = np.zeros(nloc, dtype=np.int64)
     for off, mask, _ in terms:
         counts += 1 if mask is None else mask
-    indptr = np.zeros(N + 1, dtype=np.int64)
+    indptr = np.zeros(nloc + 1, dtype=np.int64)
     np.cumsum(counts, out=indptr[1:])
     nnz = int(indptr[-1])
     indices = np.empty(nnz, dtype=dtype_index)
@@ -90,12 +94,12 @@ def coupled_oscillators(dims, coupling=0.1, seed=1, dtype_index=np.int32):
             data[pos] = val
             pos += 1
         else:
-            rows = np.nonzero(mask)[0]
-            p = pos[rows]
-            indices[p] = rows + off
-            data[p] = val[rows]
-            pos[rows] += 1
-    H = sp.csr_matrix((data, indices, indptr), shape=(N, N))
+            sel = np.nonzero(mask)[0]
+            p = pos[sel]
+            indices[p] = idx[sel] + off
+            data[p] = val[sel]
+            pos[sel] += 1
+    H = sp.csr_matrix((data, indices, indptr), shape=(nloc, N))
     H.has_sorted_indices = True
     return H, omega
 

@@ -78,6 +78,11 @@ class DeviceOperator:
         data = np.ascontiguousarray(A.data, dtype=np.float64)
         if rt.world > 1:
             indptr, indices, data = op._shard(indptr, indices, data)
+        return op._finish(indptr, indices, data, fmt)
+
+    def _finish(self, indptr, indices, data, fmt):
+        """Upload the (local) CSR arrays, create the cv_op, register the halo plan, build SELL."""
+        op, rt = self, self.rt
         n_rows = len(indptr) - 1
         n_cols = op.shape[1] if rt.world == 1 else op.n_local + op.n_halo
         op.nnz = int(indptr[-1])
@@ -128,28 +133,54 @@ class DeviceOperator:
 
     # -- row-sharded mode --------------------------------------------------------------------
     def _shard(self, indptr, indices, data):
-        """Slice this rank's row block and renumber columns (cv_halo_build, comm.cu)."""
+        """Slice this rank's row block out of the FULL matrix and renumber its columns."""
         rt = self.rt
         off = rt.offsets_for(self.shape[0])
         r0, r1 = int(off[rt.rank]), int(off[rt.rank + 1])
+        return self._localize(indptr, indices, data, r0, r1, full=True)
+
+    def _localize(self, indptr, indices, data, r0, r1, full):
+        """Renumber the columns of rows [r0, r1) to [owned | halo] (cv_halo_build, comm.cu).
+        `full`: indptr/indices/data describe the whole matrix; otherwise only the row block
+        (indptr rebased to 0, global column indices)."""
+        rt = self.rt
+        off = rt.offsets_for(self.shape[0])
         nloc = r1 - r0
+        # the native routine indexes indptr[row0..row1]; for a pre-sliced block shift the base
+        p_indptr = indptr.ctypes.data - (0 if full else 8 * r0)
+        lo, hi = (int(indptr[r0]), int(indptr[r1])) if full else (0, int(indptr[-1]))
         n_halo = C.c_int64()
-        _lib.check(rt.lib.cv_halo_count(indptr.ctypes.data, indices.ctypes.data, r0, r1,
-                                        C.byref(n_halo)))
+        _lib.check(rt.lib.cv_halo_count(p_indptr, indices.ctypes.data, r0, r1, C.byref(n_halo)))
         nh = n_halo.value
-        nnz_loc = int(indptr[r1] - indptr[r0])
         halo_cols = np.empty(nh, dtype=np.int32)
         halo_owner = np.empty(nh, dtype=np.int32)
         loc_indptr = np.empty(nloc + 1, dtype=np.int64)
-        loc_indices = np.empty(nnz_loc, dtype=np.int32)
-        _lib.check(rt.lib.cv_halo_build(indptr.ctypes.data, indices.ctypes.data, r0, r1,
-                                        off.ctypes.data, rt.world, nh, halo_cols.ctypes.data,
-                                        halo_owner.ctypes.data, loc_indptr.ctypes.data,
-                                        loc_indices.ctypes.data))
+        loc_indices = np.empty(hi - lo, dtype=np.int32)
+        _lib.check(rt.lib.cv_halo_build(p_indptr, indices.ctypes.data, r0, r1, off.ctypes.data,
+                                        rt.world, nh, halo_cols.ctypes.data, halo_owner.ctypes.data,
+                                        loc_indptr.ctypes.data, loc_indices.ctypes.data))
         self.n_local, self.n_halo = nloc, nh
         self.halo_cols, self.halo_owner = halo_cols, halo_owner
         self.row0 = r0
-        return loc_indptr, loc_indices, np.ascontiguousarray(data[indptr[r0]:indptr[r1]])
+        return loc_indptr, loc_indices, np.ascontiguousarray(data[lo:hi])
+
+    @classmethod
+    def from_local_rows(cls, H_rows, n_global, runtime=None, fmt="auto"):
+        """Row-sharded construction without ever holding the full matrix: `H_rows` is this rank's
+        row block H[r_p:r_{p+1}] (scipy CSR, GLOBAL column indices), n_global the matrix order."""
+        from .runtime import Runtime
+        rt = runtime or Runtime.get()
+        A = cls._as_csr(H_rows)
+        op = cls(rt, (n_global, n_global))
+        r0, r1 = rt.local_range(n_global)
+        if A.shape[0] != r1 - r0:
+            raise ValueError(f"rank {rt.rank} owns rows [{r0},{r1}) but got {A.shape[0]} rows")
+        indptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(A.indices, dtype=np.int32)
+        data = np.ascontiguousarray(A.data, dtype=np.float64)
+        if rt.world > 1:
+            indptr, indices, data = op._localize(indptr, indices, data, r0, r1, full=False)
+        return op._finish(indptr, indices, data, fmt)
 
     def _register_halo(self):
         """Exchange the halo request lists once (host, torch.distributed) and register the plan."""

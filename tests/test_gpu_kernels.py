@@ -188,8 +188,11 @@ def test_gram_schmidt(rt, cplx, m):
     for q in qs:
         ref = ref - q * (np.dot(ref, q) / np.dot(q, q))
     ip = np.dot(ref, ref)
-    ref = ref / np.sqrt(ip)
     out = CudaVector.orthogonalize_against_set(CudaVector(x), [CudaVector(q) for q in qs])
+    if not (ip > 1e-14):      # numpyVector.py:141 — for complex data numpy orders by the real part first
+        assert out is None
+        return
+    ref = ref / np.sqrt(ip)
     np.testing.assert_allclose(out.array, ref, rtol=1e-10, atol=1e-12)
 
 
