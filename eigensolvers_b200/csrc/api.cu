@@ -1,6 +1,7 @@
 // api.cu — C ABI of libcudavec: context, operator, BLAS-1 / tall-skinny / SpMV entry points.
 // Host-side glue only; kernels live in kernels_vec.cuh / kernels_spmv.cuh.
 #include <stdarg.h>
+#include <unordered_map>
 #include <vector>
 #include "internal.h"
 
@@ -45,6 +46,7 @@ extern "C" int cv_ctx_create(int device, void *scratch_dev, size_t scratch_bytes
   CV_CUDA(cudaMallocHost(&c->mailbox, CV_N_SCALARS * sizeof(double)));
   c->launches = 0;
   c->prof = nullptr;
+  c->reorth_eta = 0.1;
   c->comm = nullptr;
   c->rank = 0;
   c->world = 1;
@@ -156,6 +158,30 @@ int cv_check_launch(cv_ctx *ctx, const char *what) {
   return CV_OK;
 }
 
+// Grid size of a persistent grid-stride launch: enough CTAs for the work, at most ONE resident
+// wave of this particular kernel (SMs x CTAs/SM from the occupancy calculator), so that no
+// partial second wave leaves SMs idle at the tail.
+int cv_occ_grid(cv_ctx *ctx, const void *kernel, int64_t work_items, int items_per_cta) {
+  static std::unordered_map<const void *, int> cache;
+  int occ;
+  auto it = cache.find(kernel);
+  if (it == cache.end()) {
+    occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, CV_BLOCK, 0) != cudaSuccess || occ < 1) {
+      cudaGetLastError();
+      occ = 1;
+    }
+    cache[kernel] = occ;
+  } else {
+    occ = it->second;
+  }
+  int64_t need = (work_items + items_per_cta - 1) / items_per_cta;
+  int64_t cap = (int64_t)ctx->sms * occ;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+#define CV_KGRID(kf, work) cv_occ_grid(ctx, (const void *)(kf), (work), CV_BLOCK)
+
 // ------------------------------------------------------------------------------------------
 // BLAS-1 (internal launchers are shared with solvers.cu through internal.h)
 // ------------------------------------------------------------------------------------------
@@ -183,18 +209,22 @@ extern "C" int cv_scal(cv_ctx *ctx, int64_t n, int x_cplx, int y_cplx, double a_
   cudaStream_t st = (cudaStream_t)stream;
   if (!x_cplx && !y_cplx) {
     int W = vecW(0, {x, y});
-    int grid = cv_grid_for(ctx, (n + W - 1) / W, CV_BLOCK);
-    if (W == 2)
-      k_scal_rr<2><<<grid, CV_BLOCK, 0, st>>>(n, a_re, (const double *)x, (double *)y);
-    else
-      k_scal_rr<1><<<grid, CV_BLOCK, 0, st>>>(n, a_re, (const double *)x, (double *)y);
+    if (W == 2) {
+      auto kf = k_scal_rr<2>;
+      kf<<<CV_KGRID(kf, n / 2 + 1), CV_BLOCK, 0, st>>>(n, a_re, (const double *)x, (double *)y);
+    } else {
+      auto kf = k_scal_rr<1>;
+      kf<<<CV_KGRID(kf, n), CV_BLOCK, 0, st>>>(n, a_re, (const double *)x, (double *)y);
+    }
   } else {
-    int grid = cv_grid_for(ctx, n, CV_BLOCK);
     cplx a = make_cplx(a_re, a_im);
-    if (x_cplx)
-      k_scal<cplx, cplx, cplx><<<grid, CV_BLOCK, 0, st>>>(n, a, (const cplx *)x, (cplx *)y);
-    else
-      k_scal<double, cplx, cplx><<<grid, CV_BLOCK, 0, st>>>(n, a, (const double *)x, (cplx *)y);
+    if (x_cplx) {
+      auto kf = k_scal<cplx, cplx, cplx>;
+      kf<<<CV_KGRID(kf, n), CV_BLOCK, 0, st>>>(n, a, (const cplx *)x, (cplx *)y);
+    } else {
+      auto kf = k_scal<double, cplx, cplx>;
+      kf<<<CV_KGRID(kf, n), CV_BLOCK, 0, st>>>(n, a, (const double *)x, (cplx *)y);
+    }
   }
   return cv_check_launch(ctx, "scal");
 }
@@ -202,15 +232,14 @@ extern "C" int cv_scal(cv_ctx *ctx, int64_t n, int x_cplx, int y_cplx, double a_
 extern "C" int cv_real(cv_ctx *ctx, int64_t n, const void *x, double *y, void *stream) {
   CV_REQUIRE(ctx && x && y && n >= 0, "cv_real: bad argument");
   if (n == 0) return CV_OK;
-  k_real<<<cv_grid_for(ctx, n, CV_BLOCK), CV_BLOCK, 0, (cudaStream_t)stream>>>(n, (const cplx *)x, y);
+  k_real<<<CV_KGRID(k_real, n), CV_BLOCK, 0, (cudaStream_t)stream>>>(n, (const cplx *)x, y);
   return cv_check_launch(ctx, "real");
 }
 
 extern "C" int cv_conj(cv_ctx *ctx, int64_t n, const void *x, void *y, void *stream) {
   CV_REQUIRE(ctx && x && y && n >= 0, "cv_conj: bad argument");
   if (n == 0) return CV_OK;
-  k_conj<<<cv_grid_for(ctx, n, CV_BLOCK), CV_BLOCK, 0, (cudaStream_t)stream>>>(n, (const cplx *)x,
-                                                                                (cplx *)y);
+  k_conj<<<CV_KGRID(k_conj, n), CV_BLOCK, 0, (cudaStream_t)stream>>>(n, (const cplx *)x, (cplx *)y);
   return cv_check_launch(ctx, "conj");
 }
 
@@ -218,10 +247,14 @@ extern "C" int cv_conj(cv_ctx *ctx, int64_t n, const void *x, void *y, void *str
 int cv_dot_dev(cv_ctx *ctx, int64_t n, int cplx_, int conj, const void *x, const void *y, int slot,
                cudaStream_t st) {
   int W = vecW(cplx_, {x, y});
-  int grid = cv_grid_for(ctx, (n + W - 1) / W, CV_BLOCK);
   double *out = ctx->scalars + slot;
-#define LAUNCH_DOT(T, WW, CJ) \
-  k_dot<T, WW, CJ><<<grid, CV_BLOCK, 0, st>>>(n, (const T *)x, (const T *)y, ctx->partials, ctx->counters, out)
+  cv_prof_scope prof(ctx, 3, st);
+#define LAUNCH_DOT(T, WW, CJ)                                                                          \
+  do {                                                                                                 \
+    auto kf = k_dot<T, WW, CJ>;                                                                        \
+    kf<<<CV_KGRID(kf, n / WW + 1), CV_BLOCK, 0, st>>>(n, (const T *)x, (const T *)y, ctx->partials,     \
+                                                      ctx->counters, out);                            \
+  } while (0)
   if (cplx_) {
     if (conj)
       LAUNCH_DOT(cplx, 1, true);
@@ -239,25 +272,34 @@ int cv_dot_dev(cv_ctx *ctx, int64_t n, int cplx_, int conj, const void *x, const
 
 int cv_nrm2sq_dev(cv_ctx *ctx, int64_t n, int cplx_, const void *x, int slot, cudaStream_t st) {
   int W = vecW(cplx_, {x});
-  int grid = cv_grid_for(ctx, (n + W - 1) / W, CV_BLOCK);
   double *out = ctx->scalars + slot;
+  cv_prof_scope prof(ctx, 3, st);
+#define LAUNCH_NRM(T, WW)                                                                            \
+  do {                                                                                               \
+    auto kf = k_nrm2sq<T, WW>;                                                                       \
+    kf<<<CV_KGRID(kf, n / WW + 1), CV_BLOCK, 0, st>>>(n, (const T *)x, ctx->partials, ctx->counters, out); \
+  } while (0)
   if (cplx_)
-    k_nrm2sq<cplx, 1><<<grid, CV_BLOCK, 0, st>>>(n, (const cplx *)x, ctx->partials, ctx->counters, out);
+    LAUNCH_NRM(cplx, 1);
   else if (W == 2)
-    k_nrm2sq<double, 2><<<grid, CV_BLOCK, 0, st>>>(n, (const double *)x, ctx->partials, ctx->counters, out);
+    LAUNCH_NRM(double, 2);
   else
-    k_nrm2sq<double, 1><<<grid, CV_BLOCK, 0, st>>>(n, (const double *)x, ctx->partials, ctx->counters, out);
+    LAUNCH_NRM(double, 1);
+#undef LAUNCH_NRM
   CV_TRY(cv_check_launch(ctx, "nrm2sq"));
   return cv_reduce_ranks(ctx, slot, 1, st);
 }
 
-// x (and optionally x2) *= 1/sqrt(scalars[slot]); mode 1 keeps x when the factor is not finite
-int cv_scale_dev(cv_ctx *ctx, int64_t n, int cplx_, void *x, void *x2, int slot, int mode,
-                 cudaStream_t st) {
-  int W = vecW(cplx_, {x, x2});
-  int grid = cv_grid_for(ctx, (n + W - 1) / W, CV_BLOCK);
+// x *= 1/sqrt(scalars[slot]); mode 1 keeps x when the factor is not finite
+int cv_scale_dev(cv_ctx *ctx, int64_t n, int cplx_, void *x, int slot, int mode, cudaStream_t st) {
+  int W = vecW(cplx_, {x});
   const double *s = ctx->scalars + slot;
-#define LAUNCH_SC(T, WW, MD) k_scale_dev<T, WW, MD><<<grid, CV_BLOCK, 0, st>>>(n, (T *)x, (T *)x2, s)
+  cv_prof_scope prof(ctx, 3, st);
+#define LAUNCH_SC(T, WW, MD)                                                   \
+  do {                                                                         \
+    auto kf = k_scale_dev<T, WW, MD>;                                          \
+    kf<<<CV_KGRID(kf, n / WW + 1), CV_BLOCK, 0, st>>>(n, (T *)x, s);            \
+  } while (0)
   if (cplx_) {
     if (mode) LAUNCH_SC(cplx, 1, 1); else LAUNCH_SC(cplx, 1, 0);
   } else if (W == 2) {
@@ -303,7 +345,7 @@ extern "C" int cv_normalize(cv_ctx *ctx, int64_t n, int cplx_, void *x, double *
     return CV_OK;
   }
   CV_TRY(cv_nrm2sq_dev(ctx, n, cplx_, x, CV_S_TMP, st));
-  CV_TRY(cv_scale_dev(ctx, n, cplx_, x, nullptr, CV_S_TMP, 0, st));
+  CV_TRY(cv_scale_dev(ctx, n, cplx_, x, CV_S_TMP, 0, st));
   if (norm_host) {
     CV_TRY(cv_fetch_scalars(ctx, CV_S_TMP, 1, st));
     *norm_host = sqrt(ctx->mailbox[CV_S_TMP]);
@@ -317,9 +359,13 @@ extern "C" int cv_normalize(cv_ctx *ctx, int64_t n, int cplx_, void *x, double *
 template <typename TV, typename TC, typename TY, int W, bool NORM>
 static int launch_lincomb_nc(cv_ctx *ctx, const LcParams &p, int ncol, int grid, double *out_norm,
                              cudaStream_t st) {
-#define LC(NC)                                                                                   \
-  k_lincomb<TV, TC, TY, W, NC, NORM><<<grid, CV_BLOCK, 0, st>>>(p, ctx->partials, ctx->counters, \
-                                                                out_norm)
+  (void)grid;
+  cv_prof_scope prof(ctx, 3, st);
+#define LC(NC)                                                                                     \
+  do {                                                                                             \
+    auto kf = k_lincomb<TV, TC, TY, W, NC, NORM>;                                                  \
+    kf<<<CV_KGRID(kf, p.n / W + 1), CV_BLOCK, 0, st>>>(p, ctx->partials, ctx->counters, out_norm);  \
+  } while (0)
   switch (ncol) {
     case 1: LC(1); break;
     case 2: LC(2); break;
@@ -407,26 +453,29 @@ extern "C" int cv_lincomb(cv_ctx *ctx, int64_t n, int v_cplx, int c_cplx, int m,
 // ------------------------------------------------------------------------------------------
 template <typename T, int W, bool CONJ>
 static int launch_tsdot(cv_ctx *ctx, const TsParams &p, int slot, const double *gate, cudaStream_t st) {
+  const double eta2 = ctx->reorth_eta * ctx->reorth_eta;
   constexpr int NR = Num<T>::NRED;
   const int64_t np = (p.n + W - 1) / W;
   double *out = ctx->scalars + slot;
   // MI vectors per CTA slab: 16 for a single right-hand side, 8 for 2, 4 for 3..4
   int MI = p.b == 1 ? 16 : (p.b == 2 ? 8 : 4);
   int ny = (p.m + MI - 1) / MI;
-  int gx = cv_grid_for(ctx, np, CV_BLOCK);
-  // keep (gx * values) inside the partials area and the whole grid near one wave
   int64_t per_slab = (int64_t)MI * p.b * NR;
-  while ((int64_t)gx * per_slab * ny > (int64_t)CV_N_PARTIALS && gx > 1) gx >>= 1;
-  if (ny > 1) {
-    int cap = (ctx->sms * CV_CTAS_PER_SM * 2) / ny;
-    if (cap < 1) cap = 1;
-    if (gx > cap) gx = cap;
-  }
-  dim3 grid(gx, ny);
   {
     cv_prof_scope prof(ctx, 1, st);
-#define TSD(MI_, B_) \
-  k_tsdot<T, W, CONJ, MI_, B_><<<grid, CV_BLOCK, 0, st>>>(p, gate, ctx->partials, ctx->counters, out)
+    // one resident wave in total: the y-slabs share the SMs
+#define TSD(MI_, B_)                                                                               \
+  do {                                                                                             \
+    auto kf = k_tsdot<T, W, CONJ, MI_, B_>;                                                        \
+    int wave = CV_KGRID(kf, (int64_t)1 << 40);                                                     \
+    int gx = wave / ny;                                                                            \
+    if (gx < 1) gx = 1;                                                                            \
+    int64_t need = (np + CV_BLOCK - 1) / CV_BLOCK;                                                 \
+    if (gx > need) gx = (int)need;                                                                 \
+    while ((int64_t)gx * per_slab * ny > (int64_t)CV_N_PARTIALS && gx > 1) gx >>= 1;               \
+    dim3 grid(gx, ny);                                                                             \
+    kf<<<grid, CV_BLOCK, 0, st>>>(p, gate, eta2, ctx->partials, ctx->counters, out);               \
+  } while (0)
     switch (p.b) {
       case 1: TSD(16, 1); break;
       case 2: TSD(8, 2); break;
@@ -500,14 +549,18 @@ int cv_tsupdate_dev(cv_ctx *ctx, int64_t n, int cplx_, int m, const void *const 
     if ((uintptr_t)v[i] & 15) W = 1;
   }
   if ((uintptr_t)w & 15) W = 1;
-  int grid = cv_grid_for(ctx, (n + W - 1) / W, CV_BLOCK);
   const double *h = ctx->scalars + h_slot;
   double *on = norm_slot >= 0 ? ctx->scalars + norm_slot : nullptr;
   size_t sh = sizeof(double) * m * (cplx_ ? 2 : 1);
+  const double eta2 = ctx->reorth_eta * ctx->reorth_eta;
   {
     cv_prof_scope prof(ctx, 2, st);
-#define TSU(T, WW, NM) \
-  k_tsupdate<T, WW, NM><<<grid, CV_BLOCK, sh, st>>>(p, h, gate, (T *)w, ctx->partials, ctx->counters, on)
+#define TSU(T, WW, NM)                                                                             \
+  do {                                                                                             \
+    auto kf = k_tsupdate<T, WW, NM>;                                                               \
+    kf<<<CV_KGRID(kf, n / WW + 1), CV_BLOCK, sh, st>>>(p, h, gate, eta2, (T *)w, ctx->partials,     \
+                                                       ctx->counters, on);                        \
+  } while (0)
     if (cplx_) {
       if (on) TSU(cplx, 1, true); else TSU(cplx, 1, false);
     } else if (W == 2) {
@@ -529,7 +582,9 @@ template <typename T, int W>
 static int gs_chain(cv_ctx *ctx, int64_t n, const T *x_in, int m, const void *const *q, T *x_out,
                     cudaStream_t st) {
   constexpr int NR = Num<T>::NRED;
-  int grid = cv_grid_for(ctx, (n + W - 1) / W, CV_BLOCK);
+  auto kf = k_mgs_step<T, W>;
+  int grid = CV_KGRID(kf, n / W + 1);
+  cv_prof_scope prof(ctx, 3, st);
   // step i: subtract projection on q[i-1] (coefficients from slot i-1), dots with q[i]
   for (int i = 0; i <= m; ++i) {
     const T *src = (i == 0) ? x_in : x_out;
@@ -577,10 +632,10 @@ extern "C" int cv_gs_against_set(cv_ctx *ctx, int64_t n, int cplx_, const void *
   }
   *status = 0;
   if (cplx_) {
-    k_div_csqrt<<<cv_grid_for(ctx, n, CV_BLOCK), CV_BLOCK, 0, st>>>(n, (cplx *)x_out, ctx->scalars + slot);
+    k_div_csqrt<<<CV_KGRID(k_div_csqrt, n), CV_BLOCK, 0, st>>>(n, (cplx *)x_out, ctx->scalars + slot);
     return cv_check_launch(ctx, "div_csqrt");
   }
-  return cv_scale_dev(ctx, n, 0, x_out, nullptr, slot, 0, st);
+  return cv_scale_dev(ctx, n, 0, x_out, slot, 0, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -665,13 +720,20 @@ template <typename T, bool HALO, bool EPI, bool DOTS>
 static int launch_spmv_fmt(cv_ctx *ctx, cv_op *op, const SpmvArgs<T> &a, cudaStream_t st) {
   cv_prof_scope prof(ctx, 0, st);
   if (op->fmt == CV_FMT_SELL) {
-    int grid = cv_grid_for(ctx, op->n_slices, CV_WARPS);
-    k_spmv_sell<T, HALO, EPI, DOTS><<<grid, CV_BLOCK, 0, st>>>(a);
+    auto kf = k_spmv_sell<T, HALO, EPI, DOTS>;
+    int wave = cv_occ_grid(ctx, (const void *)kf, (int64_t)1 << 40, CV_WARPS);
+    int64_t need = (op->n_slices + CV_WARPS - 1) / CV_WARPS;
+    // few slices per warp: a static slice->warp map would quantise badly (3.3 slices per warp on
+    // the 100^3 Laplacian = 18 % idle); launch one slice per warp and let the hardware CTA
+    // scheduler balance.  Many slices per warp: one persistent wave.
+    int grid = (int)(need <= 16 * (int64_t)wave ? need : wave);
+    kf<<<grid, CV_BLOCK, 0, st>>>(a);
   } else {
-#define CSR(G)                                                    \
-  {                                                               \
-    int grid = cv_grid_for(ctx, op->n_rows, CV_BLOCK / G);        \
-    k_spmv_csr<T, G, HALO, EPI, DOTS><<<grid, CV_BLOCK, 0, st>>>(a); \
+#define CSR(G)                                                                    \
+  {                                                                               \
+    auto kf = k_spmv_csr<T, G, HALO, EPI, DOTS>;                                  \
+    int grid = cv_occ_grid(ctx, (const void *)kf, op->n_rows, CV_BLOCK / G);      \
+    kf<<<grid, CV_BLOCK, 0, st>>>(a);                                             \
   }
     switch (op->csr_group) {
       case 2: CSR(2); break;

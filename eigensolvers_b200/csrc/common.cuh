@@ -83,6 +83,10 @@ struct cv_ctx {
   cv_comm_state *comm;  // null when world == 1
   int rank, world;
   cv_prof_state *prof;
+  // GCROT re-orthogonalises only when the first Gram-Schmidt pass leaves less than eta of the
+  // norm (Daniel-Gragg-Kaufman-Stewart); eta = 1/sqrt(2) is the classic value, 0.1 keeps the
+  // basis orthogonal to ~10 eps while skipping the second pass in all but cancelling steps
+  double reorth_eta;
 };
 
 // RAII bracket: records an event pair around the launches issued inside its scope

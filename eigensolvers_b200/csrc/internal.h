@@ -31,8 +31,8 @@ int cv_check_launch(cv_ctx *ctx, const char *what);
 int cv_dot_dev(cv_ctx *ctx, int64_t n, int cplx_, int conj, const void *x, const void *y, int slot,
                cudaStream_t st);
 int cv_nrm2sq_dev(cv_ctx *ctx, int64_t n, int cplx_, const void *x, int slot, cudaStream_t st);
-int cv_scale_dev(cv_ctx *ctx, int64_t n, int cplx_, void *x, void *x2, int slot, int mode,
-                 cudaStream_t st);
+int cv_scale_dev(cv_ctx *ctx, int64_t n, int cplx_, void *x, int slot, int mode, cudaStream_t st);
+int cv_occ_grid(cv_ctx *ctx, const void *kernel, int64_t work_items, int items_per_cta);
 int cv_lincomb_launch(cv_ctx *ctx, int64_t n, int v_cplx, int c_cplx, int m, const void *const *v,
                       int ncol, const double *coef, int ldc, int col0, void *const *y, int norm_slot,
                       cudaStream_t st);

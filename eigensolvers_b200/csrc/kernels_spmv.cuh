@@ -92,13 +92,16 @@ __device__ __forceinline__ void spmv_reduce(const SpmvArgs<T> &a, T d_xy, double
 // 8 streaming loads + 4 gathers in flight.
 // ------------------------------------------------------------------------------------------
 template <typename T, bool HALO, bool EPI, bool DOTS>
-__global__ void __launch_bounds__(CV_BLOCK) k_spmv_sell(const __grid_constant__ SpmvArgs<T> a) {
+__global__ void __launch_bounds__(CV_BLOCK, sizeof(T) == 8 ? 8 : 5)
+    k_spmv_sell(const __grid_constant__ SpmvArgs<T> a) {
   const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (int64_t)blockIdx.x * CV_WARPS + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * CV_WARPS;
+  // 32-bit slice/row counters (rows < 2^31 because column indices are int32): fewer registers
+  const int warp0 = blockIdx.x * CV_WARPS + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * CV_WARPS;
+  const int n_slices = (int)a.n_slices;
   T d_xy = Num<T>::zero();
   double d_yy = 0.0;
-  for (int64_t s = warp0; s < a.n_slices; s += nwarps) {
+  for (int s = warp0; s < n_slices; s += nwarps) {
     const int64_t base = __ldg(a.slice_ptr + s);
     const int width = (int)((__ldg(a.slice_ptr + s + 1) - base) >> 5);
     const double *vp = a.sell_val + base + lane;
@@ -122,8 +125,8 @@ __global__ void __launch_bounds__(CV_BLOCK) k_spmv_sell(const __grid_constant__ 
       double v0 = ld_stream(vp + j * 32);
       Num<T>::fmar(acc0, v0, spmv_gather<T, HALO>(a, c0));
     }
-    const int64_t row = s * 32 + lane;
-    if (row < a.n_rows) spmv_finish_row<T, EPI, DOTS>(a, row, Num<T>::add(acc0, acc1), d_xy, d_yy);
+    const int row = s * 32 + lane;
+    if (row < (int)a.n_rows) spmv_finish_row<T, EPI, DOTS>(a, row, Num<T>::add(acc0, acc1), d_xy, d_yy);
   }
   spmv_reduce<T, DOTS>(a, d_xy, d_yy);
 }

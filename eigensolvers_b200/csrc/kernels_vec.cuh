@@ -1,10 +1,16 @@
 // kernels_vec.cuh — length-N vector kernels (BLAS-1 family, tall-skinny products, fused
 // Krylov updates).  All are HBM-bound streaming kernels: 16-byte loads, persistent
-// grid-stride grids (148 SMs x 8 CTAs x 256 threads), deterministic reductions.
+// grid-stride grids sized from the kernel's real occupancy, deterministic reductions.
 //
 // T is double or cplx.  Real vectors are processed W=2 elements per thread (one 128-bit
 // load); complex vectors W=1 (one complex128 = 128 bits).  The host wrapper falls back to
 // W=1 for real vectors whose pointers are not 16-byte aligned.
+//
+// Memory-level parallelism is explicit: every loop first issues ALL loads of an iteration
+// into registers (branch-free, full packs only) and only then does arithmetic; the odd tail
+// element of a W=2 run is handled once by thread 0 outside the loop.  (The first version
+// bounds-checked inside the pack load; ptxas then serialised load -> DFMA -> load and the
+// tall-skinny dot ran with ONE load in flight per thread: 4.6 TB/s, profiles/r1_notes.md.)
 #pragma once
 #include "common.cuh"
 
@@ -21,86 +27,141 @@ __device__ __forceinline__ Pack<T, W> pk_zero() {
   return p;
 }
 
-// STREAM=true: one-shot data (L1 no-allocate); false: plain loads
+// full pack load, no bounds check.  STREAM=true: one-shot data (L1 no-allocate)
 template <typename T, int W, bool STREAM>
-__device__ __forceinline__ Pack<T, W> pk_load(const T *base, int64_t ip, int64_t n) {
+__device__ __forceinline__ Pack<T, W> pk_ld(const T *base, int64_t ip) {
   Pack<T, W> p;
   if constexpr (W == 1) {
     p.e[0] = STREAM ? ld_stream(base + ip) : ld_plain(base + ip);
   } else {
     static_assert(W == 2 && sizeof(T) == 8, "W=2 is for double only");
-    int64_t i0 = ip * 2;
-    if (i0 + 2 <= n) {
-      double2 v = STREAM ? ld_stream2(reinterpret_cast<const double2 *>(base + i0))
-                         : *reinterpret_cast<const double2 *>(base + i0);
-      p.e[0] = v.x;
-      p.e[1] = v.y;
-    } else {
-      p.e[0] = (i0 < n) ? base[i0] : 0.0;
-      p.e[1] = 0.0;
-    }
+    double2 v = STREAM ? ld_stream2(reinterpret_cast<const double2 *>(base) + ip)
+                       : *(reinterpret_cast<const double2 *>(base) + ip);
+    p.e[0] = v.x;
+    p.e[1] = v.y;
   }
   return p;
 }
 
 template <typename T, int W>
-__device__ __forceinline__ void pk_store(T *base, int64_t ip, int64_t n, const Pack<T, W> &p) {
+__device__ __forceinline__ void pk_st(T *base, int64_t ip, const Pack<T, W> &p) {
   if constexpr (W == 1) {
     st_plain(base + ip, p.e[0]);
   } else {
-    int64_t i0 = ip * 2;
-    if (i0 + 2 <= n) {
-      *reinterpret_cast<double2 *>(base + i0) = make_double2(p.e[0], p.e[1]);
-    } else if (i0 < n) {
-      base[i0] = p.e[0];
-    }
+    *(reinterpret_cast<double2 *>(base) + ip) = make_double2(p.e[0], p.e[1]);
   }
 }
 
-__device__ __forceinline__ int64_t n_packs(int64_t n, int W) { return (n + W - 1) / W; }
+// loop bookkeeping shared by all kernels
+struct VecLoop {
+  int64_t npf;     // number of FULL packs
+  int64_t tid;     // global thread id
+  int64_t stride;  // threads in the grid
+  bool tail;       // this thread owns the odd last element (W=2, n odd)
+  int64_t itail;
+};
+template <int W>
+__device__ __forceinline__ VecLoop vec_loop(int64_t n) {
+  VecLoop L;
+  L.npf = n / W;
+  L.tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  L.stride = (int64_t)gridDim.x * blockDim.x;
+  L.tail = (W == 2) && (n & 1) && L.tid == 0;
+  L.itail = n - 1;
+  return L;
+}
 
 // ------------------------------------------------------------------------------------------
 // y = a * x   (TX in {double,cplx}, TA in {double,cplx}, TY = promoted type)
 // numpyVector.py:57-64 (__mul__, __rmul__, __truediv__)
 // ------------------------------------------------------------------------------------------
 template <typename TX, typename TA, typename TY>
-__global__ void __launch_bounds__(CV_BLOCK) k_scal(int64_t n, TA a, const TX *__restrict__ x,
-                                                   TY *__restrict__ y) {
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    TY acc = Num<TY>::zero();
-    cfma(acc, a, ld_stream(x + i));
-    st_plain(y + i, acc);
+__global__ void __launch_bounds__(CV_BLOCK, 8) k_scal(int64_t n, TA a, const TX *__restrict__ x,
+                                                      TY *__restrict__ y) {
+  constexpr int U = 4;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = tid; i0 < n; i0 += U * stride) {
+    TX v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int64_t i = i0 + u * stride;
+      v[u] = (i < n) ? ld_stream(x + i) : Num<TX>::zero();
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int64_t i = i0 + u * stride;
+      if (i < n) {
+        TY acc = Num<TY>::zero();
+        cfma(acc, a, v[u]);
+        st_plain(y + i, acc);
+      }
+    }
   }
 }
 
 // real-by-real scaling with 128-bit accesses
 template <int W>
-__global__ void __launch_bounds__(CV_BLOCK) k_scal_rr(int64_t n, double a,
-                                                      const double *__restrict__ x,
-                                                      double *__restrict__ y) {
-  int64_t np = n_packs(n, W), stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t ip = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ip < np; ip += stride) {
-    Pack<double, W> p = pk_load<double, W, true>(x, ip, n);
+__global__ void __launch_bounds__(CV_BLOCK, 8) k_scal_rr(int64_t n, double a,
+                                                         const double *__restrict__ x,
+                                                         double *__restrict__ y) {
+  constexpr int U = 4;
+  const VecLoop L = vec_loop<W>(n);
+  for (int64_t ip0 = L.tid; ip0 < L.npf; ip0 += U * L.stride) {
+    Pack<double, W> p[U];
 #pragma unroll
-    for (int k = 0; k < W; ++k) p.e[k] *= a;
-    pk_store<double, W>(y, ip, n, p);
+    for (int u = 0; u < U; ++u) {
+      int64_t ip = ip0 + u * L.stride;
+      p[u] = (ip < L.npf) ? pk_ld<double, W, true>(x, ip) : pk_zero<double, W>();
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int64_t ip = ip0 + u * L.stride;
+#pragma unroll
+      for (int k = 0; k < W; ++k) p[u].e[k] *= a;
+      if (ip < L.npf) pk_st<double, W>(y, ip, p[u]);
+    }
   }
+  if (L.tail) y[L.itail] = a * x[L.itail];
 }
 
 // y = Re(x)  /  y = conj(x)      numpyVector.py:83-87
-__global__ void __launch_bounds__(CV_BLOCK) k_real(int64_t n, const cplx *__restrict__ x,
-                                                   double *__restrict__ y) {
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    y[i] = ld_stream(x + i).re;
+static __global__ void __launch_bounds__(CV_BLOCK, 8) k_real(int64_t n, const cplx *__restrict__ x,
+                                                             double *__restrict__ y) {
+  constexpr int U = 4;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = tid; i0 < n; i0 += U * stride) {
+    cplx v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int64_t i = i0 + u * stride;
+      v[u] = (i < n) ? ld_stream(x + i) : make_cplx(0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int64_t i = i0 + u * stride;
+      if (i < n) y[i] = v[u].re;
+    }
+  }
 }
-__global__ void __launch_bounds__(CV_BLOCK) k_conj(int64_t n, const cplx *__restrict__ x,
-                                                   cplx *__restrict__ y) {
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    cplx v = ld_stream(x + i);
-    st_plain(y + i, make_cplx(v.re, -v.im));
+static __global__ void __launch_bounds__(CV_BLOCK, 8) k_conj(int64_t n, const cplx *__restrict__ x,
+                                                             cplx *__restrict__ y) {
+  constexpr int U = 4;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = tid; i0 < n; i0 += U * stride) {
+    cplx v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int64_t i = i0 + u * stride;
+      v[u] = (i < n) ? ld_stream(x + i) : make_cplx(0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int64_t i = i0 + u * stride;
+      if (i < n) st_plain(y + i, make_cplx(v[u].re, -v[u].im));
+    }
   }
 }
 
@@ -108,22 +169,32 @@ __global__ void __launch_bounds__(CV_BLOCK) k_conj(int64_t n, const cplx *__rest
 // out[0..NRED) = sum conj?(x) y     numpyVector.py:89-93 (vdot / dot)
 // ------------------------------------------------------------------------------------------
 template <typename T, int W, bool CONJ>
-__global__ void __launch_bounds__(CV_BLOCK) k_dot(int64_t n, const T *__restrict__ x,
-                                                  const T *__restrict__ y, double *partials,
-                                                  unsigned *counter, double *out) {
-  int64_t np = n_packs(n, W), stride = (int64_t)gridDim.x * blockDim.x;
+__global__ void __launch_bounds__(CV_BLOCK, 8) k_dot(int64_t n, const T *__restrict__ x,
+                                                     const T *__restrict__ y, double *partials,
+                                                     unsigned *counter, double *out) {
+  constexpr int U = 4;
+  const VecLoop L = vec_loop<W>(n);
   T acc = Num<T>::zero();
-  for (int64_t ip = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ip < np; ip += stride) {
-    Pack<T, W> a = pk_load<T, W, false>(x, ip, n);
-    Pack<T, W> b = pk_load<T, W, false>(y, ip, n);
+  for (int64_t ip0 = L.tid; ip0 < L.npf; ip0 += U * L.stride) {
+    Pack<T, W> a[U], b[U];
 #pragma unroll
-    for (int k = 0; k < W; ++k) {
-      if (CONJ)
-        Num<T>::fmac(acc, a.e[k], b.e[k]);
-      else
-        Num<T>::fma(acc, a.e[k], b.e[k]);
+    for (int u = 0; u < U; ++u) {
+      int64_t ip = ip0 + u * L.stride;
+      const bool ok = ip < L.npf;
+      a[u] = ok ? pk_ld<T, W, false>(x, ip) : pk_zero<T, W>();
+      b[u] = ok ? pk_ld<T, W, false>(y, ip) : pk_zero<T, W>();
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        if (CONJ)
+          Num<T>::fmac(acc, a[u].e[k], b[u].e[k]);
+        else
+          Num<T>::fma(acc, a[u].e[k], b[u].e[k]);
+      }
   }
+  if (L.tail) Num<T>::fma(acc, x[L.itail], y[L.itail]);  // W=2 is real: conj is the identity
   double vals[Num<T>::NRED];
   Num<T>::to_red(acc, vals);
   grid_reduce<Num<T>::NRED>(vals, partials, counter, out, gridDim.x, blockIdx.x);
@@ -131,16 +202,25 @@ __global__ void __launch_bounds__(CV_BLOCK) k_dot(int64_t n, const T *__restrict
 
 // out[0] = sum |x|^2
 template <typename T, int W>
-__global__ void __launch_bounds__(CV_BLOCK) k_nrm2sq(int64_t n, const T *__restrict__ x,
-                                                     double *partials, unsigned *counter,
-                                                     double *out) {
-  int64_t np = n_packs(n, W), stride = (int64_t)gridDim.x * blockDim.x;
+__global__ void __launch_bounds__(CV_BLOCK, 8) k_nrm2sq(int64_t n, const T *__restrict__ x,
+                                                        double *partials, unsigned *counter,
+                                                        double *out) {
+  constexpr int U = 8;
+  const VecLoop L = vec_loop<W>(n);
   double acc = 0.0;
-  for (int64_t ip = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ip < np; ip += stride) {
-    Pack<T, W> a = pk_load<T, W, false>(x, ip, n);
+  for (int64_t ip0 = L.tid; ip0 < L.npf; ip0 += U * L.stride) {
+    Pack<T, W> a[U];
 #pragma unroll
-    for (int k = 0; k < W; ++k) acc += Num<T>::abs2(a.e[k]);
+    for (int u = 0; u < U; ++u) {
+      int64_t ip = ip0 + u * L.stride;
+      a[u] = (ip < L.npf) ? pk_ld<T, W, false>(x, ip) : pk_zero<T, W>();
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int k = 0; k < W; ++k) acc += Num<T>::abs2(a[u].e[k]);
   }
+  if (L.tail) acc += Num<T>::abs2(x[L.itail]);
   double vals[1] = {acc};
   grid_reduce<1>(vals, partials, counter, out, gridDim.x, blockIdx.x);
 }
@@ -149,27 +229,30 @@ __global__ void __launch_bounds__(CV_BLOCK) k_nrm2sq(int64_t n, const T *__restr
 // x *= f(s) with s a DEVICE scalar produced by an earlier reduction (no host round trip).
 //   MODE 0: f = 1/sqrt(s)   (normalise by a squared norm)
 //   MODE 1: f = 1/sqrt(s) if that is finite, else 1   (scipy _fgmres: "if isfinite(alpha)")
-// optional second vector x2 gets the same factor (GCROT scales cx and ux together).
 // ------------------------------------------------------------------------------------------
 template <typename T, int W, int MODE>
-__global__ void __launch_bounds__(CV_BLOCK) k_scale_dev(int64_t n, T *__restrict__ x,
-                                                        T *__restrict__ x2,
-                                                        const double *__restrict__ s) {
+__global__ void __launch_bounds__(CV_BLOCK, 8) k_scale_dev(int64_t n, T *__restrict__ x,
+                                                           const double *__restrict__ s) {
+  constexpr int U = 4;
   double f = 1.0 / sqrt(__ldcg(s));
   if (MODE == 1 && !isfinite(f)) f = 1.0;
-  int64_t np = n_packs(n, W), stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t ip = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ip < np; ip += stride) {
-    Pack<T, W> a = pk_load<T, W, false>(x, ip, n);
+  const VecLoop L = vec_loop<W>(n);
+  for (int64_t ip0 = L.tid; ip0 < L.npf; ip0 += U * L.stride) {
+    Pack<T, W> a[U];
 #pragma unroll
-    for (int k = 0; k < W; ++k) a.e[k] = Num<T>::scale(a.e[k], f);
-    pk_store<T, W>(x, ip, n, a);
-    if (x2) {
-      Pack<T, W> b = pk_load<T, W, false>(x2, ip, n);
+    for (int u = 0; u < U; ++u) {
+      int64_t ip = ip0 + u * L.stride;
+      a[u] = (ip < L.npf) ? pk_ld<T, W, false>(x, ip) : pk_zero<T, W>();
+    }
 #pragma unroll
-      for (int k = 0; k < W; ++k) b.e[k] = Num<T>::scale(b.e[k], f);
-      pk_store<T, W>(x2, ip, n, b);
+    for (int u = 0; u < U; ++u) {
+      int64_t ip = ip0 + u * L.stride;
+#pragma unroll
+      for (int k = 0; k < W; ++k) a[u].e[k] = Num<T>::scale(a[u].e[k], f);
+      if (ip < L.npf) pk_st<T, W>(x, ip, a[u]);
     }
   }
+  if (L.tail) x[L.itail] = Num<T>::scale(x[L.itail], f);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -201,32 +284,50 @@ template <typename TV, typename TC, typename TY, int W, int NC, bool NORM>
 __global__ void __launch_bounds__(CV_BLOCK)
     k_lincomb(const __grid_constant__ LcParams p, double *partials, unsigned *counter,
               double *out_norm) {
+  constexpr int JB = 4;  // inputs loaded per batch
   const int64_t n = p.n;
-  int64_t np = n_packs(n, W), stride = (int64_t)gridDim.x * blockDim.x;
+  const VecLoop L = vec_loop<W>(n);
   double nrm[NC];
 #pragma unroll
   for (int k = 0; k < NC; ++k) nrm[k] = 0.0;
-  for (int64_t ip = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ip < np; ip += stride) {
+  for (int64_t ip = L.tid; ip < L.npf; ip += L.stride) {
     Pack<TY, W> acc[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) acc[k] = pk_zero<TY, W>();
-#pragma unroll 4
-    for (int j = 0; j < p.m; ++j) {
-      Pack<TV, W> v = pk_load<TV, W, false>(static_cast<const TV *>(p.v[j]), ip, n);
+    for (int j0 = 0; j0 < p.m; j0 += JB) {
+      Pack<TV, W> v[JB];
 #pragma unroll
-      for (int k = 0; k < NC; ++k) {
-        TC c = lc_coef<TC>(p, j, k);
+      for (int jj = 0; jj < JB; ++jj)
+        v[jj] = (j0 + jj < p.m) ? pk_ld<TV, W, false>(static_cast<const TV *>(p.v[j0 + jj]), ip)
+                                : pk_zero<TV, W>();
 #pragma unroll
-        for (int w = 0; w < W; ++w) cfma(acc[k].e[w], c, v.e[w]);
+      for (int jj = 0; jj < JB; ++jj) {
+        if (j0 + jj < p.m) {
+#pragma unroll
+          for (int k = 0; k < NC; ++k) {
+            TC c = lc_coef<TC>(p, j0 + jj, k);
+#pragma unroll
+            for (int w = 0; w < W; ++w) cfma(acc[k].e[w], c, v[jj].e[w]);
+          }
+        }
       }
     }
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-      pk_store<TY, W>(static_cast<TY *>(p.y[k]), ip, n, acc[k]);
+      pk_st<TY, W>(static_cast<TY *>(p.y[k]), ip, acc[k]);
       if (NORM) {
 #pragma unroll
         for (int w = 0; w < W; ++w) nrm[k] += Num<TY>::abs2(acc[k].e[w]);
       }
+    }
+  }
+  if (L.tail) {
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      TY acc = Num<TY>::zero();
+      for (int j = 0; j < p.m; ++j) cfma(acc, lc_coef<TC>(p, j, k), static_cast<const TV *>(p.v[j])[L.itail]);
+      static_cast<TY *>(p.y[k])[L.itail] = acc;
+      if (NORM) nrm[k] += Num<TY>::abs2(acc);
     }
   }
   if (NORM) grid_reduce<NC>(nrm, partials, counter, out_norm, gridDim.x, blockIdx.x);
@@ -237,7 +338,8 @@ __global__ void __launch_bounds__(CV_BLOCK)
 // overlapMatrix / matrixRepresentation / extend* (numpyVector.py:180-238), pick
 // (util_funcs.py:321-322), GCROT's orthogonalisation coefficients (_gcrotmk.py:117-128).
 // grid = (gx, ceil(m/MI)); CTA (bx,by) handles vectors by*MI .. by*MI+MI-1 for its rows, so W
-// is re-read ceil(m/MI) times and V exactly once.
+// is re-read ceil(m/MI) times and V exactly once.  The MI loads of an iteration are issued
+// LB at a time into registers before any arithmetic.
 // ------------------------------------------------------------------------------------------
 struct TsParams {
   const void *v[CV_MAX_PTRS];
@@ -247,17 +349,19 @@ struct TsParams {
 };
 
 template <typename T, int W, bool CONJ, int MI, int B>
-__global__ void __launch_bounds__(CV_BLOCK)
-    k_tsdot(const __grid_constant__ TsParams p, const double *__restrict__ gate, double *partials,
-            unsigned *counters, double *out /* [m*B*NRED] as ((i*B + k)*NRED + c) */) {
+__global__ void __launch_bounds__(CV_BLOCK, 3)
+    k_tsdot(const __grid_constant__ TsParams p, const double *__restrict__ gate, double eta2,
+            double *partials, unsigned *counters,
+            double *out /* [m*B*NRED] as ((i*B + k)*NRED + c) */) {
   constexpr int NR = Num<T>::NRED;
+  constexpr int LB = MI < 8 ? MI : 8;  // loads per batch
   const int64_t n = p.n;
   const int i0 = blockIdx.y * MI;
   const int mi = min(MI, p.m - i0);
   // Selective re-orthogonalisation (Daniel-Gragg-Kaufman-Stewart): gate = {|w|^2 before,
-  // |w'|^2 after the first projection}.  If the first pass removed less than half of the
-  // squared norm there was no cancellation and the second pass is skipped: result = 0.
-  if (gate && __ldcg(gate + 1) >= 0.5 * __ldcg(gate)) {
+  // |w'|^2 after the first projection}.  If the first pass kept at least eta^2 of the squared
+  // norm there was no harmful cancellation and the second pass is skipped: result = 0.
+  if (gate && __ldcg(gate + 1) >= eta2 * __ldcg(gate)) {
     if (blockIdx.x == 0)
       for (int v = threadIdx.x; v < mi * B * NR; v += blockDim.x) out[(size_t)i0 * B * NR + v] = 0.0;
     return;
@@ -268,26 +372,36 @@ __global__ void __launch_bounds__(CV_BLOCK)
 #pragma unroll
     for (int k = 0; k < B; ++k) acc[i][k] = Num<T>::zero();
 
-  int64_t np = n_packs(n, W), stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t ip = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ip < np; ip += stride) {
+  const VecLoop L = vec_loop<W>(n);
+  for (int64_t ip = L.tid; ip < L.npf; ip += L.stride) {
     Pack<T, W> wv[B];
 #pragma unroll
-    for (int k = 0; k < B; ++k) wv[k] = pk_load<T, W, false>(static_cast<const T *>(p.w[k]), ip, n);
+    for (int k = 0; k < B; ++k) wv[k] = pk_ld<T, W, false>(static_cast<const T *>(p.w[k]), ip);
 #pragma unroll
-    for (int i = 0; i < MI; ++i) {
-      if (i < mi) {
-        Pack<T, W> vv = pk_load<T, W, false>(static_cast<const T *>(p.v[i0 + i]), ip, n);
+    for (int ib = 0; ib < MI; ib += LB) {
+      Pack<T, W> vv[LB];
+#pragma unroll
+      for (int l = 0; l < LB; ++l)
+        vv[l] = (ib + l < mi) ? pk_ld<T, W, false>(static_cast<const T *>(p.v[i0 + ib + l]), ip)
+                              : pk_zero<T, W>();
+#pragma unroll
+      for (int l = 0; l < LB; ++l)
 #pragma unroll
         for (int k = 0; k < B; ++k)
 #pragma unroll
           for (int w = 0; w < W; ++w) {
             if (CONJ)
-              Num<T>::fmac(acc[i][k], vv.e[w], wv[k].e[w]);
+              Num<T>::fmac(acc[ib + l][k], vv[l].e[w], wv[k].e[w]);
             else
-              Num<T>::fma(acc[i][k], vv.e[w], wv[k].e[w]);
+              Num<T>::fma(acc[ib + l][k], vv[l].e[w], wv[k].e[w]);
           }
-      }
     }
+  }
+  if (L.tail) {
+    for (int i = 0; i < mi; ++i)
+      for (int k = 0; k < B; ++k)
+        Num<T>::fma(acc[i][k], static_cast<const T *>(p.v[i0 + i])[L.itail],
+                    static_cast<const T *>(p.w[k])[L.itail]);
   }
   // CTA reduction of MI*B*NR doubles
   __shared__ double s_part[CV_WARPS][MI * B * NR];
@@ -325,34 +439,49 @@ __global__ void __launch_bounds__(CV_BLOCK)
 template <typename T, int W, bool NORM>
 __global__ void __launch_bounds__(CV_BLOCK)
     k_tsupdate(const __grid_constant__ TsParams p, const double *__restrict__ h,
-               const double *__restrict__ gate, T *__restrict__ wvec, double *partials,
-               unsigned *counter, double *out_norm) {
+               const double *__restrict__ gate, double eta2, T *__restrict__ wvec,
+               double *partials, unsigned *counter, double *out_norm) {
   extern __shared__ double s_h[];  // m * NRED doubles
   constexpr int NR = Num<T>::NRED;
-  if (gate && __ldcg(gate + 1) >= 0.5 * __ldcg(gate)) {  // second pass skipped (see k_tsdot)
+  constexpr int JB = 8;
+  if (gate && __ldcg(gate + 1) >= eta2 * __ldcg(gate)) {  // second pass skipped (see k_tsdot)
     if (NORM && blockIdx.x == 0 && threadIdx.x == 0) out_norm[0] = __ldcg(gate + 1);
     return;
   }
-  for (int j = threadIdx.x; j < p.m * NR; j += blockDim.x) s_h[j] = __ldcg(h + j);
+  for (int j = threadIdx.x; j < p.m * NR; j += blockDim.x) s_h[j] = -__ldcg(h + j);
   __syncthreads();
   const int64_t n = p.n;
-  int64_t np = n_packs(n, W), stride = (int64_t)gridDim.x * blockDim.x;
+  const VecLoop L = vec_loop<W>(n);
   double nrm[1] = {0.0};
-  for (int64_t ip = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ip < np; ip += stride) {
-    Pack<T, W> acc = pk_load<T, W, false>(wvec, ip, n);
-#pragma unroll 4
-    for (int j = 0; j < p.m; ++j) {
-      Pack<T, W> v = pk_load<T, W, false>(static_cast<const T *>(p.v[j]), ip, n);
-      T c = Num<T>::from_red(s_h + j * NR);
-      T mc = Num<T>::sub(Num<T>::zero(), c);
+  for (int64_t ip = L.tid; ip < L.npf; ip += L.stride) {
+    Pack<T, W> acc = pk_ld<T, W, false>(wvec, ip);
+    for (int j0 = 0; j0 < p.m; j0 += JB) {
+      Pack<T, W> v[JB];
 #pragma unroll
-      for (int w = 0; w < W; ++w) Num<T>::fma(acc.e[w], mc, v.e[w]);
+      for (int jj = 0; jj < JB; ++jj)
+        v[jj] = (j0 + jj < p.m) ? pk_ld<T, W, false>(static_cast<const T *>(p.v[j0 + jj]), ip)
+                                : pk_zero<T, W>();
+#pragma unroll
+      for (int jj = 0; jj < JB; ++jj) {
+        if (j0 + jj < p.m) {
+          T mc = Num<T>::from_red(s_h + (j0 + jj) * NR);
+#pragma unroll
+          for (int w = 0; w < W; ++w) Num<T>::fma(acc.e[w], mc, v[jj].e[w]);
+        }
+      }
     }
-    pk_store<T, W>(wvec, ip, n, acc);
+    pk_st<T, W>(wvec, ip, acc);
     if (NORM) {
 #pragma unroll
       for (int w = 0; w < W; ++w) nrm[0] += Num<T>::abs2(acc.e[w]);
     }
+  }
+  if (L.tail) {
+    T acc = wvec[L.itail];
+    for (int j = 0; j < p.m; ++j)
+      Num<T>::fma(acc, Num<T>::from_red(s_h + j * NR), static_cast<const T *>(p.v[j])[L.itail]);
+    wvec[L.itail] = acc;
+    if (NORM) nrm[0] += Num<T>::abs2(acc);
   }
   if (NORM) grid_reduce<1>(nrm, partials, counter, out_norm, gridDim.x, blockIdx.x);
 }
@@ -365,11 +494,12 @@ __global__ void __launch_bounds__(CV_BLOCK)
 // Coefficients stay in device memory; the host reads only the final innerprod.
 // ------------------------------------------------------------------------------------------
 template <typename T, int W>
-__global__ void __launch_bounds__(CV_BLOCK)
+__global__ void __launch_bounds__(CV_BLOCK, 6)
     k_mgs_step(int64_t n, const T *__restrict__ x_in, T *__restrict__ x_out,
                const T *__restrict__ q_prev, const double *__restrict__ t_prev,
                const T *__restrict__ q_cur, double *partials, unsigned *counter, double *t_out) {
   constexpr int NR = Num<T>::NRED;
+  constexpr int U = 2;
   T coef = Num<T>::zero();
   if (q_prev) {
     // c = t1/t2 (complex division for complex data)
@@ -381,27 +511,45 @@ __global__ void __launch_bounds__(CV_BLOCK)
       coef = make_cplx((t1.re * t2.re + t1.im * t2.im) / d, (t1.im * t2.re - t1.re * t2.im) / d);
     }
   }
-  T mc = Num<T>::sub(Num<T>::zero(), coef);
+  const T mc = Num<T>::sub(Num<T>::zero(), coef);
   T a1 = Num<T>::zero(), a2 = Num<T>::zero();
-  int64_t np = n_packs(n, W), stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t ip = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ip < np; ip += stride) {
-    Pack<T, W> x = pk_load<T, W, false>(x_in, ip, n);
-    if (q_prev) {
-      Pack<T, W> qp = pk_load<T, W, false>(q_prev, ip, n);
+  const bool store = q_prev || x_out != x_in;
+  const VecLoop L = vec_loop<W>(n);
+  for (int64_t ip0 = L.tid; ip0 < L.npf; ip0 += U * L.stride) {
+    Pack<T, W> x[U], qp[U], qc[U];
 #pragma unroll
-      for (int w = 0; w < W; ++w) Num<T>::fma(x.e[w], mc, qp.e[w]);
+    for (int u = 0; u < U; ++u) {
+      int64_t ip = ip0 + u * L.stride;
+      const bool ok = ip < L.npf;
+      x[u] = ok ? pk_ld<T, W, false>(x_in, ip) : pk_zero<T, W>();
+      qp[u] = (ok && q_prev) ? pk_ld<T, W, false>(q_prev, ip) : pk_zero<T, W>();
+      qc[u] = (ok && q_cur) ? pk_ld<T, W, false>(q_cur, ip) : pk_zero<T, W>();
     }
-    if (q_prev || x_out != x_in) pk_store<T, W>(x_out, ip, n, x);
-    if (q_cur) {
-      Pack<T, W> qc = pk_load<T, W, false>(q_cur, ip, n);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int64_t ip = ip0 + u * L.stride;
 #pragma unroll
       for (int w = 0; w < W; ++w) {
-        Num<T>::fma(a1, x.e[w], qc.e[w]);
-        Num<T>::fma(a2, qc.e[w], qc.e[w]);
+        Num<T>::fma(x[u].e[w], mc, qp[u].e[w]);
+        if (q_cur) {
+          Num<T>::fma(a1, x[u].e[w], qc[u].e[w]);
+          Num<T>::fma(a2, qc[u].e[w], qc[u].e[w]);
+        } else {
+          Num<T>::fma(a1, x[u].e[w], x[u].e[w]);
+        }
       }
+      if (store && ip < L.npf) pk_st<T, W>(x_out, ip, x[u]);
+    }
+  }
+  if (L.tail) {
+    T x = x_in[L.itail];
+    if (q_prev) Num<T>::fma(x, mc, q_prev[L.itail]);
+    if (store) x_out[L.itail] = x;
+    if (q_cur) {
+      Num<T>::fma(a1, x, q_cur[L.itail]);
+      Num<T>::fma(a2, q_cur[L.itail], q_cur[L.itail]);
     } else {
-#pragma unroll
-      for (int w = 0; w < W; ++w) Num<T>::fma(a1, x.e[w], x.e[w]);
+      Num<T>::fma(a1, x, x);
     }
   }
   double vals[2 * NR];
@@ -412,7 +560,7 @@ __global__ void __launch_bounds__(CV_BLOCK)
 
 // x *= 1/sqrt(s) for complex s (np.sqrt of a complex innerprod, numpyVector.py:142).
 // For real data MODE 0 of k_scale_dev is used instead.
-__global__ void __launch_bounds__(CV_BLOCK)
+static __global__ void __launch_bounds__(CV_BLOCK)
     k_div_csqrt(int64_t n, cplx *__restrict__ x, const double *__restrict__ s) {
   // principal square root of s = (sr, si), then 1/sqrt
   double sr = __ldcg(s), si = __ldcg(s + 1);
@@ -430,20 +578,37 @@ __global__ void __launch_bounds__(CV_BLOCK)
 // beta^2 = r2.r2 in one pass (minres.py:222-228).
 // ------------------------------------------------------------------------------------------
 template <typename T, int W, bool NORM>
-__global__ void __launch_bounds__(CV_BLOCK)
+__global__ void __launch_bounds__(CV_BLOCK, 8)
     k_axpy_norm(int64_t n, T a, const T *__restrict__ x, T *__restrict__ y, double *partials,
                 unsigned *counter, double *out) {
-  int64_t np = n_packs(n, W), stride = (int64_t)gridDim.x * blockDim.x;
+  constexpr int U = 2;
+  const VecLoop L = vec_loop<W>(n);
   double nrm[1] = {0.0};
-  for (int64_t ip = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ip < np; ip += stride) {
-    Pack<T, W> xv = pk_load<T, W, false>(x, ip, n);
-    Pack<T, W> yv = pk_load<T, W, false>(y, ip, n);
+  for (int64_t ip0 = L.tid; ip0 < L.npf; ip0 += U * L.stride) {
+    Pack<T, W> xv[U], yv[U];
 #pragma unroll
-    for (int w = 0; w < W; ++w) {
-      Num<T>::fma(yv.e[w], a, xv.e[w]);
-      if (NORM) nrm[0] += Num<T>::abs2(yv.e[w]);
+    for (int u = 0; u < U; ++u) {
+      int64_t ip = ip0 + u * L.stride;
+      const bool ok = ip < L.npf;
+      xv[u] = ok ? pk_ld<T, W, false>(x, ip) : pk_zero<T, W>();
+      yv[u] = ok ? pk_ld<T, W, false>(y, ip) : pk_zero<T, W>();
     }
-    pk_store<T, W>(y, ip, n, yv);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int64_t ip = ip0 + u * L.stride;
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        Num<T>::fma(yv[u].e[w], a, xv[u].e[w]);
+        if (NORM) nrm[0] += Num<T>::abs2(yv[u].e[w]);
+      }
+      if (ip < L.npf) pk_st<T, W>(y, ip, yv[u]);
+    }
+  }
+  if (L.tail) {
+    T v = y[L.itail];
+    Num<T>::fma(v, a, x[L.itail]);
+    y[L.itail] = v;
+    if (NORM) nrm[0] += Num<T>::abs2(v);
   }
   if (NORM) grid_reduce<1>(nrm, partials, counter, out, gridDim.x, blockIdx.x);
 }
@@ -462,23 +627,31 @@ __global__ void __launch_bounds__(CV_BLOCK)
   double gv[NR];
 #pragma unroll
   for (int c = 0; c < NR; ++c) gv[c] = __ldcg(g + c);
-  T gamma = Num<T>::from_red(gv);
-  T mgamma = Num<T>::sub(Num<T>::zero(), gamma);
-  int64_t np = n_packs(n, W), stride = (int64_t)gridDim.x * blockDim.x;
+  const T gamma = Num<T>::from_red(gv);
+  const T mgamma = Num<T>::sub(Num<T>::zero(), gamma);
+  const VecLoop L = vec_loop<W>(n);
   double nrm[1] = {0.0};
-  for (int64_t ip = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ip < np; ip += stride) {
-    Pack<T, W> c = pk_load<T, W, false>(cx, ip, n);
-    Pack<T, W> u = pk_load<T, W, false>(ux, ip, n);
-    Pack<T, W> rv = pk_load<T, W, false>(r, ip, n);
-    Pack<T, W> xv = pk_load<T, W, false>(x, ip, n);
+  for (int64_t ip = L.tid; ip < L.npf; ip += L.stride) {
+    Pack<T, W> c = pk_ld<T, W, false>(cx, ip);
+    Pack<T, W> u = pk_ld<T, W, false>(ux, ip);
+    Pack<T, W> rv = pk_ld<T, W, false>(r, ip);
+    Pack<T, W> xv = pk_ld<T, W, false>(x, ip);
 #pragma unroll
     for (int w = 0; w < W; ++w) {
       Num<T>::fma(rv.e[w], mgamma, c.e[w]);
       Num<T>::fma(xv.e[w], gamma, u.e[w]);
       nrm[0] += Num<T>::abs2(rv.e[w]);
     }
-    pk_store<T, W>(r, ip, n, rv);
-    pk_store<T, W>(x, ip, n, xv);
+    pk_st<T, W>(r, ip, rv);
+    pk_st<T, W>(x, ip, xv);
+  }
+  if (L.tail) {
+    T rv = r[L.itail], xv = x[L.itail];
+    Num<T>::fma(rv, mgamma, cx[L.itail]);
+    Num<T>::fma(xv, gamma, ux[L.itail]);
+    r[L.itail] = rv;
+    x[L.itail] = xv;
+    nrm[0] += Num<T>::abs2(rv);
   }
   grid_reduce<1>(nrm, partials, counter, out, gridDim.x, blockIdx.x);
 }
@@ -491,20 +664,26 @@ __global__ void __launch_bounds__(CV_BLOCK)
                       T *__restrict__ ux, const T *__restrict__ r, double *partials,
                       unsigned *counter, double *out) {
   const double f = 1.0 / sqrt(__ldcg(s));
-  int64_t np = n_packs(n, W), stride = (int64_t)gridDim.x * blockDim.x;
+  const VecLoop L = vec_loop<W>(n);
   T acc = Num<T>::zero();
-  for (int64_t ip = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ip < np; ip += stride) {
-    Pack<T, W> c = pk_load<T, W, false>(cx, ip, n);
-    Pack<T, W> u = pk_load<T, W, false>(ux, ip, n);
-    Pack<T, W> rv = pk_load<T, W, false>(r, ip, n);
+  for (int64_t ip = L.tid; ip < L.npf; ip += L.stride) {
+    Pack<T, W> c = pk_ld<T, W, false>(cx, ip);
+    Pack<T, W> u = pk_ld<T, W, false>(ux, ip);
+    Pack<T, W> rv = pk_ld<T, W, false>(r, ip);
 #pragma unroll
     for (int w = 0; w < W; ++w) {
       c.e[w] = Num<T>::scale(c.e[w], f);
       u.e[w] = Num<T>::scale(u.e[w], f);
       Num<T>::fmac(acc, c.e[w], rv.e[w]);
     }
-    pk_store<T, W>(cx, ip, n, c);
-    pk_store<T, W>(ux, ip, n, u);
+    pk_st<T, W>(cx, ip, c);
+    pk_st<T, W>(ux, ip, u);
+  }
+  if (L.tail) {
+    T c = Num<T>::scale(cx[L.itail], f), u = Num<T>::scale(ux[L.itail], f);
+    cx[L.itail] = c;
+    ux[L.itail] = u;
+    Num<T>::fmac(acc, c, r[L.itail]);
   }
   double vals[Num<T>::NRED];
   Num<T>::to_red(acc, vals);
@@ -523,13 +702,13 @@ __global__ void __launch_bounds__(CV_BLOCK)
                     const double *__restrict__ vsrc, double *__restrict__ w1,
                     const double *__restrict__ w2, double *__restrict__ x, double *partials,
                     unsigned *counter, double *out) {
-  int64_t np = n_packs(n, W), stride = (int64_t)gridDim.x * blockDim.x;
+  const VecLoop L = vec_loop<W>(n);
   double nrm[1] = {0.0};
-  for (int64_t ip = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ip < np; ip += stride) {
-    Pack<double, W> v = pk_load<double, W, false>(vsrc, ip, n);
-    Pack<double, W> a = pk_load<double, W, false>(w1, ip, n);
-    Pack<double, W> b = pk_load<double, W, false>(w2, ip, n);
-    Pack<double, W> xv = pk_load<double, W, false>(x, ip, n);
+  for (int64_t ip = L.tid; ip < L.npf; ip += L.stride) {
+    Pack<double, W> v = pk_ld<double, W, false>(vsrc, ip);
+    Pack<double, W> a = pk_ld<double, W, false>(w1, ip);
+    Pack<double, W> b = pk_ld<double, W, false>(w2, ip);
+    Pack<double, W> xv = pk_ld<double, W, false>(x, ip);
 #pragma unroll
     for (int w = 0; w < W; ++w) {
       // same association as the reference expression (v - oldeps*w1 - delta*w2) * denom
@@ -538,8 +717,15 @@ __global__ void __launch_bounds__(CV_BLOCK)
       xv.e[w] = xv.e[w] + phi * wn;
       nrm[0] += xv.e[w] * xv.e[w];
     }
-    pk_store<double, W>(w1, ip, n, a);
-    pk_store<double, W>(x, ip, n, xv);
+    pk_st<double, W>(w1, ip, a);
+    pk_st<double, W>(x, ip, xv);
+  }
+  if (L.tail) {
+    const int64_t i = L.itail;
+    double wn = ((s * vsrc[i] - oldeps * w1[i]) - delta * w2[i]) * denom;
+    w1[i] = wn;
+    x[i] = x[i] + phi * wn;
+    nrm[0] += x[i] * x[i];
   }
   grid_reduce<1>(nrm, partials, counter, out, gridDim.x, blockIdx.x);
 }

@@ -152,7 +152,7 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
       CV_TRY(cv_tsupdate_dev(ctx, n, cplx_, nb, basis.data(), S_H1, w, S_GATE + 1, st));
       CV_TRY(cv_tsdot_dev(ctx, n, cplx_, 1, nb, basis.data(), 1, wp, S_H2, st, S_GATE));
       CV_TRY(cv_tsupdate_dev(ctx, n, cplx_, nb, basis.data(), S_H2, w, S_NRM, st, S_GATE));
-      CV_TRY(cv_scale_dev(ctx, n, cplx_, w, nullptr, S_NRM, 1, st));
+      CV_TRY(cv_scale_dev(ctx, n, cplx_, w, S_NRM, 1, st));
       CV_TRY(cv_fetch_scalars(ctx, S_W, S_H2 + nb * NR - S_W, st));
       stats->n_sync++;
       const double w_norm = sqrt(mb[S_W + 2]);
@@ -273,7 +273,9 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
     // cx, ux *= alpha; gamma = <cx|r>; r -= gamma cx; x += gamma ux; beta = |r|
     {
       const int W = cplx_ ? 1 : 2;
-      int grid = cv_grid_for(ctx, (n + W - 1) / W, CV_BLOCK);
+      int grid = cplx_ ? cv_occ_grid(ctx, (const void *)k_gcrot_update<cplx, 1>, n / W + 1, CV_BLOCK)
+                       : cv_occ_grid(ctx, (const void *)k_gcrot_update<double, 2>, n / W + 1, CV_BLOCK);
+      cv_prof_scope prof(ctx, 3, st);
       if (cplx_) {
         k_gcrot_scale_dot<cplx, 1><<<grid, CV_BLOCK, 0, st>>>(n, ctx->scalars + S_CX + 1, (cplx *)Cs(slot_new),
                                                              (cplx *)Us(slot_new), (const cplx *)r,
@@ -325,7 +327,8 @@ int minres(cv_ctx *ctx, cv_op *op, int mode, double sigma, const double *b, cons
   double *rbuf[3] = {(double *)ws.vec(0), (double *)ws.vec(1), (double *)ws.vec(2)};
   double *wbuf[2] = {(double *)ws.vec(3), (double *)ws.vec(4)};
   const int W = ((uintptr_t)x & 15) ? 1 : 2;
-  const int grid = cv_grid_for(ctx, (n + W - 1) / W, CV_BLOCK);
+  const int grid = W == 2 ? cv_occ_grid(ctx, (const void *)k_minres_update<2>, n / W + 1, CV_BLOCK)
+                          : cv_occ_grid(ctx, (const void *)k_minres_update<1>, n / W + 1, CV_BLOCK);
 
   double *r1 = rbuf[0], *r2 = rbuf[0], *ynew = rbuf[1], *spare = rbuf[2];
   if (x0) {
