@@ -47,6 +47,7 @@ extern "C" int cv_ctx_create(int device, void *scratch_dev, size_t scratch_bytes
   c->launches = 0;
   c->prof = nullptr;
   c->reorth_eta = 0.1;
+  c->defer_reduce = false;
   c->comm = nullptr;
   c->rank = 0;
   c->world = 1;
@@ -558,8 +559,8 @@ int cv_tsupdate_dev(cv_ctx *ctx, int64_t n, int cplx_, int m, const void *const 
 #define TSU(T, WW, NM)                                                                             \
   do {                                                                                             \
     auto kf = k_tsupdate<T, WW, NM>;                                                               \
-    kf<<<CV_KGRID(kf, n / WW + 1), CV_BLOCK, sh, st>>>(p, h, gate, eta2, (T *)w, ctx->partials,     \
-                                                       ctx->counters, on);                        \
+    kf<<<CV_KGRID(kf, n / WW + 1), CV_BLOCK, sh, st>>>(p, h, gate, eta2, ctx->rank == 0 ? 1.0 : 0.0, \
+                                                       (T *)w, ctx->partials, ctx->counters, on);  \
   } while (0)
     if (cplx_) {
       if (on) TSU(cplx, 1, true); else TSU(cplx, 1, false);

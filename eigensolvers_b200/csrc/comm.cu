@@ -121,7 +121,7 @@ extern "C" int cv_comm_allreduce(cv_ctx *ctx, double *buf_dev, int count, void *
 }
 
 int cv_reduce_ranks(cv_ctx *ctx, int offset, int count, cudaStream_t st) {
-  if (ctx->world == 1) return CV_OK;
+  if (ctx->world == 1 || ctx->defer_reduce) return CV_OK;
   return cv_comm_allreduce(ctx, ctx->scalars + offset, count, (void *)st);
 }
 

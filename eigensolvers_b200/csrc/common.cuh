@@ -87,6 +87,7 @@ struct cv_ctx {
   // norm (Daniel-Gragg-Kaufman-Stewart); eta = 1/sqrt(2) is the classic value, 0.1 keeps the
   // basis orthogonal to ~10 eps while skipping the second pass in all but cancelling steps
   double reorth_eta;
+  bool defer_reduce;  // solvers batch several reductions into one all-reduce
 };
 
 // RAII bracket: records an event pair around the launches issued inside its scope

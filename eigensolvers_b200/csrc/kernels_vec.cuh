@@ -439,13 +439,15 @@ __global__ void __launch_bounds__(CV_BLOCK, 3)
 template <typename T, int W, bool NORM>
 __global__ void __launch_bounds__(CV_BLOCK)
     k_tsupdate(const __grid_constant__ TsParams p, const double *__restrict__ h,
-               const double *__restrict__ gate, double eta2, T *__restrict__ wvec,
-               double *partials, unsigned *counter, double *out_norm) {
+               const double *__restrict__ gate, double eta2, double skip_scale,
+               T *__restrict__ wvec, double *partials, unsigned *counter, double *out_norm) {
   extern __shared__ double s_h[];  // m * NRED doubles
   constexpr int NR = Num<T>::NRED;
   constexpr int JB = 8;
   if (gate && __ldcg(gate + 1) >= eta2 * __ldcg(gate)) {  // second pass skipped (see k_tsdot)
-    if (NORM && blockIdx.x == 0 && threadIdx.x == 0) out_norm[0] = __ldcg(gate + 1);
+    // the value is already summed over ranks; the all-reduce that follows must not count it
+    // once per rank: rank 0 contributes it (skip_scale 1), the others contribute 0
+    if (NORM && blockIdx.x == 0 && threadIdx.x == 0) out_norm[0] = skip_scale * __ldcg(gate + 1);
     return;
   }
   for (int j = threadIdx.x; j < p.m * NR; j += blockDim.x) s_h[j] = -__ldcg(h + j);

@@ -25,13 +25,15 @@ typedef std::complex<double> zc;
 
 namespace {
 
-constexpr int S_W = CV_S_SOLVER;         // {Re<x|y>, Im<x|y>, <y|y>} of the fused SpMV
-constexpr int S_GATE = CV_S_SOLVER + 2;  // {|w|^2, |w'|^2}: gate of the second projection pass
-constexpr int S_NRM = CV_S_SOLVER + 4;   // squared norm of the orthogonalised vector
-constexpr int S_CX = CV_S_SOLVER + 5;    // |ux|^2, |cx|^2
-constexpr int S_GAMMA = CV_S_SOLVER + 8; // <cx|r> (NRED)
-constexpr int S_BETA = CV_S_SOLVER + 10; // |r|^2
-constexpr int S_H1 = CV_S_SOLVER + 16;
+// scalar slots (doubles) inside ctx->scalars / ctx->mailbox.  The slots one Arnoldi step reads back
+// are contiguous — S_NRM | S_W | S_H1 — so that one all-reduce and one device-to-host copy move
+// them together.
+constexpr int S_CX = CV_S_SOLVER;          // |ux|^2, |cx|^2
+constexpr int S_GAMMA = CV_S_SOLVER + 2;   // <cx|r> (NRED)
+constexpr int S_BETA = CV_S_SOLVER + 4;    // |r|^2
+constexpr int S_NRM = CV_S_SOLVER + 7;     // squared norm of the orthogonalised vector
+constexpr int S_W = CV_S_SOLVER + 8;       // {Re<x|y>, Im<x|y>, <y|y>} of the fused SpMV
+constexpr int S_H1 = CV_S_SOLVER + 11;     // first-pass projection coefficients
 constexpr int S_H2 = S_H1 + 2 * CV_MAX_PTRS;
 constexpr int S_END = S_H2 + 2 * CV_MAX_PTRS;
 static_assert(S_END <= (int)CV_N_SCALARS, "solver scalar slots exceed the mailbox");
@@ -83,11 +85,11 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
     CV_CUDA(cudaMemsetAsync(x, 0, (size_t)n * ebytes, st));
     CV_TRY(cv_copy(ctx, n, cplx_, b, r, (void *)st));
   }
-  CV_TRY(cv_nrm2sq_dev(ctx, n, cplx_, b, S_W, st));
+  CV_TRY(cv_nrm2sq_dev(ctx, n, cplx_, b, S_BETA + 1, st));
   CV_TRY(cv_nrm2sq_dev(ctx, n, cplx_, r, S_BETA, st));
-  CV_TRY(cv_fetch_scalars(ctx, S_W, S_BETA - S_W + 1, st));
+  CV_TRY(cv_fetch_scalars(ctx, S_BETA, 2, st));
   stats->n_sync++;
-  const double b_norm = sqrt(mb[S_W]);
+  const double b_norm = sqrt(mb[S_BETA + 1]);
   double beta = sqrt(mb[S_BETA]);
   stats->b_norm = b_norm;
   if (!std::isfinite(b_norm)) {
@@ -141,29 +143,50 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
     double res = NAN;
     for (j = 0; j < ml; ++j) {
       void *w = V(j + 1);
-      CV_TRY(cv_spmv_dev(ctx, op, cplx_, mode, sre, sim, V(j), w, 1.0, 0.0, nullptr, false, S_W, st));
+      ctx->defer_reduce = true;  // reduced together with the projection coefficients below
+      int rc_mv = cv_spmv_dev(ctx, op, cplx_, mode, sre, sim, V(j), w, 1.0, 0.0, nullptr, false, S_W, st);
+      ctx->defer_reduce = false;
+      CV_TRY(rc_mv);
       stats->n_matvec++;
       basis[nc + j] = V(j);
       const int nb = nc + j + 1;
       const void *wp[1] = {w};
-      // classical Gram-Schmidt against [C, V]; the second pass runs only if the first one
-      // cancelled more than half of |w|^2 (decided on the device, no host round trip)
-      CV_TRY(cv_tsdot_dev(ctx, n, cplx_, 1, nb, basis.data(), 1, wp, S_H1, st));
-      CV_TRY(cv_tsupdate_dev(ctx, n, cplx_, nb, basis.data(), S_H1, w, S_GATE + 1, st));
-      CV_TRY(cv_tsdot_dev(ctx, n, cplx_, 1, nb, basis.data(), 1, wp, S_H2, st, S_GATE));
-      CV_TRY(cv_tsupdate_dev(ctx, n, cplx_, nb, basis.data(), S_H2, w, S_NRM, st, S_GATE));
-      CV_TRY(cv_scale_dev(ctx, n, cplx_, w, S_NRM, 1, st));
-      CV_TRY(cv_fetch_scalars(ctx, S_W, S_H2 + nb * NR - S_W, st));
+      // Classical Gram-Schmidt against [C, V] in two tall-skinny passes.  The SpMV's dots and the
+      // projection coefficients travel in ONE all-reduce and, with |w'|^2, ONE copy to the host.
+      ctx->defer_reduce = true;
+      int rc_dot = cv_tsdot_dev(ctx, n, cplx_, 1, nb, basis.data(), 1, wp, S_H1, st);
+      ctx->defer_reduce = false;
+      CV_TRY(rc_dot);
+      CV_TRY(cv_reduce_ranks(ctx, S_W, 3 + nb * NR, st));
+      CV_TRY(cv_tsupdate_dev(ctx, n, cplx_, nb, basis.data(), S_H1, w, S_NRM, st));
+      CV_TRY(cv_fetch_scalars(ctx, S_NRM, 4 + nb * NR, st));
       stats->n_sync++;
       const double w_norm = sqrt(mb[S_W + 2]);
       for (int i = 0; i < nb; ++i) {
-        zc h = cplx_ ? zc(mb[S_H1 + 2 * i] + mb[S_H2 + 2 * i], mb[S_H1 + 2 * i + 1] + mb[S_H2 + 2 * i + 1])
-                     : zc(mb[S_H1 + i] + mb[S_H2 + i], 0.0);
+        zc h = cplx_ ? zc(mb[S_H1 + 2 * i], mb[S_H1 + 2 * i + 1]) : zc(mb[S_H1 + i], 0.0);
         if (i < nc)
           B[(size_t)i * ldb + j] = h;
         else
           hcur[i - nc] = h;
       }
+      // Re-orthogonalise only if the projection cancelled the vector down to less than eta of
+      // its norm (Daniel-Gragg-Kaufman-Stewart); otherwise orthogonality is already ~eps/eta.
+      if (!(mb[S_NRM] >= ctx->reorth_eta * ctx->reorth_eta * mb[S_W + 2])) {
+        CV_TRY(cv_tsdot_dev(ctx, n, cplx_, 1, nb, basis.data(), 1, wp, S_H2, st));
+        CV_TRY(cv_tsupdate_dev(ctx, n, cplx_, nb, basis.data(), S_H2, w, S_NRM, st));
+        CV_TRY(cv_fetch_scalars(ctx, S_NRM, 1, st));
+        CV_TRY(cv_fetch_scalars(ctx, S_H2, nb * NR, st));
+        stats->n_sync++;
+        stats->n_reorth++;
+        for (int i = 0; i < nb; ++i) {
+          zc h2 = cplx_ ? zc(mb[S_H2 + 2 * i], mb[S_H2 + 2 * i + 1]) : zc(mb[S_H2 + i], 0.0);
+          if (i < nc)
+            B[(size_t)i * ldb + j] += h2;
+          else
+            hcur[i - nc] += h2;
+        }
+      }
+      CV_TRY(cv_scale_dev(ctx, n, cplx_, w, S_NRM, 1, st));
       const double hlast = sqrt(mb[S_NRM]);
       hcur[j + 1] = hlast;
       if (!(hlast > eps * w_norm)) breakdown = true;

@@ -337,6 +337,7 @@ class CudaVector(AbstractVector):
         rt.stats["matvecs"] += stats.n_matvec
         rt.stats["syncs"] += stats.n_sync
         rt.stats["outer"] += stats.n_outer
+        rt.stats["reorth"] = rt.stats.get("reorth", 0) + stats.n_reorth
         rt.last_solve = stats
         if stats.info != 0:  # numpyVector.py:175-177 (turns the warning into an exception)
             warnings.simplefilter('error', UserWarning)

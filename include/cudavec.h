@@ -177,6 +177,7 @@ typedef struct cv_solve_stats {
   int n_matvec;      /* operator applications                                               */
   int n_outer;       /* GCROT outer iterations / MINRES iterations                          */
   int n_sync;        /* host synchronisations                                               */
+  int n_reorth;      /* Arnoldi steps that needed the second Gram-Schmidt pass              */
   double resid;      /* last residual norm estimate                                         */
   double b_norm;
 } cv_solve_stats;

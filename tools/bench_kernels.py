@@ -49,9 +49,11 @@ def main():
             ab = op.algorithmic_bytes()
             for label, fn in (
                 ("spmv_plain", lambda: _lib.check(rt.lib.cv_spmv(rt.ctx, op.handle, 0, 0, 0.0, 0.0, x._ptr, y.data_ptr(), rt.stream))),
+                ("spmv_shift", lambda: _lib.check(rt.lib.cv_spmv(rt.ctx, op.handle, 0, 1, 0.7, 0.0, x._ptr, y.data_ptr(), rt.stream))),
+                ("spmv_plain_dots", lambda: _lib.check(rt.lib.cv_spmv_dots(rt.ctx, op.handle, 0, 0, 0.0, 0.0, x._ptr, y.data_ptr(), None, rt.stream))),
                 ("spmv_shift_dots", lambda: _lib.check(rt.lib.cv_spmv_dots(rt.ctx, op.handle, 0, 1, 0.7, 0.0, x._ptr, y.data_ptr(), None, rt.stream))),
             ):
-                for fl in (None, flush):
+                for fl in ((None, flush) if fmt == "sell" else (flush,)):
                     med, mn = timeit(rt, fn, flush=fl)
                     print(json.dumps({"kernel": label, "matrix": name, "fmt": fmt, "n": n, "nnz": int(H.nnz),
                                       "padded": op.padded_nnz, "l2_flush": fl is not None, "ms": med * 1e3,
