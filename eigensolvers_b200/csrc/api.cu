@@ -698,9 +698,54 @@ extern "C" int cv_op_attach_sell(cv_ctx *ctx, cv_op *op, const int64_t *slice_pt
   return CV_OK;
 }
 
+extern "C" int cv_op_attach_dia(cv_ctx *ctx, cv_op *op, int n_diag, const int32_t *offsets_host,
+                                const int32_t *col_global_dev, int64_t row0, double *dia_val_dev,
+                                int64_t ld, int *ok_host, void *stream) {
+  CV_REQUIRE(ctx && op && offsets_host && dia_val_dev && ok_host, "cv_op_attach_dia: null argument");
+  CV_REQUIRE(n_diag >= 1 && n_diag <= CV_MAX_DIAG, "cv_op_attach_dia: n_diag=%d outside 1..%d", n_diag, CV_MAX_DIAG);
+  CV_REQUIRE(ld >= op->n_rows, "cv_op_attach_dia: leading dimension smaller than the row count");
+  for (int d = 1; d < n_diag; ++d)
+    CV_REQUIRE(offsets_host[d] > offsets_host[d - 1], "cv_op_attach_dia: offsets must be strictly ascending");
+  cudaStream_t st = (cudaStream_t)stream;
+  // offsets and the error flag go through the scalar scratch area (reinterpreted as ints)
+  int *d_off = reinterpret_cast<int *>(ctx->scalars + CV_S_TS);
+  int *d_bad = d_off + CV_MAX_DIAG;
+  int h_buf[CV_MAX_DIAG + 1];
+  for (int d = 0; d < n_diag; ++d) h_buf[d] = offsets_host[d];
+  for (int d = n_diag; d <= CV_MAX_DIAG; ++d) h_buf[d] = 0;
+  CV_CUDA(cudaMemcpyAsync(d_off, h_buf, sizeof(h_buf), cudaMemcpyHostToDevice, st));
+  CV_CUDA(cudaStreamSynchronize(st));  // h_buf is a stack array
+  if (op->n_rows > 0) {
+    k_dia_fill<<<cv_grid_for(ctx, op->n_rows, CV_BLOCK), CV_BLOCK, 0, st>>>(
+        op->n_rows, row0, op->indptr, col_global_dev ? col_global_dev : op->indices, op->data, n_diag, d_off,
+        dia_val_dev, ld, d_bad);
+    CV_TRY(cv_check_launch(ctx, "dia_fill"));
+  }
+  int bad = 0;
+  CV_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CV_CUDA(cudaStreamSynchronize(st));
+  *ok_host = bad ? 0 : 1;
+  if (bad) return CV_OK;
+  op->n_diag = n_diag;
+  int mn = 0, mx = 0;
+  for (int d = 0; d < n_diag; ++d) {
+    op->dia_off[d] = offsets_host[d];
+    mn = offsets_host[d] < mn ? offsets_host[d] : mn;
+    mx = offsets_host[d] > mx ? offsets_host[d] : mx;
+  }
+  op->dia_val = dia_val_dev;
+  op->dia_ld = ld;
+  op->lo_len = -mn;
+  op->hi_len = mx;
+  op->row0 = row0;
+  op->fmt = CV_FMT_DIA;
+  return CV_OK;
+}
+
 extern "C" int cv_op_set_format(cv_op *op, int fmt) {
   CV_REQUIRE(op, "cv_op_set_format: null operator");
-  CV_REQUIRE(fmt == CV_FMT_CSR || (fmt == CV_FMT_SELL && op->slice_ptr), "cv_op_set_format: format %d not available", fmt);
+  CV_REQUIRE(fmt == CV_FMT_CSR || (fmt == CV_FMT_SELL && op->slice_ptr) || (fmt == CV_FMT_DIA && op->dia_val),
+             "cv_op_set_format: format %d not available", fmt);
   op->fmt = fmt;
   return CV_OK;
 }
@@ -720,14 +765,34 @@ extern "C" int cv_op_info(cv_op *op, int64_t *n_rows, int64_t *nnz, int64_t *pad
 template <typename T, bool HALO, bool EPI, bool DOTS>
 static int launch_spmv_fmt(cv_ctx *ctx, cv_op *op, const SpmvArgs<T> &a, cudaStream_t st) {
   cv_prof_scope prof(ctx, 0, st);
-  if (op->fmt == CV_FMT_SELL) {
+  if (op->fmt == CV_FMT_DIA) {
+    DiaArgs<T> d;
+    d.s = a;
+    d.dia_val = op->dia_val;
+    d.ld = op->dia_ld;
+    d.n_diag = op->n_diag;
+    for (int k = 0; k < CV_MAX_DIAG; ++k) d.off[k] = k < op->n_diag ? op->dia_off[k] : 0;
+    d.halo_lo = static_cast<const T *>(op->halo_lo);
+    d.halo_hi = static_cast<const T *>(op->halo_hi);
+    d.lo_len = op->lo_len;
+    d.hi_len = op->hi_len;
+    auto kf = k_spmv_dia<T, HALO, EPI, DOTS>;
+    int wave = cv_occ_grid(ctx, (const void *)kf, (int64_t)1 << 40, CV_BLOCK);
+    int64_t need = (op->n_rows + CV_BLOCK - 1) / CV_BLOCK;
+    // with fused dots every CTA ends in a reduction epilogue (~3 us of latency): keep ONE
+    // persistent wave; without, small problems run one row per thread for load balance
+    int grid = (int)((!DOTS && need <= 16 * (int64_t)wave) || need < wave ? need : wave);
+    kf<<<grid, CV_BLOCK, 0, st>>>(d);
+  } else if (op->fmt == CV_FMT_SELL) {
     auto kf = k_spmv_sell<T, HALO, EPI, DOTS>;
     int wave = cv_occ_grid(ctx, (const void *)kf, (int64_t)1 << 40, CV_WARPS);
     int64_t need = (op->n_slices + CV_WARPS - 1) / CV_WARPS;
     // few slices per warp: a static slice->warp map would quantise badly (3.3 slices per warp on
     // the 100^3 Laplacian = 18 % idle); launch one slice per warp and let the hardware CTA
     // scheduler balance.  Many slices per warp: one persistent wave.
-    int grid = (int)(need <= 16 * (int64_t)wave ? need : wave);
+    // many slices per warp, or fused dots (each CTA then ends in a ~3 us reduction epilogue,
+    // measured 33 us extra with 7813 small CTAs): one persistent wave.
+    int grid = (int)((!DOTS && need <= 16 * (int64_t)wave) || need < wave ? need : wave);
     kf<<<grid, CV_BLOCK, 0, st>>>(a);
   } else {
 #define CSR(G)                                                                    \
@@ -772,9 +837,15 @@ static int launch_spmv_t(cv_ctx *ctx, cv_op *op, int mode, T sigma, const T *x, 
   a.partials = ctx->partials;
   a.counter = ctx->counters;
   a.out = dots_slot >= 0 ? ctx->scalars + dots_slot : nullptr;
-  const bool halo = op->n_halo > 0;
+  const bool dia = op->fmt == CV_FMT_DIA;
+  const bool halo = dia ? (ctx->world > 1 && (op->lo_len > 0 || op->hi_len > 0)) : op->n_halo > 0;
   const bool dots = dots_slot >= 0;
-  if (halo) CV_TRY(cv_halo_exchange(ctx, op, sizeof(T) == 16, x, st));
+  if (halo) {
+    if (dia)
+      CV_TRY(cv_halo_exchange_dia(ctx, op, sizeof(T) == 16, x, st));
+    else
+      CV_TRY(cv_halo_exchange(ctx, op, sizeof(T) == 16, x, st));
+  }
   int rc;
 #define GO(H, E, D) rc = launch_spmv_fmt<T, H, E, D>(ctx, op, a, st)
   if (halo) {

@@ -173,6 +173,68 @@ int cv_halo_exchange(cv_ctx *ctx, cv_op *op, bool cplx_, const void *x, cudaStre
 }
 
 // ------------------------------------------------------------------------------------------
+// DIA halo: the band below / above the owned rows arrives as contiguous ranges (no pack kernel)
+// ------------------------------------------------------------------------------------------
+extern "C" int cv_op_set_dia_halo(cv_ctx *ctx, cv_op *op, const int64_t *offsets, void *halo_lo_dev,
+                                  void *halo_hi_dev) {
+  CV_REQUIRE(ctx && op && offsets, "cv_op_set_dia_halo: null argument");
+  CV_REQUIRE(op->dia_val, "cv_op_set_dia_halo: operator has no DIA storage");
+  CV_REQUIRE((op->lo_len == 0 || halo_lo_dev) && (op->hi_len == 0 || halo_hi_dev), "cv_op_set_dia_halo: null halo buffer");
+  const int P = ctx->world, me = ctx->rank;
+  const int64_t N = offsets[P], r0 = offsets[me], r1 = offsets[me + 1];
+  op->halo_lo = halo_lo_dev;
+  op->halo_hi = halo_hi_dev;
+  op->n_global = N;
+  op->dia_send.clear();
+  op->dia_recv_lo.clear();
+  op->dia_recv_hi.clear();
+  auto overlap = [](int64_t a0, int64_t a1, int64_t b0, int64_t b1, int64_t &s, int64_t &c) {
+    s = a0 > b0 ? a0 : b0;
+    int64_t e = a1 < b1 ? a1 : b1;
+    c = e > s ? e - s : 0;
+  };
+  for (int p = 0; p < P; ++p) {
+    if (p == me) continue;
+    const int64_t p0 = offsets[p], p1 = offsets[p + 1];
+    int64_t s, c;
+    // what p needs from my rows: first the part of p's lower band, then of its upper band
+    overlap(p0 - op->lo_len < 0 ? 0 : p0 - op->lo_len, p0, r0, r1, s, c);
+    if (c > 0) op->dia_send.push_back({p, s - r0, c});
+    overlap(p1, p1 + op->hi_len > N ? N : p1 + op->hi_len, r0, r1, s, c);
+    if (c > 0) op->dia_send.push_back({p, s - r0, c});
+    // what I need from p's rows
+    overlap(r0 - op->lo_len < 0 ? 0 : r0 - op->lo_len, r0, p0, p1, s, c);
+    if (c > 0) op->dia_recv_lo.push_back({p, s - (r0 - op->lo_len), c});
+    overlap(r1, r1 + op->hi_len > N ? N : r1 + op->hi_len, p0, p1, s, c);
+    if (c > 0) op->dia_recv_hi.push_back({p, s - r1, c});
+  }
+  return CV_OK;
+}
+
+int cv_halo_exchange_dia(cv_ctx *ctx, cv_op *op, bool cplx_, const void *x, cudaStream_t st) {
+  CV_REQUIRE(ctx->world > 1 && ctx->comm, "halo exchange without a communicator");
+  CV_REQUIRE(op->n_global > 0, "DIA operator has no exchange plan (cv_op_set_dia_halo)");
+  const size_t w = cplx_ ? 2 : 1;
+  CV_NCCL(g_nccl.GroupStart());
+  // per peer the matching order is: sends (for its lower band, then upper band) / receives (my
+  // lower band, then upper band); both sides enumerate peers and bands in the same order
+  for (int p = 0; p < ctx->world; ++p) {
+    if (p == ctx->rank) continue;
+    for (const auto &r : op->dia_send)
+      if (r.peer == p)
+        CV_NCCL(g_nccl.Send((const double *)x + r.start * w, (size_t)r.count * w, ncclFloat64_, p, ctx->comm->comm, st));
+    for (const auto &r : op->dia_recv_lo)
+      if (r.peer == p)
+        CV_NCCL(g_nccl.Recv((double *)op->halo_lo + r.start * w, (size_t)r.count * w, ncclFloat64_, p, ctx->comm->comm, st));
+    for (const auto &r : op->dia_recv_hi)
+      if (r.peer == p)
+        CV_NCCL(g_nccl.Recv((double *)op->halo_hi + r.start * w, (size_t)r.count * w, ncclFloat64_, p, ctx->comm->comm, st));
+  }
+  CV_NCCL(g_nccl.GroupEnd());
+  return CV_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // host-side integer routines: row partition and halo maps
 // ------------------------------------------------------------------------------------------
 extern "C" int cv_partition_rows(int64_t n, int world, int64_t *offsets) {

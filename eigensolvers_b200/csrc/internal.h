@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "kernels_vec.cuh"
 #include "kernels_spmv.cuh"
+#include "kernels_dia.cuh"
 
 struct cv_op {
   int64_t n_rows = 0, n_cols = 0, nnz = 0;
@@ -18,6 +19,16 @@ struct cv_op {
   const int32_t *sell_col = nullptr;
   const double *sell_val = nullptr;
   int fmt = CV_FMT_CSR;
+  // DIA (borrowed device array)
+  int n_diag = 0;
+  int dia_off[CV_MAX_DIAG];
+  const double *dia_val = nullptr;
+  int64_t dia_ld = 0;
+  int lo_len = 0, hi_len = 0;          // band below / above the owned rows (sharded mode)
+  void *halo_lo = nullptr, *halo_hi = nullptr;
+  struct Range { int peer; int64_t start, count; };  // start: local row (send) / buffer slot (recv)
+  std::vector<Range> dia_send, dia_recv_lo, dia_recv_hi;
+  int64_t row0 = 0, n_global = 0;
   // row-sharded mode: columns >= n_cols - n_halo address the halo buffer
   int64_t n_halo = 0;
   const int32_t *send_idx = nullptr;
@@ -44,3 +55,4 @@ int cv_spmv_dev(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double 
                 void *y, double alpha, double beta1, const void *u1, bool epi, int dots_slot,
                 cudaStream_t st);
 int cv_halo_exchange(cv_ctx *ctx, cv_op *op, bool cplx_, const void *x, cudaStream_t st);
+int cv_halo_exchange_dia(cv_ctx *ctx, cv_op *op, bool cplx_, const void *x, cudaStream_t st);

@@ -76,12 +76,16 @@ class DeviceOperator:
         indptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
         indices = np.ascontiguousarray(A.indices, dtype=np.int32)
         data = np.ascontiguousarray(A.data, dtype=np.float64)
+        gcols, row0 = indices, 0
         if rt.world > 1:
+            r0, r1 = rt.local_range(A.shape[0])
+            gcols, row0 = indices[int(indptr[r0]):int(indptr[r1])], r0
             indptr, indices, data = op._shard(indptr, indices, data)
-        return op._finish(indptr, indices, data, fmt)
+        return op._finish(indptr, indices, data, fmt, gcols, row0)
 
-    def _finish(self, indptr, indices, data, fmt):
-        """Upload the (local) CSR arrays, create the cv_op, register the halo plan, build SELL."""
+    def _finish(self, indptr, indices, data, fmt, gcols=None, row0=0):
+        """Upload the (local) CSR arrays, create the cv_op, register the halo plan, then pick the
+        storage format: DIA (banded structure) > SELL-32 (short regular rows) > CSR."""
         op, rt = self, self.rt
         n_rows = len(indptr) - 1
         n_cols = op.shape[1] if rt.world == 1 else op.n_local + op.n_halo
@@ -96,9 +100,86 @@ class DeviceOperator:
                                            C.byref(op.handle)))
         if rt.world > 1:
             op._register_halo()
+        if fmt in ("auto", "dia") and op.shape[0] == op.shape[1]:
+            ok = op._build_dia(indptr, indices if gcols is None else gcols, row0, force=(fmt == "dia"))
+            if ok:
+                return op
+            if fmt == "dia":
+                raise ValueError("operator is not banded enough for DIA storage")
         if fmt in ("auto", "sell") and n_rows > 0 and op.nnz > 0:
             op._build_sell(force=(fmt == "sell"))
         return op
+
+    # ---------------------------------------------------------------------------------------
+    MAX_DIAG = 64
+
+    def _build_dia(self, indptr, gcols, row0, force=False):
+        """Diagonal storage when every entry sits on one of <= 64 column offsets (stencil and
+        product-basis Hamiltonians).  The offset table comes from a sample of rows on the host;
+        the device fill kernel verifies EVERY entry and the format is dropped if one is off-table.
+        All ranks take the same decision (the table is the union over ranks)."""
+        rt, t = self.rt, self.rt.torch
+        n_rows = len(indptr) - 1
+        if n_rows == 0 and rt.world == 1:
+            return False
+        sample = np.unique(np.concatenate([
+            np.arange(0, min(n_rows, 2048)), np.arange(max(n_rows - 2048, 0), n_rows),
+            np.linspace(0, max(n_rows - 1, 0), num=min(n_rows, 4096), dtype=np.int64)])) if n_rows else np.empty(0, np.int64)
+        offs = set()
+        for r in sample:
+            lo, hi = int(indptr[r]), int(indptr[r + 1])
+            offs.update((gcols[lo:hi].astype(np.int64) - (row0 + int(r))).tolist())
+            if len(offs) > self.MAX_DIAG:
+                break
+        info = (sorted(offs), int(self.nnz), int(n_rows))
+        if rt.world > 1:
+            import torch.distributed as dist
+            box = [None] * rt.world
+            dist.all_gather_object(box, info)
+        else:
+            box = [info]
+        table = sorted(set().union(*[set(b[0]) for b in box]))
+        nnz_all, rows_all = sum(b[1] for b in box), sum(b[2] for b in box)
+        D = len(table)
+        if D == 0 or D > self.MAX_DIAG:
+            return False
+        # 8 bytes per stored slot against 12 per CSR entry; tiny matrices are not worth a format
+        if not force and (8.0 * D * rows_all > 0.95 * 12.0 * nnz_all or rows_all < 1024):
+            return False
+        if max(abs(table[0]), abs(table[-1])) >= 2 ** 31 - 1:
+            return False
+        ld = (n_rows + 31) // 32 * 32
+        d_val = t.zeros(max(D * ld, 1), dtype=t.float64, device=rt.device)
+        d_gcols = None
+        if rt.world > 1:
+            d_gcols = rt.upload(np.ascontiguousarray(gcols, dtype=np.int32)) if len(gcols) else None
+        offs_arr = np.ascontiguousarray(table, dtype=np.int32)
+        ok = C.c_int(0)
+        _lib.check(rt.lib.cv_op_attach_dia(rt.ctx, self.handle, D, offs_arr.ctypes.data,
+                                           None if d_gcols is None else d_gcols.data_ptr(), int(row0),
+                                           d_val.data_ptr(), ld, C.byref(ok), rt.stream))
+        good = bool(ok.value)
+        if rt.world > 1:
+            import torch.distributed as dist
+            flags = [None] * rt.world
+            dist.all_gather_object(flags, good)
+            good = all(flags)
+        if not good:
+            _lib.check(rt.lib.cv_op_set_format(self.handle, _lib.CV_FMT_CSR))
+            return False
+        self._keep.append(d_val)
+        self.dia_offsets = offs_arr
+        self.padded_nnz = D * n_rows
+        self.format = "dia"
+        if rt.world > 1:
+            lo_len, hi_len = max(0, -int(table[0])), max(0, int(table[-1]))
+            halo_lo = t.zeros(2 * max(lo_len, 1), dtype=t.float64, device=rt.device)
+            halo_hi = t.zeros(2 * max(hi_len, 1), dtype=t.float64, device=rt.device)
+            self._keep += [halo_lo, halo_hi]
+            off = rt.offsets_for(self.shape[0])
+            _lib.check(rt.lib.cv_op_set_dia_halo(rt.ctx, self.handle, off.ctypes.data, halo_lo.data_ptr(),
+                                                 halo_hi.data_ptr()))
+        return True
 
     # ---------------------------------------------------------------------------------------
     def _build_sell(self, force=False):
@@ -125,7 +206,7 @@ class DeviceOperator:
         self.format = "sell"
 
     def set_format(self, fmt):
-        code = {"csr": _lib.CV_FMT_CSR, "sell": _lib.CV_FMT_SELL}[fmt]
+        code = {"csr": _lib.CV_FMT_CSR, "sell": _lib.CV_FMT_SELL, "dia": _lib.CV_FMT_DIA}[fmt]
         if fmt == "sell" and self.padded_nnz == 0:
             self._build_sell(force=True)
         _lib.check(self.rt.lib.cv_op_set_format(self.handle, code))
@@ -178,9 +259,10 @@ class DeviceOperator:
         indptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
         indices = np.ascontiguousarray(A.indices, dtype=np.int32)
         data = np.ascontiguousarray(A.data, dtype=np.float64)
+        gcols = indices
         if rt.world > 1:
             indptr, indices, data = op._localize(indptr, indices, data, r0, r1, full=False)
-        return op._finish(indptr, indices, data, fmt)
+        return op._finish(indptr, indices, data, fmt, gcols, r0)
 
     def _register_halo(self):
         """Exchange the halo request lists once (host, torch.distributed) and register the plan."""

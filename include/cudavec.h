@@ -47,6 +47,7 @@ extern "C" {
 /* operator storage formats */
 #define CV_FMT_CSR 0
 #define CV_FMT_SELL 1     /* sliced ELL, slice height 32 */
+#define CV_FMT_DIA 2      /* one dense value stream per distinct column offset (banded structure) */
 
 /* linear solvers (numpyVector.py:160-163) */
 #define CV_SOLVER_GCROTMK 0
@@ -116,6 +117,20 @@ int cv_op_destroy(cv_op *op);
 int cv_op_sell_widths(cv_ctx *ctx, cv_op *op, int32_t *widths_dev, void *stream);
 int cv_op_attach_sell(cv_ctx *ctx, cv_op *op, const int64_t *slice_ptr_dev, int64_t padded_nnz,
                       int32_t *sell_col_dev, double *sell_val_dev, void *stream);
+/* Diagonal storage for operators whose entries all lie on n_diag (<= 64) distinct offsets
+ * col-row (sorted ascending, host array).  dia_val_dev is caller storage of n_diag*ld doubles,
+ * zero-filled; the fill kernel scatters the CSR values into it.  col_global_dev (may be NULL =
+ * the operator's own column array) holds GLOBAL column ids and row0 the first global row, so the
+ * call also works for a rank's row block.  *ok_host = 0 if some entry is off the given diagonals
+ * (the operator then keeps its previous format).                                               */
+int cv_op_attach_dia(cv_ctx *ctx, cv_op *op, int n_diag, const int32_t *offsets_host,
+                     const int32_t *col_global_dev, int64_t row0, double *dia_val_dev, int64_t ld,
+                     int *ok_host, void *stream);
+/* Row-sharded DIA: the band below/above the owned block is received into two contiguous buffers
+ * (16*lo_len and 16*hi_len bytes, lo_len = max(0,-min offset), hi_len = max(0,max offset)) by
+ * contiguous range sends derived from the partition `offsets` (host, world+1).                   */
+int cv_op_set_dia_halo(cv_ctx *ctx, cv_op *op, const int64_t *offsets, void *halo_lo_dev,
+                       void *halo_hi_dev);
 int cv_op_set_format(cv_op *op, int fmt);
 int cv_op_info(cv_op *op, int64_t *n_rows, int64_t *nnz, int64_t *padded_nnz, int *fmt);
 

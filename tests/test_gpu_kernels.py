@@ -125,7 +125,7 @@ def _sym_sparse(n, density, seed):
     return A.tocsr()
 
 
-@pytest.mark.parametrize("fmt", ["csr", "sell"])
+@pytest.mark.parametrize("fmt", ["csr", "sell", "dia"])
 @pytest.mark.parametrize("cplx", [False, True])
 @pytest.mark.parametrize("case", ["lap", "rand", "dense", "osc", "empty_rows"])
 def test_spmv(rt, fmt, cplx, case):
@@ -142,6 +142,10 @@ def test_spmv(rt, fmt, cplx, case):
         H = hm.coupled_oscillators((6, 5, 4, 4, 3))[0]
     else:
         H = sp.csr_matrix(([1.0, 2.0, 3.0], ([0, 5, 70], [3, 5, 1])), shape=(75, 75))
+    if fmt == "dia" and case in ("rand", "empty_rows"):
+        with pytest.raises(ValueError):      # not banded: DIA is refused, never silently wrong
+            DeviceOperator.from_host(H, fmt=fmt)
+        return
     op = DeviceOperator.from_host(H, fmt=fmt)
     assert op.format == fmt
     Hd = H if not sp.issparse(H) else H
@@ -160,6 +164,24 @@ def test_spmv(rt, fmt, cplx, case):
         np.testing.assert_allclose(yh, ref, rtol=1e-12, atol=1e-12)
         np.testing.assert_allclose(complex(out[0], out[1]), np.vdot(x, ref), rtol=1e-11, atol=1e-10)
         np.testing.assert_allclose(out[2], np.vdot(ref, ref).real, rtol=1e-12)
+
+
+def test_format_selection(rt):
+    """auto: DIA for banded structure, SELL for short irregular rows, CSR for tiny/dense."""
+    from eigensolvers_b200 import DeviceOperator, hamiltonians as hm
+    assert DeviceOperator.from_host(hm.laplacian3d(17)).format == "dia"
+    assert DeviceOperator.from_host(hm.coupled_oscillators((6, 5, 4, 4, 3))[0]).format == "dia"
+    assert DeviceOperator.from_host(_sym_sparse(3001, 0.004, 3)).format == "sell"
+    assert DeviceOperator.from_host(hm.prescribed_spectrum(100)[0]).format == "csr"
+    # a banded matrix with ONE stray entry must not be stored as DIA
+    H = hm.laplacian3d(17).tolil()
+    H[5, 4000] = 1.0
+    H[4000, 5] = 1.0
+    op = DeviceOperator.from_host(H.tocsr())
+    assert op.format == "sell"
+    x = np.random.default_rng(0).standard_normal(H.shape[0])
+    from eigensolvers_b200 import CudaVector
+    np.testing.assert_allclose(CudaVector(x).applyOp(op).array, H.tocsr() @ x, rtol=1e-12, atol=1e-12)
 
 
 def test_operator_cache_and_types(rt):

@@ -44,7 +44,7 @@ def main():
         n = H.shape[0]
         x = CudaVector(np.random.default_rng(0).standard_normal(n))
         y = rt.empty(n, 0)
-        for fmt in ("csr", "sell"):
+        for fmt in ("csr", "sell", "dia"):
             op = DeviceOperator.from_host(H, fmt=fmt)
             ab = op.algorithmic_bytes()
             for label, fn in (
@@ -53,7 +53,7 @@ def main():
                 ("spmv_plain_dots", lambda: _lib.check(rt.lib.cv_spmv_dots(rt.ctx, op.handle, 0, 0, 0.0, 0.0, x._ptr, y.data_ptr(), None, rt.stream))),
                 ("spmv_shift_dots", lambda: _lib.check(rt.lib.cv_spmv_dots(rt.ctx, op.handle, 0, 1, 0.7, 0.0, x._ptr, y.data_ptr(), None, rt.stream))),
             ):
-                for fl in ((None, flush) if fmt == "sell" else (flush,)):
+                for fl in ((None, flush) if fmt != "csr" else (flush,)):
                     med, mn = timeit(rt, fn, flush=fl)
                     print(json.dumps({"kernel": label, "matrix": name, "fmt": fmt, "n": n, "nnz": int(H.nnz),
                                       "padded": op.padded_nnz, "l2_flush": fl is not None, "ms": med * 1e3,

@@ -48,9 +48,10 @@ def main():
         check(f"{name} roundtrip", np.array_equal(X.array, x))
         check(f"{name} dot", abs(X.vdot(Y) - x @ y) <= 1e-11 * np.sqrt(n))
         check(f"{name} norm", abs(X.norm() - np.linalg.norm(x)) <= 1e-12 * np.linalg.norm(x))
-        for fmt in ("csr", "sell"):
+        for fmt in ("csr", "sell", "dia"):
             op = DeviceOperator.from_host(H, fmt=fmt)
             check(f"{name} {fmt} halo>0", op.n_halo > 0)
+            check(f"{name} {fmt} format", op.format == fmt)
             hx = X.applyOp(op).array
             check(f"{name} {fmt} spmv", np.allclose(hx, H @ x, rtol=1e-12, atol=1e-12))
         # row-block construction equals slicing the full matrix
