@@ -142,7 +142,7 @@ def test_spmv(rt, fmt, cplx, case):
         H = hm.coupled_oscillators((6, 5, 4, 4, 3))[0]
     else:
         H = sp.csr_matrix(([1.0, 2.0, 3.0], ([0, 5, 70], [3, 5, 1])), shape=(75, 75))
-    if fmt == "dia" and case in ("rand", "empty_rows"):
+    if fmt == "dia" and case in ("rand", "empty_rows", "dense"):
         with pytest.raises(ValueError):      # not banded: DIA is refused, never silently wrong
             DeviceOperator.from_host(H, fmt=fmt)
         return

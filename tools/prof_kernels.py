@@ -15,12 +15,13 @@ def main():
     t = rt.torch
     H = hm.coupled_oscillators((20, 10, 10, 10, 10, 10))[0]
     n = H.shape[0]
-    op = DeviceOperator.from_host(H, fmt="sell")
     x = CudaVector(np.random.default_rng(0).standard_normal(n))
     y = rt.empty(n, 0)
-    for _ in range(2):
-        _lib.check(rt.lib.cv_spmv(rt.ctx, op.handle, 0, 0, 0.0, 0.0, x._ptr, y.data_ptr(), rt.stream))
-        _lib.check(rt.lib.cv_spmv_dots(rt.ctx, op.handle, 0, 1, 0.7, 0.0, x._ptr, y.data_ptr(), None, rt.stream))
+    for fmt in ("sell", "dia"):
+        op = DeviceOperator.from_host(H, fmt=fmt)
+        for _ in range(2):
+            _lib.check(rt.lib.cv_spmv(rt.ctx, op.handle, 0, 0, 0.0, 0.0, x._ptr, y.data_ptr(), rt.stream))
+            _lib.check(rt.lib.cv_spmv_dots(rt.ctx, op.handle, 0, 1, 0.7, 0.0, x._ptr, y.data_ptr(), None, rt.stream))
     t.cuda.synchronize()
     n = 20_000_000
     rng = np.random.default_rng(1)
