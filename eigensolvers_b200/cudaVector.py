@@ -437,6 +437,25 @@ class CudaVector(AbstractVector):
         overlap = np.append(overlap, elems.T, axis=1)
         return overlap
 
+    @staticmethod
+    def sumOverRanks(vectors, like=None):
+        """FEAST with one quadrature node per GPU (contour.py, distribute="nodes"): every rank holds
+        the partial contour sum of ITS nodes in full-length vectors (H replicated, runtime NOT in
+        row-sharded mode); one NCCL all-reduce per subspace vector adds them up in place."""
+        import torch.distributed as dist
+        rt = Runtime.get()
+        if rt.world != 1:
+            raise RuntimeError("node-distributed FEAST needs an unsharded runtime (do not call init_distributed)")
+        out = []
+        for i, v in enumerate(vectors):
+            if v is None:  # this rank owned no node
+                ref = like[i]
+                t = rt.torch.zeros(ref._nloc, dtype=rt.torch.float64, device=rt.device)
+                v = CudaVector._wrap(t, ref.options, ref._n_global)
+            dist.all_reduce(v._t)
+            out.append(v)
+        return out
+
     def extendBoth(operator, vectors, overlap, opMat):
         """Fused form of the two extend* calls the Lanczos driver makes back to back
         (inexact_Lanczos.py:349-350): one SpMV and ONE pass over the Krylov list."""

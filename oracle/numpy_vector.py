@@ -124,6 +124,19 @@ class NumpyVectorOracle(AbstractVector):
             warnings.warn("Warning:: Iterative solver is not converged ")
         return NumpyVectorOracle(wk, b.options)
 
+    @staticmethod
+    def sumOverRanks(vectors, like=None):
+        """Test-only counterpart of CudaVector.sumOverRanks (node-distributed FEAST over gloo)."""
+        import torch
+        import torch.distributed as dist
+        out = []
+        for i, v in enumerate(vectors):
+            arr = np.zeros(len(like[i])) if v is None else np.ascontiguousarray(v.array, dtype=np.float64)
+            t = torch.from_numpy(arr)
+            dist.all_reduce(t)
+            out.append(NumpyVectorOracle(t.numpy(), like[i].options))
+        return out
+
     def matrixRepresentation(operator, vectors):          # :180-190
         m = len(vectors)
         M = np.zeros((m, m), dtype=vectors[0].dtype)

@@ -134,3 +134,43 @@ def test_halo_exchange_two_gloo_ranks():
     assert sorted(r[0] for r in results) == [0, 1]
     assert all(r[1] for r in results), results
     assert all(r[2] == 64 for r in results)  # one 8x8 plane of halo on each side of the cut
+
+
+def _feast_worker(rank, world, port, q):
+    import warnings
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from eigensolvers_b200.contour import feastDiagonalization
+        from oracle.numpy_vector import NumpyVectorOracle as NV
+        g = np.load(os.path.join(ROOT, "tests", "golden", "feast_t1.npz"))
+        o = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 1000, "linear_tol": 1e-2}}
+        Y = [NV(g["Y1"][:, i].copy(), o) for i in range(6)]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ev, vecs, st = feastDiagonalization(g["A"], Y, 8, "legendre", 160.0, 166.0, 1e-10, 20, writeOut=False,
+                                                distribute="nodes")
+        inside = np.sort([e for e in ev if 160.0 <= e <= 166.0])
+        ref = np.sort([e for e in g["ev"] if 160.0 <= e <= 166.0])
+        q.put((rank, len(inside) == len(ref) and bool(np.allclose(inside, ref, rtol=0, atol=1e-6)), [float(x) for x in inside]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_feast_nodes_distributed_over_two_gloo_ranks():
+    """FEAST with the quadrature nodes split over 2 ranks (H replicated, one all-reduce of the m0
+    accumulated vectors per iteration) finds the same eigenvalues as the reference's serial run."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_feast_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in results), results
+    assert results[0][2] == results[1][2]        # both ranks hold identical Ritz values
