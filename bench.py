@@ -200,6 +200,7 @@ def config_dict(args, w):
                         f"sigma={w['sigma']:.6f}, L={w['L']}, maxit={w['maxit']}, eConv={w['eConv']:g}, "
                         f"gcrotmk rtol={w['tol']:g}",
             "format": w.get("format", "auto"), "parallelism": f"row-shard x{args.gpus}",
+            "transport": w.get("transport", "single"),
             "l2": "working set >> 126 MB L2; L2 also flushed between steps"}
 
 
@@ -255,6 +256,7 @@ def run_ours(args, w):
     # ---- resident leg: operator and guesses already in HBM
     op = make_operator()
     w["format"] = op.format
+    w["transport"] = rt.transport  # 'peer': collectives over CUDA-IPC peer memory (NVLink); 'nccl' fall-back
     guess_dev = [CudaVector(g, dict(opts))._t for g in guesses_p]
     for _ in range(args.warmup):
         flush.add_(1.0)

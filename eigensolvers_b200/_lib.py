@@ -44,6 +44,16 @@ SIGNATURES = {
     "cv_comm_init": (_i, [_vp, _vp, _i, _i]),
     "cv_comm_finalize": (_i, [_vp]),
     "cv_comm_allreduce": (_i, [_vp, _vp, _i, _vp]),
+    "cv_peer_window_bytes": (_sz, []),
+    "cv_peer_alloc": (_i, [_vp, _sz, _pvp, _vp]),
+    "cv_peer_open": (_i, [_vp, _vp, _pvp]),
+    "cv_peer_close": (_i, [_vp, _vp]),
+    "cv_peer_free": (_i, [_vp, _vp]),
+    "cv_comm_attach_peers": (_i, [_vp, _pvp]),
+    "cv_comm_transport": (_i, [_vp, _pi]),
+    "cv_op_set_halo_peers": (_i, [_vp, _vp, _pvp, _vp, _vp]),
+    "cv_op_dia_halo_bytes": (_sz, [_vp]),
+    "cv_op_set_dia_halo_peers": (_i, [_vp, _vp, _pvp]),
     "cv_partition_rows": (_i, [_i64, _i, _pi64]),
     "cv_halo_count": (_i, [_vp, _vp, _i64, _i64, _pi64]),
     "cv_halo_build": (_i, [_vp, _vp, _i64, _i64, _vp, _i, _i64, _vp, _vp, _vp, _vp]),

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcudavec.so")
 SOURCES = ["cudavec.cu"]
-DEPS = ["api.cu", "comm.cu", "solvers.cu", "common.cuh", "internal.h", "kernels_vec.cuh",
+DEPS = ["api.cu", "comm.cu", "peer.cu", "solvers.cu", "common.cuh", "internal.h", "kernels_vec.cuh",
         "kernels_spmv.cuh", "kernels_dia.cuh", os.path.join("..", "..", "include", "cudavec.h")]
 
 NVCC_FLAGS = [

@@ -49,6 +49,7 @@ extern "C" int cv_ctx_create(int device, void *scratch_dev, size_t scratch_bytes
   c->reorth_eta = 0.1;
   c->defer_reduce = false;
   c->comm = nullptr;
+  c->peer = nullptr;
   c->rank = 0;
   c->world = 1;
   *out = c;
@@ -145,7 +146,14 @@ extern "C" int cv_ctx_profile_read(cv_ctx *ctx, double *ms4, uint64_t *count4) {
 int cv_fetch_scalars(cv_ctx *ctx, int offset, int count, cudaStream_t st) {
   CV_CUDA(cudaMemcpyAsync(ctx->mailbox + offset, ctx->scalars + offset, sizeof(double) * count,
                           cudaMemcpyDeviceToHost, st));
+  if (ctx->peer)
+    CV_CUDA(cudaMemcpyAsync(ctx->mailbox + CV_S_ERR, ctx->scalars + CV_S_ERR, sizeof(double),
+                            cudaMemcpyDeviceToHost, st));
   CV_CUDA(cudaStreamSynchronize(st));
+  if (ctx->peer && ctx->mailbox[CV_S_ERR] != 0.0) {
+    cv_set_error("peer-memory collective timed out waiting for another rank");
+    return CV_ERR_COMM;
+  }
   return CV_OK;
 }
 
@@ -772,8 +780,8 @@ static int launch_spmv_fmt(cv_ctx *ctx, cv_op *op, const SpmvArgs<T> &a, cudaStr
     d.ld = op->dia_ld;
     d.n_diag = op->n_diag;
     for (int k = 0; k < CV_MAX_DIAG; ++k) d.off[k] = k < op->n_diag ? op->dia_off[k] : 0;
-    d.halo_lo = static_cast<const T *>(op->halo_lo);
-    d.halo_hi = static_cast<const T *>(op->halo_hi);
+    d.halo_lo = static_cast<const T *>(op->peer_halo ? op->halo_lo_cur : op->halo_lo);
+    d.halo_hi = static_cast<const T *>(op->peer_halo ? op->halo_hi_cur : op->halo_hi);
     d.lo_len = op->lo_len;
     d.hi_len = op->hi_len;
     auto kf = k_spmv_dia<T, HALO, EPI, DOTS>;
@@ -845,6 +853,7 @@ static int launch_spmv_t(cv_ctx *ctx, cv_op *op, int mode, T sigma, const T *x, 
       CV_TRY(cv_halo_exchange_dia(ctx, op, sizeof(T) == 16, x, st));
     else
       CV_TRY(cv_halo_exchange(ctx, op, sizeof(T) == 16, x, st));
+    if (op->peer_halo) a.halo = static_cast<const T *>(op->halo_cur);  // parity of this exchange
   }
   int rc;
 #define GO(H, E, D) rc = launch_spmv_fmt<T, H, E, D>(ctx, op, a, st)

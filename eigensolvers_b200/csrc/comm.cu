@@ -104,6 +104,7 @@ extern "C" int cv_comm_finalize(cv_ctx *ctx) {
     delete ctx->comm;
     ctx->comm = nullptr;
   }
+  if (ctx && ctx->peer) cv_peer_detach(ctx);
   if (ctx) {
     ctx->world = 1;
     ctx->rank = 0;
@@ -114,6 +115,7 @@ extern "C" int cv_comm_finalize(cv_ctx *ctx) {
 extern "C" int cv_comm_allreduce(cv_ctx *ctx, double *buf_dev, int count, void *stream) {
   CV_REQUIRE(ctx && buf_dev && count >= 0, "cv_comm_allreduce: bad argument");
   if (ctx->world == 1 || count == 0) return CV_OK;
+  if (ctx->peer) return cv_peer_allreduce(ctx, buf_dev, count, (cudaStream_t)stream);
   CV_REQUIRE(ctx->comm, "cv_comm_allreduce: communicator not initialised");
   CV_NCCL(g_nccl.AllReduce(buf_dev, buf_dev, (size_t)count, ncclFloat64_, ncclSum_, ctx->comm->comm,
                            (cudaStream_t)stream));
@@ -145,6 +147,7 @@ extern "C" int cv_op_set_halo(cv_ctx *ctx, cv_op *op, int64_t n_halo, const int3
 
 int cv_halo_exchange(cv_ctx *ctx, cv_op *op, bool cplx_, const void *x, cudaStream_t st) {
   if (op->n_halo == 0 && (op->send_off.empty() || op->send_off.back() == 0)) return CV_OK;
+  if (op->peer_halo) return cv_halo_exchange_peer(ctx, op, cplx_, x, st);
   CV_REQUIRE(ctx->world > 1 && ctx->comm, "halo exchange without a communicator");
   const int64_t n_send = op->send_off[ctx->world];
   if (n_send > 0) {
@@ -199,19 +202,20 @@ extern "C" int cv_op_set_dia_halo(cv_ctx *ctx, cv_op *op, const int64_t *offsets
     int64_t s, c;
     // what p needs from my rows: first the part of p's lower band, then of its upper band
     overlap(p0 - op->lo_len < 0 ? 0 : p0 - op->lo_len, p0, r0, r1, s, c);
-    if (c > 0) op->dia_send.push_back({p, s - r0, c});
+    if (c > 0) op->dia_send.push_back({p, s - r0, c, 0, s - (p0 - op->lo_len)});
     overlap(p1, p1 + op->hi_len > N ? N : p1 + op->hi_len, r0, r1, s, c);
-    if (c > 0) op->dia_send.push_back({p, s - r0, c});
+    if (c > 0) op->dia_send.push_back({p, s - r0, c, 1, s - p1});
     // what I need from p's rows
     overlap(r0 - op->lo_len < 0 ? 0 : r0 - op->lo_len, r0, p0, p1, s, c);
-    if (c > 0) op->dia_recv_lo.push_back({p, s - (r0 - op->lo_len), c});
+    if (c > 0) op->dia_recv_lo.push_back({p, s - (r0 - op->lo_len), c, 0, 0});
     overlap(r1, r1 + op->hi_len > N ? N : r1 + op->hi_len, p0, p1, s, c);
-    if (c > 0) op->dia_recv_hi.push_back({p, s - r1, c});
+    if (c > 0) op->dia_recv_hi.push_back({p, s - r1, c, 1, 0});
   }
   return CV_OK;
 }
 
 int cv_halo_exchange_dia(cv_ctx *ctx, cv_op *op, bool cplx_, const void *x, cudaStream_t st) {
+  if (op->peer_halo) return cv_halo_exchange_dia_peer(ctx, op, cplx_, x, st);
   CV_REQUIRE(ctx->world > 1 && ctx->comm, "halo exchange without a communicator");
   CV_REQUIRE(op->n_global > 0, "DIA operator has no exchange plan (cv_op_set_dia_halo)");
   const size_t w = cplx_ ? 2 : 1;

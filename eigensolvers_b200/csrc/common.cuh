@@ -58,6 +58,13 @@ constexpr size_t CV_N_SCALARS = 4096;                    // doubles: reduction r
 constexpr size_t CV_N_PARTIALS = (size_t)1 << 21;        // doubles: per-CTA partial sums (16 MiB)
 
 struct cv_comm_state;  // NCCL state, comm.cu
+struct cv_peer_state;  // peer-memory transport (CUDA IPC windows over NVLink), peer.cu
+
+// peer-memory transport limits: one NVSwitch node
+constexpr int CV_MAX_WORLD = 8;
+constexpr int CV_AR_DEPTH = 4;       // all-reduce slots in flight (2 suffice, see peer.cu)
+constexpr int CV_AR_MAX = 1152;      // doubles per all-reduce message
+constexpr int CV_COUNTER_PUSH = 63;  // ticket of the halo push kernel inside ctx->counters
 
 // optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline)
 constexpr int CV_PROF_CLASSES = 4;  // 0 spmv, 1 tsdot, 2 tsupdate, 3 other vector kernels
@@ -81,6 +88,7 @@ struct cv_ctx {
   double *mailbox;      // pinned host mirror of `scalars`
   uint64_t launches;
   cv_comm_state *comm;  // null when world == 1
+  cv_peer_state *peer;  // non-null: collectives go through peer memory instead of NCCL
   int rank, world;
   cv_prof_state *prof;
   // GCROT re-orthogonalises only when the first Gram-Schmidt pass leaves less than eta of the
@@ -334,3 +342,4 @@ constexpr int CV_S_TMP = 0;        // 16 doubles: dot/norm results of the BLAS-1
 constexpr int CV_S_GS = 16;        // 4*CV_MAX_PTRS doubles: MGS coefficients
 constexpr int CV_S_TS = 1024;      // CV_MAX_RED doubles: tall-skinny results
 constexpr int CV_S_SOLVER = 2048;  // solver scalars (h columns, norms, ...)
+constexpr int CV_S_ERR = (int)CV_N_SCALARS - 1;  // raised (1.0) by a peer kernel whose bounded spin expired

@@ -2,4 +2,5 @@
 // shared by the API layer, the solvers and the communication layer).
 #include "api.cu"
 #include "comm.cu"
+#include "peer.cu"
 #include "solvers.cu"

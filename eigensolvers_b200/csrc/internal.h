@@ -26,7 +26,9 @@ struct cv_op {
   int64_t dia_ld = 0;
   int lo_len = 0, hi_len = 0;          // band below / above the owned rows (sharded mode)
   void *halo_lo = nullptr, *halo_hi = nullptr;
-  struct Range { int peer; int64_t start, count; };  // start: local row (send) / buffer slot (recv)
+  // start: local row (send) / buffer slot (recv); band/dst_off: where a SENT range lands at the
+  // peer (0 = its lower band buffer, 1 = upper) — used by the peer-memory push
+  struct Range { int peer; int64_t start, count; int band; int64_t dst_off; };
   std::vector<Range> dia_send, dia_recv_lo, dia_recv_hi;
   int64_t row0 = 0, n_global = 0;
   // row-sharded mode: columns >= n_cols - n_halo address the halo buffer
@@ -34,6 +36,13 @@ struct cv_op {
   const int32_t *send_idx = nullptr;
   std::vector<int64_t> send_off, recv_off;
   void *sendbuf = nullptr, *halobuf = nullptr;
+  // peer-memory transport: halo buffers live in IPC-exported allocations, double-buffered by the
+  // parity of the exchange sequence number; *_cur point at the parity the next SpMV reads
+  bool peer_halo = false;
+  std::vector<void *> peer_base;         // [world] base of every rank's halo allocation (own at [rank])
+  std::vector<int64_t> peer_stride;      // [world] bytes between the two parities (general halo)
+  std::vector<int64_t> peer_dst_off;     // [world] element offset of MY block inside peer p's halo
+  void *halo_cur = nullptr, *halo_lo_cur = nullptr, *halo_hi_cur = nullptr;
 };
 
 int cv_check_launch(cv_ctx *ctx, const char *what);
@@ -56,3 +65,7 @@ int cv_spmv_dev(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double 
                 cudaStream_t st);
 int cv_halo_exchange(cv_ctx *ctx, cv_op *op, bool cplx_, const void *x, cudaStream_t st);
 int cv_halo_exchange_dia(cv_ctx *ctx, cv_op *op, bool cplx_, const void *x, cudaStream_t st);
+int cv_halo_exchange_peer(cv_ctx *ctx, cv_op *op, bool cplx_, const void *x, cudaStream_t st);
+int cv_halo_exchange_dia_peer(cv_ctx *ctx, cv_op *op, bool cplx_, const void *x, cudaStream_t st);
+int cv_peer_detach(cv_ctx *ctx);
+int cv_peer_allreduce(cv_ctx *ctx, double *buf_dev, int count, cudaStream_t st);

@@ -27,6 +27,7 @@ class DeviceOperator:
         self.shape = tuple(int(s) for s in shape)  # GLOBAL shape
         self.handle = C.c_void_p()
         self._keep = []  # tensors owning device memory
+        self._peer_owned = []  # this rank's CUDA-IPC exported halo buffers (peer-memory transport)
         self.nnz = 0
         self.padded_nnz = 0
         self.n_local = self.shape[0]
@@ -40,6 +41,9 @@ class DeviceOperator:
             if self.handle:
                 self.rt.lib.cv_op_destroy(self.handle)
                 self.handle = C.c_void_p()
+            for own in self._peer_owned:
+                self.rt.peer_release(own)
+            self._peer_owned = []
         except Exception:
             pass
 
@@ -179,6 +183,14 @@ class DeviceOperator:
             off = rt.offsets_for(self.shape[0])
             _lib.check(rt.lib.cv_op_set_dia_halo(rt.ctx, self.handle, off.ctypes.data, halo_lo.data_ptr(),
                                                  halo_hi.data_ptr()))
+            if rt.transport == "peer":
+                # neighbours push their boundary rows straight into these buffers over NVLink
+                ptrs, _ = rt.peer_shared_alloc(rt.lib.cv_op_dia_halo_bytes(self.handle))
+                if ptrs is not None:
+                    self._peer_owned.append(ptrs[rt.rank])
+                    arr = (C.c_void_p * rt.world)(*ptrs)
+                    _lib.check(rt.lib.cv_op_set_dia_halo_peers(rt.ctx, self.handle,
+                                                               C.cast(arr, C.POINTER(C.c_void_p))))
         return True
 
     # ---------------------------------------------------------------------------------------
@@ -281,6 +293,17 @@ class DeviceOperator:
         _lib.check(rt.lib.cv_op_set_halo(rt.ctx, self.handle, self.n_halo, d_send.data_ptr(),
                                          self._send_off.ctypes.data, self._recv_off.ctypes.data,
                                          sendbuf.data_ptr(), halobuf.data_ptr()))
+        if rt.transport == "peer":
+            # halo buffer in exportable memory, two parities; peers gather-push into it
+            stride = (16 * max(self.n_halo, 1) + 255) // 256 * 256
+            ptrs, infos = rt.peer_shared_alloc(2 * stride, (stride, [int(x) for x in self._recv_off]))
+            if ptrs is not None:
+                self._peer_owned.append(ptrs[rt.rank])
+                arr = (C.c_void_p * rt.world)(*ptrs)
+                strides = np.ascontiguousarray([i[0] for i in infos], dtype=np.int64)
+                dst_off = np.ascontiguousarray([i[1][rt.rank] for i in infos], dtype=np.int64)
+                _lib.check(rt.lib.cv_op_set_halo_peers(rt.ctx, self.handle, C.cast(arr, C.POINTER(C.c_void_p)),
+                                                       strides.ctypes.data, dst_off.ctypes.data))
 
     # -- roofline bookkeeping ----------------------------------------------------
     def algorithmic_bytes(self, cplx=False):

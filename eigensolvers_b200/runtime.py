@@ -40,6 +40,7 @@ class Runtime:
         self._workspaces = {}
         self._op_cache = {}
         self._tmp = {}
+        self._peer_allocs = []
         self.stats = {"solves": 0, "matvecs": 0, "syncs": 0, "outer": 0}
 
     # -- singletons ---------------------------------------------------------------------------
@@ -55,6 +56,8 @@ class Runtime:
         if inst is not None:
             inst._op_cache.clear()
             inst._workspaces.clear()
+            for own, _ in list(inst._peer_allocs):
+                inst.peer_release(own)
             inst.lib.cv_ctx_destroy(inst.ctx)
         cls._instance = None
 
@@ -115,7 +118,74 @@ class Runtime:
         uid = (C.c_char * 128).from_buffer_copy(box[0])
         _lib.check(self.lib.cv_comm_init(self.ctx, uid, rank, world))
         self.rank, self.world = rank, world
+        self._attach_peer_windows()
         return self
+
+    # -- peer-memory transport (csrc/peer.cu) ---------------------------------------------------
+    @property
+    def transport(self):
+        """'single' | 'nccl' | 'peer' — what the scalar all-reduce and the halo exchange use."""
+        code = C.c_int()
+        _lib.check(self.lib.cv_comm_transport(self.ctx, C.byref(code)))
+        return ("single", "nccl", "peer")[code.value]
+
+    def peer_shared_alloc(self, nbytes, info=None):
+        """Collective: every rank allocates `nbytes` (its own value) of CUDA-IPC exportable device
+        memory and maps the other ranks' allocations.  Returns (ptrs[world], infos[world]) — ptrs[p]
+        is rank p's allocation as addressable from THIS process — or (None, infos) if some rank
+        could not export/map (the caller then stays on NCCL)."""
+        import torch.distributed as dist
+        own, handle = C.c_void_p(), (C.c_char * 64)()
+        rc = self.lib.cv_peer_alloc(self.ctx, int(nbytes), C.byref(own), handle)
+        box = [None] * self.world
+        dist.all_gather_object(box, (bytes(handle) if rc == 0 else None, info))
+        infos = [b[1] for b in box]
+        ptrs, opened, ok = [None] * self.world, [], all(b[0] is not None for b in box)
+        if ok:
+            for p in range(self.world):
+                if p == self.rank:
+                    ptrs[p] = own.value
+                    continue
+                q = C.c_void_p()
+                if self.lib.cv_peer_open(self.ctx, (C.c_char * 64).from_buffer_copy(box[p][0]), C.byref(q)) != 0:
+                    ok = False
+                    break
+                ptrs[p] = q.value
+                opened.append(q.value)
+        flags = [None] * self.world
+        dist.all_gather_object(flags, ok)
+        if not all(flags):
+            for q in opened:
+                self.lib.cv_peer_close(self.ctx, C.c_void_p(q))
+            if rc == 0:
+                self.lib.cv_peer_free(self.ctx, own)
+            return None, infos
+        self._peer_allocs.append((own.value, opened))
+        return ptrs, infos
+
+    def peer_release(self, own_ptr):
+        """Unmap / free one peer_shared_alloc (identified by this rank's own pointer)."""
+        for i, (own, opened) in enumerate(self._peer_allocs):
+            if own == own_ptr:
+                self.torch.cuda.synchronize(self.device)
+                for q in opened:
+                    self.lib.cv_peer_close(self.ctx, C.c_void_p(q))
+                self.lib.cv_peer_free(self.ctx, C.c_void_p(own))
+                del self._peer_allocs[i]
+                return
+
+    def _attach_peer_windows(self):
+        self._peer_allocs = []
+        if os.environ.get("EIGB200_TRANSPORT", "peer").lower() != "peer" or self.world > 8:
+            return
+        ptrs, _ = self.peer_shared_alloc(self.lib.cv_peer_window_bytes())
+        if ptrs is None:
+            import warnings
+            warnings.warn("CUDA IPC peer mapping unavailable: collectives stay on NCCL "
+                          f"({self.lib.cv_last_error().decode()})")
+            return
+        arr = (C.c_void_p * self.world)(*ptrs)
+        _lib.check(self.lib.cv_comm_attach_peers(self.ctx, C.cast(arr, C.POINTER(C.c_void_p))))
 
     def offsets_for(self, n):
         from .partition import row_offsets

@@ -37,7 +37,7 @@ extern "C" {
 #define CV_ERR_ARG 2         /* invalid argument                                        */
 #define CV_ERR_UNSUPPORTED 3 /* combination not implemented                             */
 #define CV_ERR_NUMERIC 4     /* non-finite value met inside a solver (scipy LinAlgError) */
-#define CV_ERR_COMM 5        /* NCCL failure                                            */
+#define CV_ERR_COMM 5        /* NCCL / peer-memory transport failure                    */
 
 /* spmv modes */
 #define CV_SPMV_PLAIN 0   /* y = H x            numpyVector.py:98-100 (applyOp)          */
@@ -82,6 +82,23 @@ int cv_comm_finalize(cv_ctx *ctx);
 /* Sum `count` doubles in place over all ranks (device buffer); no-op for world 1. */
 int cv_comm_allreduce(cv_ctx *ctx, double *buf_dev, int count, void *stream);
 
+/* Peer-memory transport (csrc/peer.cu): inside one NVSwitch node the scalar all-reduce and the
+ * halo exchange run over CUDA-IPC-mapped peer memory (P2P stores + sequence flags over NVLink)
+ * instead of NCCL calls.  The host language allocates exportable device memory with
+ * cv_peer_alloc (handle64 = the 64-byte cudaIpcMemHandle_t to ship to the other ranks, e.g. with
+ * torch.distributed.all_gather_object), maps the other ranks' allocations with cv_peer_open and
+ * registers (a) one window of cv_peer_window_bytes() per rank with cv_comm_attach_peers
+ * (window_ptrs[p] = rank p's window as mapped in THIS process, own allocation at [rank]) and
+ * (b) per operator the halo buffers (cv_op_set_halo_peers / cv_op_set_dia_halo_peers).
+ * cv_comm_transport: 0 = single GPU, 1 = NCCL, 2 = peer memory.                               */
+size_t cv_peer_window_bytes(void);
+int cv_peer_alloc(cv_ctx *ctx, size_t bytes, void **ptr_dev, void *handle64);
+int cv_peer_open(cv_ctx *ctx, const void *handle64, void **ptr_dev);
+int cv_peer_close(cv_ctx *ctx, void *ptr_dev);
+int cv_peer_free(cv_ctx *ctx, void *ptr_dev);
+int cv_comm_attach_peers(cv_ctx *ctx, void *const *window_ptrs /* world */);
+int cv_comm_transport(cv_ctx *ctx, int *transport);
+
 /* Host-side integer routines (bit-exact vs. the scipy slicing oracle).
  * cv_partition_rows: offsets[p] = floor(p*n/P), p = 0..P.
  * cv_halo_count / cv_halo_build: for the row block [row0,row1) of a CSR matrix with GLOBAL
@@ -103,6 +120,13 @@ int cv_op_set_halo(cv_ctx *ctx, cv_op *op, int64_t n_halo, const int32_t *send_i
                    const int64_t *send_off /* host, world+1 */,
                    const int64_t *recv_off /* host, world+1 */, void *sendbuf_dev,
                    void *halobuf_dev /* each 16*max(n_send,n_halo) bytes */);
+
+/* Peer-memory halo of a general (SELL/CSR) operator, after cv_op_set_halo: halo_base[p] = rank
+ * p's halo allocation (2 parities of parity_stride_bytes[p] each; 16 bytes per halo slot),
+ * dst_off_elems[p] = first slot of MY block inside rank p's halo (p's recv_off[my rank]).      */
+int cv_op_set_halo_peers(cv_ctx *ctx, cv_op *op, void *const *halo_base /* world */,
+                         const int64_t *parity_stride_bytes /* world */,
+                         const int64_t *dst_off_elems /* world */);
 
 /* ---- operator ------------------------------------------------------------------------- */
 /* Borrow a CSR matrix already resident on the device (int64 indptr, int32 column indices,
@@ -131,6 +155,11 @@ int cv_op_attach_dia(cv_ctx *ctx, cv_op *op, int n_diag, const int32_t *offsets_
  * contiguous range sends derived from the partition `offsets` (host, world+1).                   */
 int cv_op_set_dia_halo(cv_ctx *ctx, cv_op *op, const int64_t *offsets, void *halo_lo_dev,
                        void *halo_hi_dev);
+/* Peer-memory halo of a DIA operator, after cv_op_set_dia_halo: every rank allocates
+ * cv_op_dia_halo_bytes(op) with cv_peer_alloc (same layout on all ranks: two parities of
+ * [lower band | upper band]); halo_base[p] = rank p's allocation as mapped here.              */
+size_t cv_op_dia_halo_bytes(cv_op *op);
+int cv_op_set_dia_halo_peers(cv_ctx *ctx, cv_op *op, void *const *halo_base /* world */);
 int cv_op_set_format(cv_op *op, int fmt);
 int cv_op_info(cv_op *op, int64_t *n_rows, int64_t *nnz, int64_t *padded_nnz, int *fmt);
 

@@ -15,6 +15,12 @@ Cases:
                reference's calculateQuadrature/updateQ outputs for them
   lap_blk      block Lanczos on a 12^3 Laplacian + potential (C2's generator at small N)
   osc_1        single-vector Lanczos on a 600-dim coupled-oscillator Hamiltonian (C3's generator)
+  lanczos_lindep  unittests/test_lanczosLINDEP.py setup (n=1200, loose solves rtol 1e-1, L=100: a
+               30-vector Krylov list; with SciPy 1.18 the run converges WITHOUT tripping LINDEP —
+               the reference's own test notes "may fail on some machines")
+
+`python oracle/ref_harness/make_golden.py [case ...]` regenerates only the named cases (outputs
+depend on the BLAS in the last digits, so untouched fixtures are left alone).
 """
 import json
 import math
@@ -266,14 +272,35 @@ def case_osc():
     summary["osc_1"] = status_scalars(st)
 
 
+def case_lindep():
+    # unittests/test_lanczosLINDEP.py:9-31
+    n = 1200
+    ev = np.linspace(1, 400, n)
+    np.random.seed(10)
+    Q = la.qr(np.random.rand(n, n))[0]
+    A = Q.T @ np.diag(ev) @ Q
+    Y0 = np.random.random(n)
+    o = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 500, "linear_tol": 1e-1}}
+    lf, xf, st = run_lanczos(A, NumpyVector(Y0.copy(), o), 390, 100, 1000, 1e-12,
+                             status={"writeOut": False, "writePlot": False})
+    # A is rebuilt from the seed by the tests (11 MB dense); only outputs are stored
+    save("lanczos_lindep", Y0=Y0, ev=lf, vecs=np.array([v.array for v in xf[:4]]), exact=ev)
+    summary["lanczos_lindep"] = dict(status_scalars(st), n_vectors=len(xf))
+
+
 if __name__ == "__main__":
+    all_cases = dict(ops=case_ops, solve=case_solve, c1=case_c1, t1=case_t1, blk=case_blk, ho=case_ho,
+                     feast=case_feast, fortran=case_fortran, lap_blk=case_lap_blk, osc=case_osc,
+                     lindep=case_lindep)
+    chosen = sys.argv[1:] or list(all_cases)
+    if sys.argv[1:] and os.path.exists(os.path.join(GOLD, "summary.json")):
+        summary.update(json.load(open(os.path.join(GOLD, "summary.json"))))
     with tempfile.TemporaryDirectory() as tmp:
         os.chdir(tmp)  # the drivers open files / saveTNSs in the CWD
-        for case in (case_ops, case_solve, case_c1, case_t1, case_blk, case_ho, case_feast,
-                     case_fortran, case_lap_blk, case_osc):
-            case()
+        for name in chosen:
+            all_cases[name]()
     import scipy
-    summary["_versions"] = dict(numpy=np.__version__, scipy=scipy.__version__)
+    summary.setdefault("_versions", dict(numpy=np.__version__, scipy=scipy.__version__))
     with open(os.path.join(GOLD, "summary.json"), "w") as fh:
         json.dump(summary, fh, indent=1, sort_keys=True)
     print(json.dumps(summary, indent=1, sort_keys=True))

@@ -97,6 +97,28 @@ def test_reference_unit_test_lanczos(rt):
     np.testing.assert_allclose(np.sort(ev), np.sort(g["ev"]), rtol=1e-6)
 
 
+def test_reference_unit_test_lindep_setup(rt):
+    """unittests/test_lanczosLINDEP.py set-up on CudaVector (n=1200, rtol 1e-1, L=100): the Krylov
+    list grows to ~30 vectors, stressing orthogonalize_against_set and the extend* columns.  The
+    inner solves are very loose, so trajectories may differ; the converged pair must agree."""
+    from eigensolvers_b200 import CudaVector
+    g = gold("lanczos_lindep")
+    n = 1200
+    np.random.seed(10)
+    Q = la.qr(np.random.rand(n, n))[0]
+    A = Q.T @ np.diag(np.linspace(1, 400, n)) @ Q
+    o = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 500, "linear_tol": 1e-1}}
+    ev, vecs, st = _run(A, CudaVector(g["Y0"].copy(), o), 390, 100, 1000, 1e-12)
+    ref = summary()["lanczos_lindep"]
+    assert st["isConverged"] and not st["lindep"]
+    assert abs(st["cumIter"] - ref["cumIter"]) <= 3
+    i, j = np.argmin(abs(ev - 390)), np.argmin(abs(g["ev"] - 390))
+    assert abs(ev[i] - g["ev"][j]) <= 1e-10 * abs(g["ev"][j])
+    assert j < 4 and _overlap(vecs[i].array, g["vecs"][j]) >= 1 - 1e-8
+    S = CudaVector.overlapMatrix(vecs)
+    np.testing.assert_allclose(S, np.eye(len(vecs)), atol=1e-5)
+
+
 def test_reference_unit_test_block(rt):
     """unittests/test_lanczosBlock.py on CudaVector (3-fold degenerate target)."""
     from eigensolvers_b200 import CudaVector

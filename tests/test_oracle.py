@@ -130,6 +130,29 @@ def test_lanczos_unit_test_setups_match_reference():
     np.testing.assert_allclose(ev[:3], g["exact"][5:8], rtol=1e-6)  # test_lanczosBlock.py:54
 
 
+def _lindep_matrix():
+    # unittests/test_lanczosLINDEP.py:12-16 (seeded; the 11 MB dense matrix is not stored)
+    n = 1200
+    ev = np.linspace(1, 400, n)
+    np.random.seed(10)
+    Q = la.qr(np.random.rand(n, n))[0]
+    return Q.T @ np.diag(ev) @ Q
+
+
+def test_lanczos_lindep_setup_matches_reference():
+    """unittests/test_lanczosLINDEP.py set-up (loose rtol 1e-1 solves, L=100): a 30-vector Krylov
+    list, every new vector orthogonalised against all previous ones (numpyVector.py:121-145)."""
+    g = gold("lanczos_lindep")
+    A = _lindep_matrix()
+    o = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 500, "linear_tol": 1e-1}}
+    ev, vecs, st = _run(A, NV(g["Y0"].copy(), o), 390, 100, 1000, 1e-12)
+    _check_status(st, "lanczos_lindep")
+    assert len(vecs) == summary()["lanczos_lindep"]["n_vectors"]
+    np.testing.assert_allclose(ev, g["ev"], rtol=1e-12, atol=0)      # QR of the seeded matrix is LAPACK-order dependent
+    for i in range(4):
+        assert abs(np.vdot(vecs[i].array, g["vecs"][i])) >= 1 - 1e-10
+
+
 def test_lanczos_state_following_matches_reference():
     g = gold("lanczos_ho")
     o = opts("gcrotmk", 1e-4, 30000)
