@@ -43,7 +43,12 @@ extern "C" int cv_ctx_create(int device, void *scratch_dev, size_t scratch_bytes
   p += CV_N_SCALARS * sizeof(double);
   c->partials = reinterpret_cast<double *>(p);
   CV_CUDA(cudaMemset(scratch_dev, 0, CV_N_COUNTERS * sizeof(unsigned) + CV_N_SCALARS * sizeof(double)));
-  CV_CUDA(cudaMallocHost(&c->mailbox, CV_N_SCALARS * sizeof(double)));
+  CV_CUDA(cudaMallocHost(&c->mailbox, (CV_N_SCALARS + 8) * sizeof(double)));
+  c->host_flag = reinterpret_cast<unsigned long long *>(c->mailbox + CV_N_SCALARS);
+  *c->host_flag = 0ull;
+  c->host_seq = 0ull;
+  c->prepushed_x = nullptr;
+  c->prepushed_op = nullptr;
   c->launches = 0;
   c->prof = nullptr;
   c->reorth_eta = 0.1;
@@ -585,6 +590,113 @@ int cv_tsupdate_dev(cv_ctx *ctx, int64_t n, int cplx_, int m, const void *const 
 }
 
 // ------------------------------------------------------------------------------------------
+// fused Arnoldi orthogonalisation step (kernels_orth.cuh)
+// ------------------------------------------------------------------------------------------
+// Poll the mailbox flag the fused kernel releases once its scalars are in host memory.
+int cv_wait_mailbox(cv_ctx *ctx, unsigned long long seq, cudaStream_t st) {
+  volatile unsigned long long *flag = ctx->host_flag;
+  unsigned long long spins = 0;
+  while (*flag < seq) {
+    if ((++spins & 0xFFFFull) == 0) {
+      cudaError_t e = cudaStreamQuery(st);
+      if (e == cudaSuccess) {
+        if (*flag >= seq) break;
+        cv_set_error("fused Arnoldi step finished without publishing its results");
+        return CV_ERR_CUDA;
+      }
+      if (e != cudaErrorNotReady) {
+        cv_set_error("fused Arnoldi step failed: %s", cudaGetErrorString(e));
+        return CV_ERR_CUDA;
+      }
+    }
+  }
+  __sync_synchronize();
+  if (ctx->peer && ctx->mailbox[CV_S_ERR] != 0.0) {
+    cv_set_error("peer-memory collective timed out waiting for another rank");
+    return CV_ERR_COMM;
+  }
+  return CV_OK;
+}
+
+// One launch: h = basis^H w, w -= basis h (twice if needed), w /= |w|, halo push of the new w.
+// Scalar slots (doubles in ctx->scalars, mirrored to the mailbox): s_flag, s_flag+1 = |w'|^2,
+// s_flag+2..4 = SpMV dots, s_flag+5.. = h1, s_h2.. = h2.  *fused = false when this configuration
+// has to take the separate-kernel path (NCCL transport).
+int cv_orth_step_dev(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int m, const void *const *basis, void *w,
+                     int s_flag, int s_h2, cudaStream_t st, bool *fused) {
+  *fused = false;
+  if (ctx->world > 1 && !ctx->peer) return CV_OK;
+  CV_REQUIRE(m >= 1 && m <= CV_MAX_PTRS, "orth_step: m=%d out of range", m);
+  OrthArgs a;
+  a.p.m = m;
+  a.p.b = 1;
+  a.p.n = n;
+  int W = cplx_ ? 1 : 2;
+  for (int i = 0; i < m; ++i) {
+    a.p.v[i] = basis[i];
+    if ((uintptr_t)basis[i] & 15) W = 1;
+  }
+  if ((uintptr_t)w & 15) W = 1;
+  a.p.w[0] = w;
+  a.partials = ctx->partials;
+  a.bar = ctx->counters + CV_COUNTER_BAR;
+  a.scal = ctx->scalars;
+  a.s_flag = s_flag;
+  a.s_nrm = s_flag + 1;
+  a.s_w = s_flag + 2;
+  a.s_h1 = s_flag + 5;
+  a.s_h2 = s_h2;
+  a.eta2 = ctx->reorth_eta * ctx->reorth_eta;
+  a.me = ctx->rank;
+  a.world = ctx->world;
+  a.err = ctx->scalars + CV_S_ERR;
+  for (int p = 0; p < CV_MAX_WORLD; ++p) a.pp.win[p] = nullptr;
+  a.push.nseg = 0;
+  a.push.nflag = 0;
+  a.push.seq = 0;
+  a.push.ticket = ctx->counters + CV_COUNTER_PUSH;
+  if (ctx->world > 1) {
+    a.pp = *cv_peer_ptrs(ctx);
+    const bool dia = op->fmt == CV_FMT_DIA;
+    const bool halo = dia ? (op->lo_len > 0 || op->hi_len > 0) : (op->n_halo > 0 || (!op->send_off.empty() && op->send_off.back() > 0));
+    if (halo && op->peer_halo) {
+      CV_TRY(cv_peer_plan_exchange(ctx, op, cplx_ != 0, &a.push, nullptr));
+      ctx->prepushed_x = w;
+      ctx->prepushed_op = op;
+    }
+  }
+  a.host_mb = ctx->mailbox;
+  a.host_flag = ctx->host_flag;
+  a.host_seq = ++ctx->host_seq;
+  const void *kf = cplx_ ? (const void *)k_orth_step<cplx, 1>
+                         : (W == 2 ? (const void *)k_orth_step<double, 2> : (const void *)k_orth_step<double, 1>);
+  const size_t sh = sizeof(double) * m * (cplx_ ? 2 : 1);
+  // co-resident CTAs of this kernel with its largest dynamic shared-memory request
+  static std::unordered_map<const void *, int> occ_cache;
+  auto it = occ_cache.find(kf);
+  if (it == occ_cache.end()) {
+    int occ = 0;
+    CV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf, CV_BLOCK, sizeof(double) * 2 * CV_MAX_PTRS));
+    CV_REQUIRE(occ >= 1, "orth_step: kernel does not fit on an SM");
+    it = occ_cache.emplace(kf, occ).first;
+  }
+  const int cap = it->second * ctx->sms;
+  const int ny = (m + 15) / 16;
+  int64_t need = (n / W + CV_BLOCK - 1) / CV_BLOCK;
+  if (need < ny) need = ny;
+  const int grid = (int)(need < cap ? need : cap);
+  CV_REQUIRE(grid >= ny, "orth_step: grid %d smaller than %d slabs", grid, ny);
+  void *params[1] = {(void *)&a};
+  {
+    cv_prof_scope prof(ctx, 1, st);
+    CV_CUDA(cudaLaunchCooperativeKernel(kf, dim3(grid), dim3(CV_BLOCK), params, sh, st));
+  }
+  CV_TRY(cv_check_launch(ctx, "orth_step"));
+  *fused = true;
+  return cv_wait_mailbox(ctx, a.host_seq, st);
+}
+
+// ------------------------------------------------------------------------------------------
 // Gram-Schmidt against a set (reference semantics, numpyVector.py:121-145)
 // ------------------------------------------------------------------------------------------
 template <typename T, int W>
@@ -845,6 +957,7 @@ static int launch_spmv_t(cv_ctx *ctx, cv_op *op, int mode, T sigma, const T *x, 
   a.partials = ctx->partials;
   a.counter = ctx->counters;
   a.out = dots_slot >= 0 ? ctx->scalars + dots_slot : nullptr;
+  a.wait = HaloWait{nullptr, 0u, 0ull, nullptr};
   const bool dia = op->fmt == CV_FMT_DIA;
   const bool halo = dia ? (ctx->world > 1 && (op->lo_len > 0 || op->hi_len > 0)) : op->n_halo > 0;
   const bool dots = dots_slot >= 0;
@@ -853,7 +966,10 @@ static int launch_spmv_t(cv_ctx *ctx, cv_op *op, int mode, T sigma, const T *x, 
       CV_TRY(cv_halo_exchange_dia(ctx, op, sizeof(T) == 16, x, st));
     else
       CV_TRY(cv_halo_exchange(ctx, op, sizeof(T) == 16, x, st));
-    if (op->peer_halo) a.halo = static_cast<const T *>(op->halo_cur);  // parity of this exchange
+    if (op->peer_halo) {
+      a.halo = static_cast<const T *>(op->halo_cur);  // parity of this exchange
+      a.wait = op->wait;                              // the kernel polls its sources' flags itself
+    }
   }
   int rc;
 #define GO(H, E, D) rc = launch_spmv_fmt<T, H, E, D>(ctx, op, a, st)

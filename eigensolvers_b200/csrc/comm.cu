@@ -215,7 +215,7 @@ extern "C" int cv_op_set_dia_halo(cv_ctx *ctx, cv_op *op, const int64_t *offsets
 }
 
 int cv_halo_exchange_dia(cv_ctx *ctx, cv_op *op, bool cplx_, const void *x, cudaStream_t st) {
-  if (op->peer_halo) return cv_halo_exchange_dia_peer(ctx, op, cplx_, x, st);
+  if (op->peer_halo) return cv_halo_exchange_peer(ctx, op, cplx_, x, st);
   CV_REQUIRE(ctx->world > 1 && ctx->comm, "halo exchange without a communicator");
   CV_REQUIRE(op->n_global > 0, "DIA operator has no exchange plan (cv_op_set_dia_halo)");
   const size_t w = cplx_ ? 2 : 1;

@@ -65,6 +65,7 @@ constexpr int CV_MAX_WORLD = 8;
 constexpr int CV_AR_DEPTH = 4;       // all-reduce slots in flight (2 suffice, see peer.cu)
 constexpr int CV_AR_MAX = 1152;      // doubles per all-reduce message
 constexpr int CV_COUNTER_PUSH = 63;  // ticket of the halo push kernel inside ctx->counters
+constexpr int CV_COUNTER_BAR = 60;   // {arrivals, generation} of the fused Arnoldi step's grid barrier
 
 // optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline)
 constexpr int CV_PROF_CLASSES = 4;  // 0 spmv, 1 tsdot, 2 tsupdate, 3 other vector kernels
@@ -96,6 +97,12 @@ struct cv_ctx {
   // basis orthogonal to ~10 eps while skipping the second pass in all but cancelling steps
   double reorth_eta;
   bool defer_reduce;  // solvers batch several reductions into one all-reduce
+  // fused Arnoldi step: results arrive in the mailbox followed by a released sequence flag
+  unsigned long long *host_flag;  // pinned, device-visible
+  unsigned long long host_seq;
+  // the vector whose halo phase C of the fused step has already pushed (next SpMV skips its push)
+  const void *prepushed_x;
+  const void *prepushed_op;
 };
 
 // RAII bracket: records an event pair around the launches issued inside its scope
@@ -252,6 +259,13 @@ __device__ __forceinline__ cplx ld_plain(const cplx *p) {
   double2 v = *reinterpret_cast<const double2 *>(p);
   return make_cplx(v.x, v.y);
 }
+// L2-only loads (ld.global.cg): data another SM may have rewritten earlier in the SAME kernel
+// (fused multi-phase kernels) must not be served from a stale L1 line
+__device__ __forceinline__ double ld_cg(const double *p) { return __ldcg(p); }
+__device__ __forceinline__ cplx ld_cg(const cplx *p) {
+  double2 v = __ldcg(reinterpret_cast<const double2 *>(p));
+  return make_cplx(v.x, v.y);
+}
 __device__ __forceinline__ void st_plain(double *p, double v) { *p = v; }
 __device__ __forceinline__ void st_plain(cplx *p, cplx v) {
   *reinterpret_cast<double2 *>(p) = make_double2(v.re, v.im);
@@ -335,6 +349,200 @@ __device__ __forceinline__ void grid_reduce_dyn(const double *s_vals, int nv, do
     if (lane == 0) out[v] = r;
   }
   if (threadIdx.x == 0) *counter = 0u;
+}
+
+// ------------------------------------------------------------------------------------------
+// peer-memory transport, device side (host side and protocol notes: peer.cu)
+// ------------------------------------------------------------------------------------------
+constexpr unsigned long long CV_PEER_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+
+struct PeerWindow {  // one per rank, in CUDA-IPC exported device memory, mapped by every peer
+  unsigned long long halo_flag[CV_MAX_WORLD];  // [src] halo sequence published by src
+  unsigned long long ar_seq;                   // local all-reduce counter (owner only)
+  unsigned long long pad[23];
+  // all-reduce mailboxes, LL protocol (as NCCL's low-latency protocol): every double travels as ONE
+  // 16-byte store {lo32, seq32, hi32, seq32}; each 8-byte half carries its own tag, so the
+  // receiver needs no fence and no separate flag: it polls the slot until both tags match.
+  uint4 ar_ll[CV_AR_DEPTH][CV_MAX_WORLD][CV_AR_MAX];  // [slot][src][value]
+};
+struct PeerPtrs {
+  PeerWindow *win[CV_MAX_WORLD];
+};
+struct PushSeg {
+  void *dst;           // peer memory
+  const int32_t *idx;  // null: contiguous range starting at src_start
+  int64_t src_start;
+  int64_t count;       // elements
+};
+struct PushArgs {
+  PushSeg seg[2 * CV_MAX_WORLD];
+  int nseg;
+  unsigned long long *flag_dst[CV_MAX_WORLD];  // halo_flag[me] in each destination's window
+  int nflag;
+  unsigned long long seq;
+  unsigned *ticket;
+};
+// what a sharded SpMV waits for before it reads its halo buffers
+struct HaloWait {
+  const unsigned long long *flags;  // own window's halo_flag
+  unsigned mask;                    // source ranks
+  unsigned long long seq;
+  double *err;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double *p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until *flag >= seq; false when the bounded wait expires (a peer died)
+__device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsigned long long seq) {
+  if (ld_acquire_sys(flag) >= seq) return true;
+  const unsigned long long t0 = global_ns();
+  for (;;) {
+    for (int i = 0; i < 64; ++i)
+      if (ld_acquire_sys(flag) >= seq) return true;
+    if (global_ns() - t0 > CV_PEER_TIMEOUT_NS) return false;
+  }
+}
+// CTA prologue of a sharded SpMV: the halo of this exchange has landed
+__device__ __forceinline__ void halo_wait_cta(const HaloWait &w) {
+  if (w.mask == 0u) return;
+  if (threadIdx.x < CV_MAX_WORLD && ((w.mask >> threadIdx.x) & 1u))
+    if (!wait_flag(w.flags + threadIdx.x, w.seq)) *w.err = 1.0;
+  __syncthreads();
+}
+
+__device__ __forceinline__ void st_ll(uint4 *p, double v, unsigned tag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"((unsigned)b), "r"(tag),
+               "r"((unsigned)(b >> 32)), "r"(tag)
+               : "memory");
+}
+__device__ __forceinline__ bool ld_ll(const uint4 *p, unsigned tag, double &v) {
+  unsigned lo, f1, hi, f2;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2) : "l"(p) : "memory");
+  if (f1 != tag || f2 != tag) return false;
+  v = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+  return true;
+}
+
+// All-reduce (sum, in place) of buf[0..count), count <= CV_AR_MAX, executed by ALL threads of ONE
+// CTA.  Thread t sends value t to every peer's mailbox (one tagged 16-byte store over NVLink per
+// peer), then polls its own mailboxes for the other ranks' value t and sums in rank order, so all
+// ranks compute bit-identical sums.  One one-way NVLink latency, no fences.  Mailbox slot reuse:
+// slot = seq % CV_AR_DEPTH is rewritten at seq + DEPTH, which a rank can only reach after every
+// rank has contributed to seq + DEPTH - 1, i.e. finished reading seq.
+__device__ __forceinline__ void cta_peer_allreduce(const PeerPtrs &pp, int me, int world, double *buf,
+                                                   int count, double *err) {
+  __shared__ int s_bad;
+  PeerWindow *own = pp.win[me];
+  __syncthreads();
+  const unsigned long long seq = own->ar_seq + 1;
+  if (threadIdx.x == 0) s_bad = 0;
+  const unsigned tag = (unsigned)seq;
+  const int slot = (int)(seq % CV_AR_DEPTH);
+  for (int t = threadIdx.x; t < count; t += blockDim.x) {
+    const double v = __ldcg(buf + t);
+    for (int p = 0; p < world; ++p)
+      if (p != me) st_ll(&pp.win[p]->ar_ll[slot][me][t], v, tag);
+  }
+  for (int t = threadIdx.x; t < count; t += blockDim.x) {
+    const double mine = __ldcg(buf + t);
+    double s = 0.0;
+    for (int q = 0; q < world; ++q) {
+      double v = mine;
+      if (q != me) {
+        const uint4 *src = &own->ar_ll[slot][q][t];
+        if (!ld_ll(src, tag, v)) {
+          const unsigned long long t0 = global_ns();
+          bool ok = false;
+          while (!ok) {
+            for (int i = 0; i < 64 && !ok; ++i) ok = ld_ll(src, tag, v);
+            if (!ok && global_ns() - t0 > CV_PEER_TIMEOUT_NS) break;
+          }
+          if (!ok) {
+            s_bad = 1;
+            v = 0.0;
+          }
+        }
+      }
+      s += v;
+    }
+    buf[t] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    own->ar_seq = seq;
+    if (s_bad) *err = 1.0;
+  }
+  __threadfence();
+  __syncthreads();
+}
+
+// Push ranges of x into the peers' halo buffers (all threads of the grid), then the last CTA to
+// finish raises the peers' flags.
+template <typename T>
+__device__ __forceinline__ void grid_halo_push(const PushArgs &a, const T *__restrict__ x) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int s = 0; s < a.nseg; ++s) {
+    const PushSeg &g = a.seg[s];
+    T *dst = static_cast<T *>(g.dst);
+    if (g.idx) {
+      for (int64_t i = tid; i < g.count; i += stride) st_plain(dst + i, ld_cg(x + g.idx[i]));
+    } else {
+      const T *src = x + g.src_start;
+      if (sizeof(T) == 8 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+        const int64_t n2 = g.count >> 1;
+        const double2 *s2 = reinterpret_cast<const double2 *>(src);
+        double2 *d2 = reinterpret_cast<double2 *>(dst);
+        int64_t i = tid;
+        for (; i + 3 * stride < n2; i += 4 * stride) {
+          double2 v0 = __ldcg(s2 + i), v1 = __ldcg(s2 + i + stride), v2 = __ldcg(s2 + i + 2 * stride),
+                  v3 = __ldcg(s2 + i + 3 * stride);
+          d2[i] = v0;
+          d2[i + stride] = v1;
+          d2[i + 2 * stride] = v2;
+          d2[i + 3 * stride] = v3;
+        }
+        for (; i < n2; i += stride) d2[i] = __ldcg(s2 + i);
+        if ((g.count & 1) && tid == 0) st_plain(dst + g.count - 1, ld_cg(src + g.count - 1));
+      } else {
+        for (int64_t i = tid; i < g.count; i += stride) st_plain(dst + i, ld_cg(src + i));
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool s_last_push;
+  if (threadIdx.x == 0) s_last_push = atomicAdd(a.ticket, 1u) == gridDim.x - 1u;
+  __syncthreads();
+  if (!s_last_push) return;
+  __threadfence_system();
+  if (threadIdx.x < a.nflag) st_release_sys(a.flag_dst[threadIdx.x], a.seq);
+  if (threadIdx.x == 0) *a.ticket = 0u;
 }
 
 // scalar-slot map inside ctx->scalars (doubles).  Solvers use [CV_S_SOLVER, ...).

@@ -5,6 +5,7 @@
 #include "kernels_vec.cuh"
 #include "kernels_spmv.cuh"
 #include "kernels_dia.cuh"
+#include "kernels_orth.cuh"
 
 struct cv_op {
   int64_t n_rows = 0, n_cols = 0, nnz = 0;
@@ -43,6 +44,7 @@ struct cv_op {
   std::vector<int64_t> peer_stride;      // [world] bytes between the two parities (general halo)
   std::vector<int64_t> peer_dst_off;     // [world] element offset of MY block inside peer p's halo
   void *halo_cur = nullptr, *halo_lo_cur = nullptr, *halo_hi_cur = nullptr;
+  HaloWait wait = {nullptr, 0u, 0ull, nullptr};  // what the next sharded SpMV polls (mask 0: nothing)
 };
 
 int cv_check_launch(cv_ctx *ctx, const char *what);
@@ -66,6 +68,10 @@ int cv_spmv_dev(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double 
 int cv_halo_exchange(cv_ctx *ctx, cv_op *op, bool cplx_, const void *x, cudaStream_t st);
 int cv_halo_exchange_dia(cv_ctx *ctx, cv_op *op, bool cplx_, const void *x, cudaStream_t st);
 int cv_halo_exchange_peer(cv_ctx *ctx, cv_op *op, bool cplx_, const void *x, cudaStream_t st);
-int cv_halo_exchange_dia_peer(cv_ctx *ctx, cv_op *op, bool cplx_, const void *x, cudaStream_t st);
+int cv_peer_plan_exchange(cv_ctx *ctx, cv_op *op, bool cplx_, PushArgs *a, int64_t *total_out);
+const PeerPtrs *cv_peer_ptrs(cv_ctx *ctx);
+int cv_wait_mailbox(cv_ctx *ctx, unsigned long long seq, cudaStream_t st);
+int cv_orth_step_dev(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int m, const void *const *basis, void *w,
+                     int s_flag, int s_h2, cudaStream_t st, bool *fused);
 int cv_peer_detach(cv_ctx *ctx);
 int cv_peer_allreduce(cv_ctx *ctx, double *buf_dev, int count, cudaStream_t st);

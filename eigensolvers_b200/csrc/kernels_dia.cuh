@@ -53,6 +53,7 @@ template <typename T, bool HALO, bool EPI, bool DOTS>
 __global__ void __launch_bounds__(CV_BLOCK, sizeof(T) == 8 ? (HALO ? 5 : 6) : (HALO ? 3 : 4))
     k_spmv_dia(const __grid_constant__ DiaArgs<T> a) {
   constexpr int DB = 8;  // diagonals per load batch
+  if (HALO) halo_wait_cta(a.s.wait);
   const int n = (int)a.s.n_rows;
   const int stride = gridDim.x * blockDim.x;
   T d_xy = Num<T>::zero();

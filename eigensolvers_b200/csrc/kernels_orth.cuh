@@ -1,0 +1,281 @@
+// kernels_orth.cuh — ONE persistent kernel per Arnoldi step of GCROT's inner FGMRES
+// (_gcrotmk.py:112-141): everything between two operator applications.
+//
+//   phase A   h = [C,V]^H w                         (tall-skinny dot, V read once)
+//   barrier   last CTA sums the per-CTA partials in a fixed order, all-reduces {<x|y>,<y|y>,h}
+//             over the ranks through peer memory (one NVLink round trip), publishes h
+//   phase B   w <- w - [C,V] h,  partial |w|^2
+//   barrier   last CTA: |w|^2 summed + all-reduced; Daniel-Gragg-Kaufman-Stewart test
+//             |w'|^2 < eta^2 |w|^2  ->  phases A and B once more (h2); results are written to the
+//             HOST mailbox (mapped pinned memory) and a sequence flag released, so the host gets
+//             the Hessenberg column while the kernel is still running
+//   phase C   w <- w / |w|  and, in row-sharded mode, the boundary rows of the NEW basis vector
+//             are pushed straight into the neighbours' halo buffers for the next SpMV.
+//
+// The separate-kernel version of the same step needed 8 launches, 2 copies and a stream
+// synchronisation per step (tsdot, all-reduce, tsupdate, all-reduce, D2H, scale, halo push, halo
+// wait); at 8 GPUs that fixed cost (~90 us) was a third of the step.  Here it is one cooperative
+// launch with two grid barriers (own implementation: arrive, the LAST arriver does the serial
+// work, release) and the host polls a flag instead of synchronising the stream.
+#pragma once
+#include "kernels_vec.cuh"
+
+struct OrthArgs {
+  TsParams p;      // v[0..m) = basis [C,V];  w[0] = vector being orthogonalised (in/out);  n
+  double *partials;
+  unsigned *bar;   // [0] arrivals, [1] generation
+  double *scal;    // ctx->scalars
+  int s_flag;      // out: 1.0 if the second pass ran
+  int s_nrm;       // out: |w'|^2 after the last pass (summed over ranks)
+  int s_w;         // in: {Re<x|y>, Im<x|y>, <y|y>} partial dots of the SpMV (this rank), out: summed
+  int s_h1, s_h2;  // out: projection coefficients of pass 1 / pass 2  (s_h1 == s_w + 3)
+  double eta2;
+  // peers (world == 1: unused)
+  PeerPtrs pp;
+  int me, world;
+  double *err;
+  PushArgs push;   // nseg == 0 && nflag == 0: nothing to push
+  // host mailbox
+  double *host_mb;
+  unsigned long long *host_flag;
+  unsigned long long host_seq;
+};
+
+// Grid barrier with serial work: every CTA arrives; the last one to arrive runs `work` (all its
+// threads), then releases the others.  Needs all CTAs co-resident (cooperative launch).
+template <typename F, typename G>
+__device__ __forceinline__ void grid_barrier_with(unsigned *bar, F &&work, G &&after_release) {
+  __shared__ bool s_last_bar;
+  __shared__ unsigned s_gen_bar;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_gen_bar = ld_acquire_gpu(bar + 1);  // read BEFORE arriving: cannot advance until we arrive
+    __threadfence();
+    s_last_bar = atomicAdd(bar, 1u) == gridDim.x - 1u;
+  }
+  __syncthreads();
+  if (s_last_bar) {
+    __threadfence();
+    work();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bar[0] = 0u;
+      __threadfence();
+      st_release_gpu(bar + 1, s_gen_bar + 1u);
+    }
+    after_release();  // off the critical path of the other CTAs
+  } else if (threadIdx.x == 0) {
+    while (ld_acquire_gpu(bar + 1) == s_gen_bar) {
+    }
+  }
+  __syncthreads();
+}
+template <typename F>
+__device__ __forceinline__ void grid_barrier_with(unsigned *bar, F &&work) {
+  grid_barrier_with(bar, work, []() {});
+}
+
+template <typename T, int W>
+__device__ __forceinline__ Pack<T, W> pk_ld_cg(const T *base, int64_t ip) {
+  Pack<T, W> p;
+  if constexpr (W == 1) {
+    p.e[0] = ld_cg(base + ip);
+  } else {
+    double2 v = __ldcg(reinterpret_cast<const double2 *>(base) + ip);
+    p.e[0] = v.x;
+    p.e[1] = v.y;
+  }
+  return p;
+}
+
+template <typename T, int W>
+__global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant__ OrthArgs a) {
+  constexpr int NR = Num<T>::NRED;
+  constexpr int MI = 16, LB = 8, JB = 8;
+  extern __shared__ double s_h[];  // m * NR doubles
+  __shared__ double s_part[CV_WARPS][MI * NR];
+  __shared__ double s_vals[MI * NR];
+  __shared__ bool s_again;
+  const int G = gridDim.x, c = blockIdx.x;
+  const int m = a.p.m;
+  const int64_t n = a.p.n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T *wvec = static_cast<T *>(const_cast<void *>(a.p.w[0]));
+  const int ny = (m + MI - 1) / MI;
+  const int gx = G / ny;  // >= 1: the launcher makes G >= ny
+  const int64_t npf = n / W;
+  const bool tail_mine = (W == 2) && (n & 1);
+
+  for (int pass = 1; pass <= 2; ++pass) {
+    const int s_h_out = pass == 1 ? a.s_h1 : a.s_h2;
+    // ---------------- phase A: this CTA's slab of up to MI basis vectors against w ----------
+    if (c < gx * ny) {
+      const int by = c / gx, bx = c % gx;
+      const int i0 = by * MI;
+      const int mi = min(MI, m - i0);
+      T acc[MI];
+#pragma unroll
+      for (int i = 0; i < MI; ++i) acc[i] = Num<T>::zero();
+      for (int64_t ip = (int64_t)bx * blockDim.x + threadIdx.x; ip < npf; ip += (int64_t)gx * blockDim.x) {
+        const Pack<T, W> wv = pk_ld_cg<T, W>(wvec, ip);
+#pragma unroll
+        for (int ib = 0; ib < MI; ib += LB) {
+          Pack<T, W> vv[LB];
+#pragma unroll
+          for (int l = 0; l < LB; ++l)
+            vv[l] = (ib + l < mi) ? pk_ld<T, W, false>(static_cast<const T *>(a.p.v[i0 + ib + l]), ip)
+                                  : pk_zero<T, W>();
+#pragma unroll
+          for (int l = 0; l < LB; ++l)
+#pragma unroll
+            for (int w = 0; w < W; ++w) Num<T>::fmac(acc[ib + l], vv[l].e[w], wv.e[w]);
+        }
+      }
+      if (tail_mine && bx == 0 && threadIdx.x == 0) {
+        const T wt = ld_cg(wvec + (n - 1));
+        for (int i = 0; i < mi; ++i) Num<T>::fmac(acc[i], static_cast<const T *>(a.p.v[i0 + i])[n - 1], wt);
+      }
+#pragma unroll
+      for (int i = 0; i < MI; ++i) {
+        double r[NR];
+        Num<T>::to_red(acc[i], r);
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+          const double s = warp_sum(r[k]);
+          if (lane == 0) s_part[warp][i * NR + k] = s;
+        }
+      }
+      __syncthreads();
+      for (int v = threadIdx.x; v < MI * NR; v += blockDim.x) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < CV_WARPS; ++w) s += s_part[w][v];
+        s_vals[v] = s;
+      }
+      __syncthreads();
+      double *pslab = a.partials + (size_t)by * MI * NR * gx;
+      for (int v = threadIdx.x; v < mi * NR; v += blockDim.x) pslab[(size_t)v * gx + bx] = s_vals[v];
+    }
+    grid_barrier_with(a.bar, [&]() {
+      for (int v = warp; v < m * NR; v += CV_WARPS) {
+        const int by = (v / NR) / MI;
+        const int local = v - by * MI * NR;
+        const double *pp = a.partials + ((size_t)by * MI * NR + local) * gx;
+        double r = 0.0;
+        for (int b = lane; b < gx; b += 32) r += __ldcg(pp + b);
+        r = warp_sum(r);
+        if (lane == 0) a.scal[s_h_out + v] = r;
+      }
+      __threadfence();
+      if (a.world > 1) {
+        if (pass == 1)
+          cta_peer_allreduce(a.pp, a.me, a.world, a.scal + a.s_w, 3 + m * NR, a.err);
+        else
+          cta_peer_allreduce(a.pp, a.me, a.world, a.scal + s_h_out, m * NR, a.err);
+      }
+    });
+    // ---------------- phase B: w -= [C,V] h, partial |w|^2 ----------------------------------
+    for (int j = threadIdx.x; j < m * NR; j += blockDim.x) s_h[j] = -__ldcg(a.scal + s_h_out + j);
+    __syncthreads();
+    double nrm = 0.0;
+    for (int64_t ip = (int64_t)c * blockDim.x + threadIdx.x; ip < npf; ip += (int64_t)G * blockDim.x) {
+      Pack<T, W> acc = pk_ld_cg<T, W>(wvec, ip);
+      for (int j0 = 0; j0 < m; j0 += JB) {
+        Pack<T, W> v[JB];
+#pragma unroll
+        for (int jj = 0; jj < JB; ++jj)
+          v[jj] = (j0 + jj < m) ? pk_ld<T, W, false>(static_cast<const T *>(a.p.v[j0 + jj]), ip) : pk_zero<T, W>();
+#pragma unroll
+        for (int jj = 0; jj < JB; ++jj) {
+          if (j0 + jj < m) {
+            const T mc = Num<T>::from_red(s_h + (j0 + jj) * NR);
+#pragma unroll
+            for (int w = 0; w < W; ++w) Num<T>::fma(acc.e[w], mc, v[jj].e[w]);
+          }
+        }
+      }
+      pk_st<T, W>(wvec, ip, acc);
+#pragma unroll
+      for (int w = 0; w < W; ++w) nrm += Num<T>::abs2(acc.e[w]);
+    }
+    if (tail_mine && c == 0 && threadIdx.x == 0) {
+      T acc = ld_cg(wvec + (n - 1));
+      for (int j = 0; j < m; ++j)
+        Num<T>::fma(acc, Num<T>::from_red(s_h + j * NR), static_cast<const T *>(a.p.v[j])[n - 1]);
+      wvec[n - 1] = acc;
+      nrm += Num<T>::abs2(acc);
+    }
+    {
+      const double s = warp_sum(nrm);
+      if (lane == 0) s_part[warp][0] = s;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double r = 0.0;
+#pragma unroll
+        for (int w = 0; w < CV_WARPS; ++w) r += s_part[w][0];
+        a.partials[c] = r;
+      }
+    }
+    grid_barrier_with(a.bar, [&]() {
+      if (warp == 0) {
+        double r = 0.0;
+        for (int b = lane; b < G; b += 32) r += __ldcg(a.partials + b);
+        r = warp_sum(r);
+        if (lane == 0) a.scal[a.s_nrm] = r;
+      }
+      __threadfence();
+      if (a.world > 1) cta_peer_allreduce(a.pp, a.me, a.world, a.scal + a.s_nrm, 1, a.err);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        bool again = false;
+        if (pass == 1) {
+          again = !(__ldcg(a.scal + a.s_nrm) >= a.eta2 * __ldcg(a.scal + a.s_w + 2));
+          a.scal[a.s_flag] = again ? 1.0 : 0.0;
+        }
+        s_again = again;
+      }
+      __syncthreads();
+    }, [&]() {
+      if (!s_again) {
+        // final: hand the scalars to the host while phase C runs (after the barrier release)
+        const bool two = pass == 2;
+        for (int t = threadIdx.x; t < a.s_h1 + m * NR - a.s_flag; t += blockDim.x)
+          a.host_mb[a.s_flag + t] = __ldcg(a.scal + a.s_flag + t);
+        if (two)
+          for (int t = threadIdx.x; t < m * NR; t += blockDim.x) a.host_mb[a.s_h2 + t] = __ldcg(a.scal + a.s_h2 + t);
+        if (threadIdx.x == 0) a.host_mb[a.err - a.scal] = __ldcg(a.err);
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_sys(a.host_flag, a.host_seq);
+      }
+    });
+    if (pass == 1 && __ldcg(a.scal + a.s_flag) == 0.0) break;
+  }
+  // ---------------- phase C: normalise (scipy: only if 1/|w| is finite), push the halo -------
+  {
+    double f = 1.0 / sqrt(__ldcg(a.scal + a.s_nrm));
+    if (!isfinite(f)) f = 1.0;
+    constexpr int U = 4;
+    const int64_t tid = (int64_t)c * blockDim.x + threadIdx.x, stride = (int64_t)G * blockDim.x;
+    for (int64_t ip0 = tid; ip0 < npf; ip0 += U * stride) {
+      Pack<T, W> x[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t ip = ip0 + u * stride;
+        x[u] = (ip < npf) ? pk_ld_cg<T, W>(wvec, ip) : pk_zero<T, W>();
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t ip = ip0 + u * stride;
+#pragma unroll
+        for (int w = 0; w < W; ++w) x[u].e[w] = Num<T>::scale(x[u].e[w], f);
+        if (ip < npf) pk_st<T, W>(wvec, ip, x[u]);
+      }
+    }
+    if (tail_mine && c == 0 && threadIdx.x == 0) wvec[n - 1] = Num<T>::scale(ld_cg(wvec + (n - 1)), f);
+  }
+  if (a.push.nseg > 0 || a.push.nflag > 0) {
+    grid_barrier_with(a.bar, [&]() {});
+    grid_halo_push<T>(a.push, wvec);
+  }
+}

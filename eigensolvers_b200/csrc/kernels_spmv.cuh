@@ -45,6 +45,7 @@ struct SpmvArgs {
   double *partials;
   unsigned *counter;
   double *out;  // {Re<x|y>, Im<x|y>, <y|y>}
+  HaloWait wait;  // peer transport: flags of the ranks that push this SpMV's halo (mask 0: none)
 };
 
 template <typename T, bool HALO>
@@ -94,6 +95,7 @@ __device__ __forceinline__ void spmv_reduce(const SpmvArgs<T> &a, T d_xy, double
 template <typename T, bool HALO, bool EPI, bool DOTS>
 __global__ void __launch_bounds__(CV_BLOCK, sizeof(T) == 8 ? 8 : 5)
     k_spmv_sell(const __grid_constant__ SpmvArgs<T> a) {
+  if (HALO) halo_wait_cta(a.wait);
   const int lane = threadIdx.x & 31;
   // 32-bit slice/row counters (rows < 2^31 because column indices are int32): fewer registers
   const int warp0 = blockIdx.x * CV_WARPS + (threadIdx.x >> 5);
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(CV_BLOCK, sizeof(T) == 8 ? 8 : 5)
 // ------------------------------------------------------------------------------------------
 template <typename T, int G, bool HALO, bool EPI, bool DOTS>
 __global__ void __launch_bounds__(CV_BLOCK) k_spmv_csr(const __grid_constant__ SpmvArgs<T> a) {
+  if (HALO) halo_wait_cta(a.wait);
   constexpr int RPB = CV_BLOCK / G;
   const int grp = threadIdx.x / G, gl = threadIdx.x % G;
   T d_xy = Num<T>::zero();

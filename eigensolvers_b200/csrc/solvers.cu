@@ -31,6 +31,7 @@ namespace {
 constexpr int S_CX = CV_S_SOLVER;          // |ux|^2, |cx|^2
 constexpr int S_GAMMA = CV_S_SOLVER + 2;   // <cx|r> (NRED)
 constexpr int S_BETA = CV_S_SOLVER + 4;    // |r|^2
+constexpr int S_FLAG = CV_S_SOLVER + 6;    // fused Arnoldi step: 1.0 if the second Gram-Schmidt pass ran
 constexpr int S_NRM = CV_S_SOLVER + 7;     // squared norm of the orthogonalised vector
 constexpr int S_W = CV_S_SOLVER + 8;       // {Re<x|y>, Im<x|y>, <y|y>} of the fused SpMV
 constexpr int S_H1 = CV_S_SOLVER + 11;     // first-pass projection coefficients
@@ -52,6 +53,50 @@ struct Workspace {
 // y = a*x with a real host scalar (used for v0 = r/beta)
 int scal_real(cv_ctx *ctx, int64_t n, int cplx_, double a, const void *x, void *y, cudaStream_t st) {
   return cv_scal(ctx, n, cplx_, cplx_, a, 0.0, x, y, (void *)st);
+}
+
+// Separate-kernel form of one Arnoldi orthogonalisation step (NCCL transport): two tall-skinny
+// passes, the SpMV's dots and the projection coefficients in ONE all-reduce, one copy to the host.
+int arnoldi_orth_unfused(cv_ctx *ctx, int64_t n, int cplx_, int nc, int nb, std::vector<const void *> &basis,
+                         void *w, std::vector<zc> &B, int ldb, int j, std::vector<zc> &hcur,
+                         cv_solve_stats *stats, cudaStream_t st) {
+  const int NR = cplx_ ? 2 : 1;
+  double *mb = ctx->mailbox;
+  const void *wp[1] = {w};
+      ctx->defer_reduce = true;
+      int rc_dot = cv_tsdot_dev(ctx, n, cplx_, 1, nb, basis.data(), 1, wp, S_H1, st);
+      ctx->defer_reduce = false;
+      CV_TRY(rc_dot);
+      CV_TRY(cv_reduce_ranks(ctx, S_W, 3 + nb * NR, st));
+      CV_TRY(cv_tsupdate_dev(ctx, n, cplx_, nb, basis.data(), S_H1, w, S_NRM, st));
+      CV_TRY(cv_fetch_scalars(ctx, S_NRM, 4 + nb * NR, st));
+      stats->n_sync++;
+      for (int i = 0; i < nb; ++i) {
+        zc h = cplx_ ? zc(mb[S_H1 + 2 * i], mb[S_H1 + 2 * i + 1]) : zc(mb[S_H1 + i], 0.0);
+        if (i < nc)
+          B[(size_t)i * ldb + j] = h;
+        else
+          hcur[i - nc] = h;
+      }
+      // Re-orthogonalise only if the projection cancelled the vector down to less than eta of
+      // its norm (Daniel-Gragg-Kaufman-Stewart); otherwise orthogonality is already ~eps/eta.
+      if (!(mb[S_NRM] >= ctx->reorth_eta * ctx->reorth_eta * mb[S_W + 2])) {
+        CV_TRY(cv_tsdot_dev(ctx, n, cplx_, 1, nb, basis.data(), 1, wp, S_H2, st));
+        CV_TRY(cv_tsupdate_dev(ctx, n, cplx_, nb, basis.data(), S_H2, w, S_NRM, st));
+        CV_TRY(cv_fetch_scalars(ctx, S_NRM, 1, st));
+        CV_TRY(cv_fetch_scalars(ctx, S_H2, nb * NR, st));
+        stats->n_sync++;
+        stats->n_reorth++;
+        for (int i = 0; i < nb; ++i) {
+          zc h2 = cplx_ ? zc(mb[S_H2 + 2 * i], mb[S_H2 + 2 * i + 1]) : zc(mb[S_H2 + i], 0.0);
+          if (i < nc)
+            B[(size_t)i * ldb + j] += h2;
+          else
+            hcur[i - nc] += h2;
+        }
+      }
+      CV_TRY(cv_scale_dev(ctx, n, cplx_, w, S_NRM, 1, st));
+  return CV_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -151,42 +196,27 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
       basis[nc + j] = V(j);
       const int nb = nc + j + 1;
       const void *wp[1] = {w};
-      // Classical Gram-Schmidt against [C, V] in two tall-skinny passes.  The SpMV's dots and the
-      // projection coefficients travel in ONE all-reduce and, with |w'|^2, ONE copy to the host.
-      ctx->defer_reduce = true;
-      int rc_dot = cv_tsdot_dev(ctx, n, cplx_, 1, nb, basis.data(), 1, wp, S_H1, st);
-      ctx->defer_reduce = false;
-      CV_TRY(rc_dot);
-      CV_TRY(cv_reduce_ranks(ctx, S_W, 3 + nb * NR, st));
-      CV_TRY(cv_tsupdate_dev(ctx, n, cplx_, nb, basis.data(), S_H1, w, S_NRM, st));
-      CV_TRY(cv_fetch_scalars(ctx, S_NRM, 4 + nb * NR, st));
-      stats->n_sync++;
-      const double w_norm = sqrt(mb[S_W + 2]);
-      for (int i = 0; i < nb; ++i) {
-        zc h = cplx_ ? zc(mb[S_H1 + 2 * i], mb[S_H1 + 2 * i + 1]) : zc(mb[S_H1 + i], 0.0);
-        if (i < nc)
-          B[(size_t)i * ldb + j] = h;
-        else
-          hcur[i - nc] = h;
-      }
-      // Re-orthogonalise only if the projection cancelled the vector down to less than eta of
-      // its norm (Daniel-Gragg-Kaufman-Stewart); otherwise orthogonality is already ~eps/eta.
-      if (!(mb[S_NRM] >= ctx->reorth_eta * ctx->reorth_eta * mb[S_W + 2])) {
-        CV_TRY(cv_tsdot_dev(ctx, n, cplx_, 1, nb, basis.data(), 1, wp, S_H2, st));
-        CV_TRY(cv_tsupdate_dev(ctx, n, cplx_, nb, basis.data(), S_H2, w, S_NRM, st));
-        CV_TRY(cv_fetch_scalars(ctx, S_NRM, 1, st));
-        CV_TRY(cv_fetch_scalars(ctx, S_H2, nb * NR, st));
+      // Classical Gram-Schmidt against [C, V], repeated only if the projection cancelled the
+      // vector down to less than eta of its norm (Daniel-Gragg-Kaufman-Stewart), normalisation
+      // and the halo push of the new basis vector: ONE fused persistent kernel whose scalars land
+      // in the mailbox (kernels_orth.cuh).  The SpMV's dots travel in the same all-reduce.
+      bool fused = false;
+      CV_TRY(cv_orth_step_dev(ctx, op, n, cplx_, nb, basis.data(), w, S_FLAG, S_H2, st, &fused));
+      if (fused) {
         stats->n_sync++;
-        stats->n_reorth++;
         for (int i = 0; i < nb; ++i) {
-          zc h2 = cplx_ ? zc(mb[S_H2 + 2 * i], mb[S_H2 + 2 * i + 1]) : zc(mb[S_H2 + i], 0.0);
+          zc h = cplx_ ? zc(mb[S_H1 + 2 * i], mb[S_H1 + 2 * i + 1]) : zc(mb[S_H1 + i], 0.0);
+          if (mb[S_FLAG] != 0.0) h += cplx_ ? zc(mb[S_H2 + 2 * i], mb[S_H2 + 2 * i + 1]) : zc(mb[S_H2 + i], 0.0);
           if (i < nc)
-            B[(size_t)i * ldb + j] += h2;
+            B[(size_t)i * ldb + j] = h;
           else
-            hcur[i - nc] += h2;
+            hcur[i - nc] = h;
         }
+        if (mb[S_FLAG] != 0.0) stats->n_reorth++;
+      } else {
+        CV_TRY(arnoldi_orth_unfused(ctx, n, cplx_, nc, nb, basis, w, B, ldb, j, hcur, stats, st));
       }
-      CV_TRY(cv_scale_dev(ctx, n, cplx_, w, S_NRM, 1, st));
+      const double w_norm = sqrt(mb[S_W + 2]);
       const double hlast = sqrt(mb[S_NRM]);
       hcur[j + 1] = hlast;
       if (!(hlast > eps * w_norm)) breakdown = true;
