@@ -264,6 +264,8 @@ def run_ours(args, w):
     barrier()
     launches0 = rt.launch_count()
     mv0 = rt.stats["matvecs"]
+    tr16 = (C.c_double * 16)()
+    _lib.check(rt.lib.cv_ctx_trace_read(rt.ctx, tr16, 1))
     clocks = ClockSampler(rt.device_index)
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -279,6 +281,11 @@ def run_ours(args, w):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms = float(tt.item())
+    _lib.check(rt.lib.cv_ctx_trace_read(rt.ctx, tr16, 1))
+    nk = max(tr16[5], 1.0)
+    orth_trace = {k: round(tr16[i] / nk * 1e-3, 2) for i, k in enumerate(
+        ["dots_us", "barrier1_allreduce_us", "update_us", "barrier2_allreduce_us", "normalise_us"])}
+    orth_trace.update(launches=int(tr16[5]), passes=int(tr16[6]), late_push_us=round(tr16[7] / nk * 1e-3, 2))
     launches = rt.launch_count() - launches0
     matvecs = (rt.stats["matvecs"] - mv0) // max(args.steps, 1)
     ms_per_step = ms / args.steps
@@ -367,7 +374,7 @@ def run_ours(args, w):
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "result": {"converged": converged, "eigenvalues": ev_out, "cumIter": int(st["cumIter"]),
                        "matvecs_per_step": int(matvecs), "true_residual": true_res,
-                       "profiled_step_s": t_prof},
+                       "profiled_step_s": t_prof, "arnoldi_step_kernel_phases": orth_trace},
         }
         print(json.dumps(line))
     if world > 1:

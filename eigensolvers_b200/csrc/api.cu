@@ -49,6 +49,7 @@ extern "C" int cv_ctx_create(int device, void *scratch_dev, size_t scratch_bytes
   c->host_seq = 0ull;
   c->prepushed_x = nullptr;
   c->prepushed_op = nullptr;
+  c->push_early = getenv("EIGB200_PUSH_EARLY") ? atoi(getenv("EIGB200_PUSH_EARLY")) != 0 : true;
   c->launches = 0;
   c->prof = nullptr;
   c->reorth_eta = 0.1;
@@ -80,6 +81,14 @@ extern "C" int cv_ctx_destroy(cv_ctx *ctx) {
 extern "C" int cv_ctx_launch_count(cv_ctx *ctx, uint64_t *count) {
   CV_REQUIRE(ctx && count, "cv_ctx_launch_count: null argument");
   *count = ctx->launches;
+  return CV_OK;
+}
+
+extern "C" int cv_ctx_trace_read(cv_ctx *ctx, double *out16, int reset) {
+  CV_REQUIRE(ctx && out16, "cv_ctx_trace_read: null argument");
+  CV_CUDA(cudaDeviceSynchronize());
+  CV_CUDA(cudaMemcpy(out16, ctx->scalars + CV_S_TRACE, 16 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (reset) CV_CUDA(cudaMemset(ctx->scalars + CV_S_TRACE, 0, 16 * sizeof(double)));
   return CV_OK;
 }
 
@@ -655,6 +664,7 @@ int cv_orth_step_dev(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int m, const 
   a.push.nflag = 0;
   a.push.seq = 0;
   a.push.ticket = ctx->counters + CV_COUNTER_PUSH;
+  a.push_early = 0;
   if (ctx->world > 1) {
     a.pp = *cv_peer_ptrs(ctx);
     const bool dia = op->fmt == CV_FMT_DIA;
@@ -663,8 +673,13 @@ int cv_orth_step_dev(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int m, const 
       CV_TRY(cv_peer_plan_exchange(ctx, op, cplx_ != 0, &a.push, nullptr));
       ctx->prepushed_x = w;
       ctx->prepushed_op = op;
+      if (dia && ctx->push_early) {  // contiguous ranges only: push unnormalised rows from phase B
+        a.push_early = 1;
+        op->wait.scale_sq = ctx->scalars + a.s_nrm;
+      }
     }
   }
+  a.trace = ctx->scalars + CV_S_TRACE;
   a.host_mb = ctx->mailbox;
   a.host_flag = ctx->host_flag;
   a.host_seq = ++ctx->host_seq;
@@ -957,7 +972,7 @@ static int launch_spmv_t(cv_ctx *ctx, cv_op *op, int mode, T sigma, const T *x, 
   a.partials = ctx->partials;
   a.counter = ctx->counters;
   a.out = dots_slot >= 0 ? ctx->scalars + dots_slot : nullptr;
-  a.wait = HaloWait{nullptr, 0u, 0ull, nullptr};
+  a.wait = HaloWait{nullptr, 0u, 0ull, nullptr, nullptr};
   const bool dia = op->fmt == CV_FMT_DIA;
   const bool halo = dia ? (ctx->world > 1 && (op->lo_len > 0 || op->hi_len > 0)) : op->n_halo > 0;
   const bool dots = dots_slot >= 0;

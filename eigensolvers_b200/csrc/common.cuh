@@ -103,6 +103,7 @@ struct cv_ctx {
   // the vector whose halo phase C of the fused step has already pushed (next SpMV skips its push)
   const void *prepushed_x;
   const void *prepushed_op;
+  bool push_early;  // fused step pushes unnormalised halo rows from phase B (EIGB200_PUSH_EARLY=0: off)
 };
 
 // RAII bracket: records an event pair around the launches issued inside its scope
@@ -388,7 +389,14 @@ struct HaloWait {
   unsigned mask;                    // source ranks
   unsigned long long seq;
   double *err;
+  const double *scale_sq;  // non-null: halo entries were pushed UNNORMALISED (fused Arnoldi step);
+                           // multiply them by 1/sqrt(*scale_sq) like the owner did with its rows
 };
+__device__ __forceinline__ double halo_scale(const HaloWait &w) {
+  if (!w.scale_sq) return 1.0;
+  const double f = 1.0 / sqrt(__ldcg(w.scale_sq));
+  return isfinite(f) ? f : 1.0;
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -550,4 +558,5 @@ constexpr int CV_S_TMP = 0;        // 16 doubles: dot/norm results of the BLAS-1
 constexpr int CV_S_GS = 16;        // 4*CV_MAX_PTRS doubles: MGS coefficients
 constexpr int CV_S_TS = 1024;      // CV_MAX_RED doubles: tall-skinny results
 constexpr int CV_S_SOLVER = 2048;  // solver scalars (h columns, norms, ...)
+constexpr int CV_S_TRACE = (int)CV_N_SCALARS - 32;  // 16 doubles: phase times of the fused Arnoldi step
 constexpr int CV_S_ERR = (int)CV_N_SCALARS - 1;  // raised (1.0) by a peer kernel whose bounded spin expired

@@ -44,7 +44,7 @@ struct cv_op {
   std::vector<int64_t> peer_stride;      // [world] bytes between the two parities (general halo)
   std::vector<int64_t> peer_dst_off;     // [world] element offset of MY block inside peer p's halo
   void *halo_cur = nullptr, *halo_lo_cur = nullptr, *halo_hi_cur = nullptr;
-  HaloWait wait = {nullptr, 0u, 0ull, nullptr};  // what the next sharded SpMV polls (mask 0: nothing)
+  HaloWait wait = {nullptr, 0u, 0ull, nullptr, nullptr};  // what the next sharded SpMV polls (mask 0: nothing)
 };
 
 int cv_check_launch(cv_ctx *ctx, const char *what);

@@ -33,15 +33,15 @@ struct DiaArgs {
 // x entry at local index i (may be outside the owned block); out-of-band indices (only reached
 // through zero padding values) are clamped to a valid address
 template <typename T, bool HALO>
-__device__ __forceinline__ T dia_x(const DiaArgs<T> &a, int i, int n) {
+__device__ __forceinline__ T dia_x(const DiaArgs<T> &a, int i, int n, double hs) {
   if (HALO) {
     if (i < 0) {
       i += a.lo_len;
-      return ld_gather(a.halo_lo + (i < 0 ? 0 : i));
+      return Num<T>::scale(ld_gather(a.halo_lo + (i < 0 ? 0 : i)), hs);
     }
     if (i >= n) {
       i -= n;
-      return ld_gather(a.halo_hi + (i >= a.hi_len ? a.hi_len - 1 : i));
+      return Num<T>::scale(ld_gather(a.halo_hi + (i >= a.hi_len ? a.hi_len - 1 : i)), hs);
     }
     return ld_gather(a.s.x + i);
   }
@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(CV_BLOCK, sizeof(T) == 8 ? (HALO ? 5 : 6) : (H
     k_spmv_dia(const __grid_constant__ DiaArgs<T> a) {
   constexpr int DB = 8;  // diagonals per load batch
   if (HALO) halo_wait_cta(a.s.wait);
+  const double hs = HALO ? halo_scale(a.s.wait) : 1.0;
   const int n = (int)a.s.n_rows;
   const int stride = gridDim.x * blockDim.x;
   T d_xy = Num<T>::zero();
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(CV_BLOCK, sizeof(T) == 8 ? (HALO ? 5 : 6) : (H
       for (int k = 0; k < DB; ++k) {
         const bool ok = d0 + k < a.n_diag;
         v[k] = ok ? ld_stream(vp + (int64_t)(d0 + k) * a.ld) : 0.0;
-        xv[k] = ok ? dia_x<T, HALO>(a, row + a.off[d0 + k], n) : Num<T>::zero();
+        xv[k] = ok ? dia_x<T, HALO>(a, row + a.off[d0 + k], n, hs) : Num<T>::zero();
       }
 #pragma unroll
       for (int k = 0; k < DB; k += 2) {

@@ -35,6 +35,10 @@ struct OrthArgs {
   int me, world;
   double *err;
   PushArgs push;   // nseg == 0 && nflag == 0: nothing to push
+  int push_early;  // all segments are contiguous ranges: phase B stores the UNSCALED new rows into the
+                   // peers' halo buffers as it produces them (NVLink traffic hidden behind the HBM
+                   // stream); the consuming SpMV multiplies halo entries by 1/|w| itself
+  double *trace;   // [16] accumulated phase times of CTA 0 in ns (tools/orth_trace.py)
   // host mailbox
   double *host_mb;
   unsigned long long *host_flag;
@@ -88,6 +92,53 @@ __device__ __forceinline__ Pack<T, W> pk_ld_cg(const T *base, int64_t ip) {
   return p;
 }
 
+// sum p[lane], p[lane+32], ... in that fixed order with all loads of a batch in flight at once
+// (the serial section of a grid barrier: every microsecond here is paid by all CTAs)
+__device__ __forceinline__ double ordered_lane_sum(const double *p, int count, int lane) {
+  double r = 0.0;
+  for (int b0 = lane; b0 < count; b0 += 32 * 8) {
+    double t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = (b0 + 32 * k < count) ? __ldcg(p + b0 + 32 * k) : 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += t[k];
+  }
+  return r;
+}
+
+// store the freshly computed pack `ip` of w into every peer range that contains it
+template <typename T, int W>
+__device__ __forceinline__ bool push_pack(const PushArgs &a, int64_t ip, const Pack<T, W> &v) {
+  bool any = false;
+  for (int s = 0; s < a.nseg; ++s) {
+    const PushSeg &g = a.seg[s];
+    const int64_t e0 = ip * W - g.src_start;  // position of the pack's first element in the range
+    if (e0 + W <= 0 || e0 >= g.count) continue;
+    T *dst = static_cast<T *>(g.dst);
+    if constexpr (W == 2) {
+      if (e0 >= 0 && e0 + 1 < g.count && (((uintptr_t)(dst + e0)) & 15) == 0) {
+        *reinterpret_cast<double2 *>(dst + e0) = make_double2(v.e[0], v.e[1]);
+      } else {
+        if (e0 >= 0 && e0 < g.count) st_plain(dst + e0, v.e[0]);
+        if (e0 + 1 >= 0 && e0 + 1 < g.count) st_plain(dst + e0 + 1, v.e[1]);
+      }
+    } else {
+      st_plain(dst + e0, v.e[0]);
+    }
+    any = true;
+  }
+  return any;
+}
+
+#define ORTH_TRACE(slot)                                  \
+  do {                                                    \
+    if (a.trace && c == 0 && threadIdx.x == 0) {          \
+      const unsigned long long t_now = global_ns();       \
+      a.trace[slot] += (double)(t_now - t_prev);          \
+      t_prev = t_now;                                     \
+    }                                                     \
+  } while (0)
+
 template <typename T, int W>
 __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant__ OrthArgs a) {
   constexpr int NR = Num<T>::NRED;
@@ -105,6 +156,11 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
   const int gx = G / ny;  // >= 1: the launcher makes G >= ny
   const int64_t npf = n / W;
   const bool tail_mine = (W == 2) && (n & 1);
+  unsigned long long t_prev = 0;
+  if (a.trace && c == 0 && threadIdx.x == 0) {
+    t_prev = global_ns();
+    a.trace[5] += 1.0;
+  }
 
   for (int pass = 1; pass <= 2; ++pass) {
     const int s_h_out = pass == 1 ? a.s_h1 : a.s_h2;
@@ -156,13 +212,13 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
       double *pslab = a.partials + (size_t)by * MI * NR * gx;
       for (int v = threadIdx.x; v < mi * NR; v += blockDim.x) pslab[(size_t)v * gx + bx] = s_vals[v];
     }
+    ORTH_TRACE(0);
     grid_barrier_with(a.bar, [&]() {
       for (int v = warp; v < m * NR; v += CV_WARPS) {
         const int by = (v / NR) / MI;
         const int local = v - by * MI * NR;
         const double *pp = a.partials + ((size_t)by * MI * NR + local) * gx;
-        double r = 0.0;
-        for (int b = lane; b < gx; b += 32) r += __ldcg(pp + b);
+        double r = ordered_lane_sum(pp, gx, lane);
         r = warp_sum(r);
         if (lane == 0) a.scal[s_h_out + v] = r;
       }
@@ -174,7 +230,9 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
           cta_peer_allreduce(a.pp, a.me, a.world, a.scal + s_h_out, m * NR, a.err);
       }
     });
+    ORTH_TRACE(1);
     // ---------------- phase B: w -= [C,V] h, partial |w|^2 ----------------------------------
+    bool pushed = false;
     for (int j = threadIdx.x; j < m * NR; j += blockDim.x) s_h[j] = -__ldcg(a.scal + s_h_out + j);
     __syncthreads();
     double nrm = 0.0;
@@ -195,6 +253,7 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
         }
       }
       pk_st<T, W>(wvec, ip, acc);
+      if (a.push_early) pushed |= push_pack<T, W>(a.push, ip, acc);
 #pragma unroll
       for (int w = 0; w < W; ++w) nrm += Num<T>::abs2(acc.e[w]);
     }
@@ -203,8 +262,14 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
       for (int j = 0; j < m; ++j)
         Num<T>::fma(acc, Num<T>::from_red(s_h + j * NR), static_cast<const T *>(a.p.v[j])[n - 1]);
       wvec[n - 1] = acc;
+      if (a.push_early) {
+        Pack<T, 1> one;
+        one.e[0] = acc;
+        pushed |= push_pack<T, 1>(a.push, n - 1, one);
+      }
       nrm += Num<T>::abs2(acc);
     }
+    if (pushed) __threadfence_system();  // this thread's peer stores are visible before it arrives
     {
       const double s = warp_sum(nrm);
       if (lane == 0) s_part[warp][0] = s;
@@ -216,10 +281,10 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
         a.partials[c] = r;
       }
     }
+    ORTH_TRACE(2);
     grid_barrier_with(a.bar, [&]() {
       if (warp == 0) {
-        double r = 0.0;
-        for (int b = lane; b < G; b += 32) r += __ldcg(a.partials + b);
+        double r = ordered_lane_sum(a.partials, G, lane);
         r = warp_sum(r);
         if (lane == 0) a.scal[a.s_nrm] = r;
       }
@@ -247,8 +312,12 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
         __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) st_release_sys(a.host_flag, a.host_seq);
+        // every CTA fenced its early halo stores before arriving: the peers may read them now
+        if (a.push_early && threadIdx.x < a.push.nflag) st_release_sys(a.push.flag_dst[threadIdx.x], a.push.seq);
       }
     });
+    ORTH_TRACE(3);
+    if (a.trace && c == 0 && threadIdx.x == 0) a.trace[6] += 1.0;
     if (pass == 1 && __ldcg(a.scal + a.s_flag) == 0.0) break;
   }
   // ---------------- phase C: normalise (scipy: only if 1/|w| is finite), push the halo -------
@@ -274,8 +343,10 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
     }
     if (tail_mine && c == 0 && threadIdx.x == 0) wvec[n - 1] = Num<T>::scale(ld_cg(wvec + (n - 1)), f);
   }
-  if (a.push.nseg > 0 || a.push.nflag > 0) {
+  ORTH_TRACE(4);
+  if (!a.push_early && (a.push.nseg > 0 || a.push.nflag > 0)) {
     grid_barrier_with(a.bar, [&]() {});
     grid_halo_push<T>(a.push, wvec);
+    ORTH_TRACE(7);
   }
 }

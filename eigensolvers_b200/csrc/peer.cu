@@ -222,6 +222,7 @@ int cv_peer_plan_exchange(cv_ctx *ctx, cv_op *op, bool cplx_, PushArgs *a, int64
   op->wait.mask = src_mask;
   op->wait.seq = seq;
   op->wait.err = ctx->scalars + CV_S_ERR;
+  op->wait.scale_sq = nullptr;
   if (total_out) *total_out = total;
   return CV_OK;
 }

@@ -67,6 +67,10 @@ int cv_ctx_destroy(cv_ctx *ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int cv_ctx_launch_count(cv_ctx *ctx, uint64_t *count);
 int cv_ctx_sm_count(cv_ctx *ctx, int *sms);
+/* Accumulated phase times (ns, as seen by CTA 0) of the fused Arnoldi-step kernel: [0] dots,
+ * [1] barrier+all-reduce, [2] update, [3] barrier+all-reduce, [4] normalise, [5] launches,
+ * [6] passes, [7] late halo push.  Synchronises the device.                                  */
+int cv_ctx_trace_read(cv_ctx *ctx, double *out16, int reset);
 /* Optional kernel timing with CUDA events on the launching stream, per kernel class
  * (0 = fused SpMV, 1 = tall-skinny dot, 2 = tall-skinny update, 3 = other vector kernels).
  * cv_ctx_profile_read synchronises, returns accumulated milliseconds and launch counts
