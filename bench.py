@@ -284,8 +284,8 @@ def run_ours(args, w):
     _lib.check(rt.lib.cv_ctx_trace_read(rt.ctx, tr16, 1))
     nk = max(tr16[5], 1.0)
     orth_trace = {k: round(tr16[i] / nk * 1e-3, 2) for i, k in enumerate(
-        ["dots_us", "barrier1_allreduce_us", "update_us", "barrier2_allreduce_us", "normalise_us"])}
-    orth_trace.update(launches=int(tr16[5]), passes=int(tr16[6]), late_push_us=round(tr16[7] / nk * 1e-3, 2))
+        ["dots_us", "barrier_allreduce_us", "update_normalise_push_us", "second_pass_barrier_us"])}
+    orth_trace.update(launches=int(tr16[5]), passes=int(tr16[6]), halo_flags_us=round(tr16[7] / nk * 1e-3, 2))
     launches = rt.launch_count() - launches0
     matvecs = (rt.stats["matvecs"] - mv0) // max(args.steps, 1)
     ms_per_step = ms / args.steps

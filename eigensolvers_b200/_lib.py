@@ -38,6 +38,7 @@ SIGNATURES = {
     "cv_ctx_destroy": (_i, [_vp]),
     "cv_ctx_launch_count": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "cv_ctx_sm_count": (_i, [_vp, _pi]),
+    "cv_ctx_set_reorth_eta": (_i, [_vp, _d]),
     "cv_ctx_trace_read": (_i, [_vp, _pd, _i]),
     "cv_ctx_profile": (_i, [_vp, _i]),
     "cv_ctx_profile_read": (_i, [_vp, _pd, C.POINTER(C.c_uint64)]),

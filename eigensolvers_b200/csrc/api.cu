@@ -84,6 +84,12 @@ extern "C" int cv_ctx_launch_count(cv_ctx *ctx, uint64_t *count) {
   return CV_OK;
 }
 
+extern "C" int cv_ctx_set_reorth_eta(cv_ctx *ctx, double eta) {
+  CV_REQUIRE(ctx && eta >= 0.0, "cv_ctx_set_reorth_eta: bad argument");
+  ctx->reorth_eta = eta;
+  return CV_OK;
+}
+
 extern "C" int cv_ctx_trace_read(cv_ctx *ctx, double *out16, int reset) {
   CV_REQUIRE(ctx && out16, "cv_ctx_trace_read: null argument");
   CV_CUDA(cudaDeviceSynchronize());
@@ -673,13 +679,13 @@ int cv_orth_step_dev(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int m, const 
       CV_TRY(cv_peer_plan_exchange(ctx, op, cplx_ != 0, &a.push, nullptr));
       ctx->prepushed_x = w;
       ctx->prepushed_op = op;
-      if (dia && ctx->push_early) {  // contiguous ranges only: push unnormalised rows from phase B
-        a.push_early = 1;
-        op->wait.scale_sq = ctx->scalars + a.s_nrm;
-      }
+      if (dia && ctx->push_early) a.push_early = 1;  // contiguous ranges: pushed by phase B as produced
     }
   }
   a.trace = ctx->scalars + CV_S_TRACE;
+  static const int publish_late = getenv("EIGB200_PUBLISH_LATE") ? atoi(getenv("EIGB200_PUBLISH_LATE")) : 0;
+  static const int coop = getenv("EIGB200_COOP") ? atoi(getenv("EIGB200_COOP")) : 1;
+  a.publish_late = publish_late;
   a.host_mb = ctx->mailbox;
   a.host_flag = ctx->host_flag;
   a.host_seq = ++ctx->host_seq;
@@ -704,7 +710,11 @@ int cv_orth_step_dev(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int m, const 
   void *params[1] = {(void *)&a};
   {
     cv_prof_scope prof(ctx, 1, st);
-    CV_CUDA(cudaLaunchCooperativeKernel(kf, dim3(grid), dim3(CV_BLOCK), params, sh, st));
+    if (coop) {
+      CV_CUDA(cudaLaunchCooperativeKernel(kf, dim3(grid), dim3(CV_BLOCK), params, sh, st));
+    } else {
+      CV_CUDA(cudaLaunchKernel(kf, dim3(grid), dim3(CV_BLOCK), params, sh, st));
+    }
   }
   CV_TRY(cv_check_launch(ctx, "orth_step"));
   *fused = true;

@@ -1,22 +1,25 @@
 // kernels_orth.cuh — ONE persistent kernel per Arnoldi step of GCROT's inner FGMRES
-// (_gcrotmk.py:112-141): everything between two operator applications.
+// (_gcrotmk.py:112-141): everything between two operator applications, with ONE grid barrier and
+// ONE cross-GPU all-reduce on the critical path.
 //
-//   phase A   h = [C,V]^H w                         (tall-skinny dot, V read once)
-//   barrier   last CTA sums the per-CTA partials in a fixed order, all-reduces {<x|y>,<y|y>,h}
-//             over the ranks through peer memory (one NVLink round trip), publishes h
-//   phase B   w <- w - [C,V] h,  partial |w|^2
-//   barrier   last CTA: |w|^2 summed + all-reduced; Daniel-Gragg-Kaufman-Stewart test
-//             |w'|^2 < eta^2 |w|^2  ->  phases A and B once more (h2); results are written to the
-//             HOST mailbox (mapped pinned memory) and a sequence flag released, so the host gets
-//             the Hessenberg column while the kernel is still running
-//   phase C   w <- w / |w|  and, in row-sharded mode, the boundary rows of the NEW basis vector
-//             are pushed straight into the neighbours' halo buffers for the next SpMV.
+//   phase A   h = [C,V]^H w                          (tall-skinny dot, V read once)
+//   barrier   the last CTA to arrive sums the per-CTA partials in a fixed order, all-reduces
+//             {<x|y>, <y|y>, h} over the ranks through peer memory (one NVLink one-way latency) and
+//             obtains the norm of the projected vector WITHOUT a second reduction:
+//                 |w'|^2 = |w|^2 - sum |h_i|^2        ([C,V] orthonormal; |w|^2 comes fused out of the SpMV)
+//             Daniel-Gragg-Kaufman-Stewart test: if |w'|^2 < eta^2 |w|^2 the subtraction cancelled
+//             (and the formula lost digits) -> pass 2 below.  Otherwise the Hessenberg column is
+//             complete: it is written to the HOST mailbox (mapped pinned memory) and a sequence flag
+//             released, so the host builds its Givens rotation and queues the next SpMV while
+//   phase B   w <- (w - [C,V] h) / |w'|  streams through HBM; rows a neighbour needs are stored
+//             into its halo buffer as they are produced (NVLink traffic hidden behind the HBM
+//             stream); the last CTA to finish raises the neighbours' halo flags.
+//   pass 2    (rare) w' is not normalised, a grid barrier, then phase A on w' (h2 and |w'|^2 in
+//             the same pass), barrier, phase B with h2 and |w''|^2 = |w'|^2 - sum |h2_i|^2.
 //
 // The separate-kernel version of the same step needed 8 launches, 2 copies and a stream
-// synchronisation per step (tsdot, all-reduce, tsupdate, all-reduce, D2H, scale, halo push, halo
-// wait); at 8 GPUs that fixed cost (~90 us) was a third of the step.  Here it is one cooperative
-// launch with two grid barriers (own implementation: arrive, the LAST arriver does the serial
-// work, release) and the host polls a flag instead of synchronising the stream.
+// synchronisation (tsdot, all-reduce, tsupdate, all-reduce, D2H, scale, halo push, halo wait);
+// at 8 GPUs that fixed cost (~90 us) was a third of the step.
 #pragma once
 #include "kernels_vec.cuh"
 
@@ -35,9 +38,9 @@ struct OrthArgs {
   int me, world;
   double *err;
   PushArgs push;   // nseg == 0 && nflag == 0: nothing to push
-  int push_early;  // all segments are contiguous ranges: phase B stores the UNSCALED new rows into the
-                   // peers' halo buffers as it produces them (NVLink traffic hidden behind the HBM
-                   // stream); the consuming SpMV multiplies halo entries by 1/|w| itself
+  int push_early;  // all segments are contiguous ranges: phase B stores the new rows into the peers'
+                   // halo buffers as it produces them; otherwise (gather lists) a late push follows
+  int publish_late;  // debug: hand the scalars to the host at the END of the kernel
   double *trace;   // [16] accumulated phase times of CTA 0 in ns (tools/orth_trace.py)
   // host mailbox
   double *host_mb;
@@ -144,8 +147,8 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
   constexpr int NR = Num<T>::NRED;
   constexpr int MI = 16, LB = 8, JB = 8;
   extern __shared__ double s_h[];  // m * NR doubles
-  __shared__ double s_part[CV_WARPS][MI * NR];
-  __shared__ double s_vals[MI * NR];
+  __shared__ double s_part[CV_WARPS][MI * NR + 1];
+  __shared__ double s_vals[MI * NR + 1];
   __shared__ bool s_again;
   const int G = gridDim.x, c = blockIdx.x;
   const int m = a.p.m;
@@ -156,11 +159,13 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
   const int gx = G / ny;  // >= 1: the launcher makes G >= ny
   const int64_t npf = n / W;
   const bool tail_mine = (W == 2) && (n & 1);
+  double *p_ww = a.partials + (size_t)ny * MI * NR * gx;  // pass 2: partial |w'|^2 of the by == 0 CTAs
   unsigned long long t_prev = 0;
   if (a.trace && c == 0 && threadIdx.x == 0) {
     t_prev = global_ns();
     a.trace[5] += 1.0;
   }
+  bool pushed = false;
 
   for (int pass = 1; pass <= 2; ++pass) {
     const int s_h_out = pass == 1 ? a.s_h1 : a.s_h2;
@@ -169,7 +174,9 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
       const int by = c / gx, bx = c % gx;
       const int i0 = by * MI;
       const int mi = min(MI, m - i0);
+      const bool want_ww = pass == 2 && by == 0;
       T acc[MI];
+      double ww = 0.0;
 #pragma unroll
       for (int i = 0; i < MI; ++i) acc[i] = Num<T>::zero();
       for (int64_t ip = (int64_t)bx * blockDim.x + threadIdx.x; ip < npf; ip += (int64_t)gx * blockDim.x) {
@@ -186,10 +193,15 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
 #pragma unroll
             for (int w = 0; w < W; ++w) Num<T>::fmac(acc[ib + l], vv[l].e[w], wv.e[w]);
         }
+        if (want_ww) {
+#pragma unroll
+          for (int w = 0; w < W; ++w) ww += Num<T>::abs2(wv.e[w]);
+        }
       }
       if (tail_mine && bx == 0 && threadIdx.x == 0) {
         const T wt = ld_cg(wvec + (n - 1));
         for (int i = 0; i < mi; ++i) Num<T>::fmac(acc[i], static_cast<const T *>(a.p.v[i0 + i])[n - 1], wt);
+        if (want_ww) ww += Num<T>::abs2(wt);
       }
 #pragma unroll
       for (int i = 0; i < MI; ++i) {
@@ -201,8 +213,12 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
           if (lane == 0) s_part[warp][i * NR + k] = s;
         }
       }
+      {
+        const double s = warp_sum(ww);
+        if (lane == 0) s_part[warp][MI * NR] = s;
+      }
       __syncthreads();
-      for (int v = threadIdx.x; v < MI * NR; v += blockDim.x) {
+      for (int v = threadIdx.x; v < MI * NR + 1; v += blockDim.x) {
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < CV_WARPS; ++w) s += s_part[w][v];
@@ -211,6 +227,7 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
       __syncthreads();
       double *pslab = a.partials + (size_t)by * MI * NR * gx;
       for (int v = threadIdx.x; v < mi * NR; v += blockDim.x) pslab[(size_t)v * gx + bx] = s_vals[v];
+      if (want_ww && threadIdx.x == 0) p_ww[bx] = s_vals[MI * NR];
     }
     ORTH_TRACE(0);
     grid_barrier_with(a.bar, [&]() {
@@ -222,20 +239,66 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
         r = warp_sum(r);
         if (lane == 0) a.scal[s_h_out + v] = r;
       }
+      if (pass == 2 && warp == 0) {
+        double r = ordered_lane_sum(p_ww, gx, lane);
+        r = warp_sum(r);
+        if (lane == 0) a.scal[s_h_out + m * NR] = r;  // travels with h2 in one all-reduce
+      }
       __threadfence();
       if (a.world > 1) {
         if (pass == 1)
           cta_peer_allreduce(a.pp, a.me, a.world, a.scal + a.s_w, 3 + m * NR, a.err);
         else
-          cta_peer_allreduce(a.pp, a.me, a.world, a.scal + s_h_out, m * NR, a.err);
+          cta_peer_allreduce(a.pp, a.me, a.world, a.scal + s_h_out, m * NR + 1, a.err);
+      }
+      __syncthreads();
+      // |w'|^2 = |w|^2 - sum |h_i|^2
+      if (warp == 0) {
+        double q = 0.0;
+        for (int v = lane; v < m * NR; v += 32) {
+          const double hv = __ldcg(a.scal + s_h_out + v);
+          q = fma(hv, hv, q);
+        }
+        q = warp_sum(q);
+        if (lane == 0) {
+          const double base = pass == 1 ? __ldcg(a.scal + a.s_w + 2) : __ldcg(a.scal + s_h_out + m * NR);
+          double t = base - q;
+          bool again = false;
+          if (pass == 1) {
+            again = !(t >= a.eta2 * base);
+            a.scal[a.s_flag] = again ? 1.0 : 0.0;
+          } else if (!(t > 0.0)) {
+            t = 0.0;  // fully dependent on the basis: scipy's breakdown branch (hlast <= eps |w|)
+          }
+          if (!again) a.scal[a.s_nrm] = t;
+          s_again = again;
+        }
+      }
+      __syncthreads();
+    }, [&]() {
+      if (!s_again && !a.publish_late) {
+        // the Hessenberg column is complete: hand it to the host while phase B runs
+        const bool two = pass == 2;
+        for (int t = threadIdx.x; t < a.s_h1 + m * NR - a.s_flag; t += blockDim.x)
+          a.host_mb[a.s_flag + t] = __ldcg(a.scal + a.s_flag + t);
+        if (two)
+          for (int t = threadIdx.x; t < m * NR; t += blockDim.x) a.host_mb[a.s_h2 + t] = __ldcg(a.scal + a.s_h2 + t);
+        if (threadIdx.x == 0) a.host_mb[a.err - a.scal] = __ldcg(a.err);
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_sys(a.host_flag, a.host_seq);
       }
     });
     ORTH_TRACE(1);
-    // ---------------- phase B: w -= [C,V] h, partial |w|^2 ----------------------------------
-    bool pushed = false;
+    // ---------------- phase B: w <- (w - [C,V] h) [/ |w'| when final] ------------------------
+    const bool final_pass = pass == 2 || __ldcg(a.scal + a.s_flag) == 0.0;
+    double f = 1.0;
+    if (final_pass) {
+      f = 1.0 / sqrt(__ldcg(a.scal + a.s_nrm));
+      if (!isfinite(f)) f = 1.0;  // scipy: normalise only "if isfinite(alpha)"
+    }
     for (int j = threadIdx.x; j < m * NR; j += blockDim.x) s_h[j] = -__ldcg(a.scal + s_h_out + j);
     __syncthreads();
-    double nrm = 0.0;
     for (int64_t ip = (int64_t)c * blockDim.x + threadIdx.x; ip < npf; ip += (int64_t)G * blockDim.x) {
       Pack<T, W> acc = pk_ld_cg<T, W>(wvec, ip);
       for (int j0 = 0; j0 < m; j0 += JB) {
@@ -252,101 +315,72 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
           }
         }
       }
-      pk_st<T, W>(wvec, ip, acc);
-      if (a.push_early) pushed |= push_pack<T, W>(a.push, ip, acc);
 #pragma unroll
-      for (int w = 0; w < W; ++w) nrm += Num<T>::abs2(acc.e[w]);
+      for (int w = 0; w < W; ++w) acc.e[w] = Num<T>::scale(acc.e[w], f);
+      pk_st<T, W>(wvec, ip, acc);
+      if (final_pass && a.push_early) pushed |= push_pack<T, W>(a.push, ip, acc);
     }
     if (tail_mine && c == 0 && threadIdx.x == 0) {
       T acc = ld_cg(wvec + (n - 1));
       for (int j = 0; j < m; ++j)
         Num<T>::fma(acc, Num<T>::from_red(s_h + j * NR), static_cast<const T *>(a.p.v[j])[n - 1]);
+      acc = Num<T>::scale(acc, f);
       wvec[n - 1] = acc;
-      if (a.push_early) {
+      if (final_pass && a.push_early) {
         Pack<T, 1> one;
         one.e[0] = acc;
         pushed |= push_pack<T, 1>(a.push, n - 1, one);
       }
-      nrm += Num<T>::abs2(acc);
-    }
-    if (pushed) __threadfence_system();  // this thread's peer stores are visible before it arrives
-    {
-      const double s = warp_sum(nrm);
-      if (lane == 0) s_part[warp][0] = s;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        double r = 0.0;
-#pragma unroll
-        for (int w = 0; w < CV_WARPS; ++w) r += s_part[w][0];
-        a.partials[c] = r;
-      }
     }
     ORTH_TRACE(2);
-    grid_barrier_with(a.bar, [&]() {
-      if (warp == 0) {
-        double r = ordered_lane_sum(a.partials, G, lane);
-        r = warp_sum(r);
-        if (lane == 0) a.scal[a.s_nrm] = r;
-      }
+    if (a.trace && c == 0 && threadIdx.x == 0) a.trace[6] += 1.0;
+    if (final_pass) break;
+    grid_barrier_with(a.bar, [&]() {});  // pass 2 reads rows other CTAs have just rewritten
+    ORTH_TRACE(3);
+  }
+  if (a.publish_late) {
+    __syncthreads();
+    __shared__ bool s_last_pub;
+    if (threadIdx.x == 0) {
       __threadfence();
-      if (a.world > 1) cta_peer_allreduce(a.pp, a.me, a.world, a.scal + a.s_nrm, 1, a.err);
+      s_last_pub = atomicAdd(a.bar + 2, 1u) == gridDim.x - 1u;
+    }
+    __syncthreads();
+    if (s_last_pub) {
+      const bool two = __ldcg(a.scal + a.s_flag) != 0.0;
+      for (int t = threadIdx.x; t < a.s_h1 + m * NR - a.s_flag; t += blockDim.x)
+        a.host_mb[a.s_flag + t] = __ldcg(a.scal + a.s_flag + t);
+      if (two)
+        for (int t = threadIdx.x; t < m * NR; t += blockDim.x) a.host_mb[a.s_h2 + t] = __ldcg(a.scal + a.s_h2 + t);
+      if (threadIdx.x == 0) a.host_mb[a.err - a.scal] = __ldcg(a.err);
+      __threadfence_system();
       __syncthreads();
       if (threadIdx.x == 0) {
-        bool again = false;
-        if (pass == 1) {
-          again = !(__ldcg(a.scal + a.s_nrm) >= a.eta2 * __ldcg(a.scal + a.s_w + 2));
-          a.scal[a.s_flag] = again ? 1.0 : 0.0;
-        }
-        s_again = again;
-      }
-      __syncthreads();
-    }, [&]() {
-      if (!s_again) {
-        // final: hand the scalars to the host while phase C runs (after the barrier release)
-        const bool two = pass == 2;
-        for (int t = threadIdx.x; t < a.s_h1 + m * NR - a.s_flag; t += blockDim.x)
-          a.host_mb[a.s_flag + t] = __ldcg(a.scal + a.s_flag + t);
-        if (two)
-          for (int t = threadIdx.x; t < m * NR; t += blockDim.x) a.host_mb[a.s_h2 + t] = __ldcg(a.scal + a.s_h2 + t);
-        if (threadIdx.x == 0) a.host_mb[a.err - a.scal] = __ldcg(a.err);
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) st_release_sys(a.host_flag, a.host_seq);
-        // every CTA fenced its early halo stores before arriving: the peers may read them now
-        if (a.push_early && threadIdx.x < a.push.nflag) st_release_sys(a.push.flag_dst[threadIdx.x], a.push.seq);
-      }
-    });
-    ORTH_TRACE(3);
-    if (a.trace && c == 0 && threadIdx.x == 0) a.trace[6] += 1.0;
-    if (pass == 1 && __ldcg(a.scal + a.s_flag) == 0.0) break;
-  }
-  // ---------------- phase C: normalise (scipy: only if 1/|w| is finite), push the halo -------
-  {
-    double f = 1.0 / sqrt(__ldcg(a.scal + a.s_nrm));
-    if (!isfinite(f)) f = 1.0;
-    constexpr int U = 4;
-    const int64_t tid = (int64_t)c * blockDim.x + threadIdx.x, stride = (int64_t)G * blockDim.x;
-    for (int64_t ip0 = tid; ip0 < npf; ip0 += U * stride) {
-      Pack<T, W> x[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t ip = ip0 + u * stride;
-        x[u] = (ip < npf) ? pk_ld_cg<T, W>(wvec, ip) : pk_zero<T, W>();
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t ip = ip0 + u * stride;
-#pragma unroll
-        for (int w = 0; w < W; ++w) x[u].e[w] = Num<T>::scale(x[u].e[w], f);
-        if (ip < npf) pk_st<T, W>(wvec, ip, x[u]);
+        a.bar[2] = 0u;
+        st_release_sys(a.host_flag, a.host_seq);
       }
     }
-    if (tail_mine && c == 0 && threadIdx.x == 0) wvec[n - 1] = Num<T>::scale(ld_cg(wvec + (n - 1)), f);
   }
-  ORTH_TRACE(4);
-  if (!a.push_early && (a.push.nseg > 0 || a.push.nflag > 0)) {
-    grid_barrier_with(a.bar, [&]() {});
-    grid_halo_push<T>(a.push, wvec);
+  // ---------------- halo flags: after the LAST CTA has finished its stores --------------------
+  if (a.push.nseg > 0 || a.push.nflag > 0) {
+    if (a.push_early) {
+      if (pushed) __threadfence_system();
+      __syncthreads();
+      __shared__ bool s_last_orth;
+      if (threadIdx.x == 0) {
+        __threadfence();
+        s_last_orth = atomicAdd(a.push.ticket, 1u) == gridDim.x - 1u;
+      }
+      __syncthreads();
+      if (s_last_orth) {
+        __threadfence_system();
+        if (threadIdx.x < a.push.nflag) st_release_sys(a.push.flag_dst[threadIdx.x], a.push.seq);
+        if (threadIdx.x == 0) *a.push.ticket = 0u;
+      }
+    } else {
+      grid_barrier_with(a.bar, [&]() {});
+      grid_halo_push<T>(a.push, wvec);
+    }
     ORTH_TRACE(7);
   }
 }

@@ -67,9 +67,12 @@ int cv_ctx_destroy(cv_ctx *ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int cv_ctx_launch_count(cv_ctx *ctx, uint64_t *count);
 int cv_ctx_sm_count(cv_ctx *ctx, int *sms);
+/* GCROT's Arnoldi step repeats its Gram-Schmidt pass when the first one left less than eta of the
+ * vector's norm (Daniel-Gragg-Kaufman-Stewart).  Default 0.1; 0 = never, > 1 = always twice.    */
+int cv_ctx_set_reorth_eta(cv_ctx *ctx, double eta);
 /* Accumulated phase times (ns, as seen by CTA 0) of the fused Arnoldi-step kernel: [0] dots,
- * [1] barrier+all-reduce, [2] update, [3] barrier+all-reduce, [4] normalise, [5] launches,
- * [6] passes, [7] late halo push.  Synchronises the device.                                  */
+ * [1] barrier + all-reduce, [2] update/normalise/push, [3] barrier before a second pass,
+ * [5] launches, [6] passes, [7] halo flags / late push.  Synchronises the device.             */
 int cv_ctx_trace_read(cv_ctx *ctx, double *out16, int reset);
 /* Optional kernel timing with CUDA events on the launching stream, per kernel class
  * (0 = fused SpMV, 1 = tall-skinny dot, 2 = tall-skinny update, 3 = other vector kernels).

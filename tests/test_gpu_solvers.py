@@ -147,3 +147,40 @@ def test_iteration_counts_close_to_scipy(rt):
     st = rt.last_solve
     assert abs(st.n_matvec - count[0]) <= max(3, 0.05 * count[0]), (st.n_matvec, count[0])
     assert np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref) < 1e-4
+
+
+@pytest.mark.parametrize("eta,expect_second_pass", [(0.0, False), (0.1, None), (2.0, True)])
+@pytest.mark.parametrize("n_odd", [False, True])
+def test_fused_arnoldi_step_both_passes(rt, eta, expect_second_pass, n_odd):
+    """The fused Arnoldi-step kernel (csrc/kernels_orth.cuh): never / selectively / always taking
+    its second Gram-Schmidt pass gives the same solution to solver tolerance (the norm of the
+    projected vector comes from |w|^2 - sum|h|^2 in pass 1 and from |w'|^2 - sum|h2|^2 in pass 2);
+    odd n exercises the unpaired tail element of the 128-bit path."""
+    import ctypes as C
+    from eigensolvers_b200 import CudaVector, _lib, hamiltonians as hm
+    H = hm.laplacian3d(13 if n_odd else 12)
+    n = H.shape[0]
+    assert (n % 2 == 1) == n_odd
+    rng = np.random.default_rng(5)
+    b = rng.standard_normal(n)
+    sigma = 0.9
+    tol = 1e-10
+    x_ref, info_ref = _scipy_solve(H, b, sigma, "gcrotmk", tol, 0.0, 1000)
+    assert info_ref == 0
+    _lib.check(rt.lib.cv_ctx_set_reorth_eta(rt.ctx, C.c_double(eta)))
+    try:
+        o = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 1000, "linear_tol": tol, "linear_atol": 0.0}}
+        x = CudaVector.solve(H, CudaVector(b, o), sigma).array
+        st = rt.last_solve
+    finally:
+        _lib.check(rt.lib.cv_ctx_set_reorth_eta(rt.ctx, C.c_double(0.1)))
+    assert st.info == 0
+    if expect_second_pass is True:
+        assert st.n_reorth >= st.n_matvec - st.n_outer - 2
+    if expect_second_pass is False:
+        assert st.n_reorth == 0
+    r = b - (sigma * x - H @ x)
+    assert np.linalg.norm(r) <= tol * np.linalg.norm(b) * (1 + 1e-6)
+    assert np.linalg.norm(x - x_ref) <= 1e-7 * np.linalg.norm(x_ref)
+    if eta > 0:
+        assert abs(st.n_matvec - 0) > 0
