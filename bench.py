@@ -41,6 +41,8 @@ WORKLOADS = {
 }
 # Matvec count of one full run of each workload on the GPU path (measured);
 # the CPU arm times a bounded sample and extrapolates with it.
+# DRAM bytes per launch of the dominant kernel from the ncu --set full capture (profiles/README.md)
+TRAFFIC_NCU = {("c3", "dia", 1): 4160061000 + 136101632}
 MATVECS_TO_ECONV = {"c3": 4318, "c3mid": 6772, "c3small": 3738, "c2": 9000, "c2small": 3000}
 
 
@@ -315,7 +317,9 @@ def run_ours(args, w):
     roofline = {"bound": "hbm", "kernel": f"k_spmv_{op.format}<double> (fused shift + dots)", "achieved": achieved,
                 "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
-                "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "launches_timed": int(cnt4[0]),
+                "traffic": TRAFFIC_NCU.get((args.workload, op.format, world)),
+                "traffic_source": "profiles/r1_ncu_c3_full_kernels.csv (dram__bytes_read+write per launch)",
+                "algorithmic_bytes_per_launch": alg_bytes, "launches_timed": int(cnt4[0]),
                 "avg_launch_ms": spmv_ms,
                 "step_share": {"spmv": ms4[0] / (t_prof * 1e3), "tsdot": ms4[1] / (t_prof * 1e3),
                                "tsupdate": ms4[2] / (t_prof * 1e3)}}
