@@ -378,7 +378,9 @@ def run_ours(args, w):
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "result": {"converged": converged, "eigenvalues": ev_out, "cumIter": int(st["cumIter"]),
                        "matvecs_per_step": int(matvecs), "true_residual": true_res,
-                       "profiled_step_s": t_prof, "arnoldi_step_kernel_phases": orth_trace},
+                       "profiled_step_s": t_prof, "arnoldi_step_kernel_phases": orth_trace,
+                       "solves_total": int(rt.stats["solves"]), "solves_switched_to_safe_reorth": int(rt.stats.get("safe_solves", 0)),
+                       "max_orthogonality_loss_seen": float(rt.stats.get("orth_loss", 0.0))},
         }
         print(json.dumps(line))
     if world > 1:

@@ -22,7 +22,8 @@ class CudaVecError(RuntimeError):
 
 class SolveStats(C.Structure):
     _fields_ = [("info", C.c_int), ("n_matvec", C.c_int), ("n_outer", C.c_int), ("n_sync", C.c_int),
-                ("n_reorth", C.c_int), ("resid", C.c_double), ("b_norm", C.c_double)]
+                ("n_reorth", C.c_int), ("resid", C.c_double), ("b_norm", C.c_double),
+                ("orth_loss", C.c_double), ("n_safe", C.c_int), ("reserved", C.c_int)]
 
 
 _vp, _i, _i64, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_size_t

@@ -52,7 +52,7 @@ extern "C" int cv_ctx_create(int device, void *scratch_dev, size_t scratch_bytes
   c->push_early = getenv("EIGB200_PUSH_EARLY") ? atoi(getenv("EIGB200_PUSH_EARLY")) != 0 : true;
   c->launches = 0;
   c->prof = nullptr;
-  c->reorth_eta = 0.1;
+  c->reorth_eta = getenv("EIGB200_REORTH_ETA") ? atof(getenv("EIGB200_REORTH_ETA")) : 0.1;
   c->defer_reduce = false;
   c->comm = nullptr;
   c->peer = nullptr;
@@ -638,9 +638,10 @@ int cv_wait_mailbox(cv_ctx *ctx, unsigned long long seq, cudaStream_t st) {
 // s_flag+2..4 = SpMV dots, s_flag+5.. = h1, s_h2.. = h2.  *fused = false when this configuration
 // has to take the separate-kernel path (NCCL transport).
 int cv_orth_step_dev(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int m, const void *const *basis, void *w,
-                     int s_flag, int s_h2, cudaStream_t st, bool *fused) {
+                     int s_flag, int s_h2, int s_lag, double eta, cudaStream_t st, bool *fused) {
   *fused = false;
-  if (ctx->world > 1 && !ctx->peer) return CV_OK;
+  static const int use_fused = getenv("EIGB200_FUSED") ? atoi(getenv("EIGB200_FUSED")) : 1;
+  if (!use_fused || (ctx->world > 1 && !ctx->peer)) return CV_OK;
   CV_REQUIRE(m >= 1 && m <= CV_MAX_PTRS, "orth_step: m=%d out of range", m);
   OrthArgs a;
   a.p.m = m;
@@ -661,7 +662,8 @@ int cv_orth_step_dev(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int m, const 
   a.s_w = s_flag + 2;
   a.s_h1 = s_flag + 5;
   a.s_h2 = s_h2;
-  a.eta2 = ctx->reorth_eta * ctx->reorth_eta;
+  a.s_lag = s_lag;
+  a.eta2 = eta * eta;
   a.me = ctx->rank;
   a.world = ctx->world;
   a.err = ctx->scalars + CV_S_ERR;

@@ -72,6 +72,6 @@ int cv_peer_plan_exchange(cv_ctx *ctx, cv_op *op, bool cplx_, PushArgs *a, int64
 const PeerPtrs *cv_peer_ptrs(cv_ctx *ctx);
 int cv_wait_mailbox(cv_ctx *ctx, unsigned long long seq, cudaStream_t st);
 int cv_orth_step_dev(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int m, const void *const *basis, void *w,
-                     int s_flag, int s_h2, cudaStream_t st, bool *fused);
+                     int s_flag, int s_h2, int s_lag, double eta, cudaStream_t st, bool *fused);
 int cv_peer_detach(cv_ctx *ctx);
 int cv_peer_allreduce(cv_ctx *ctx, double *buf_dev, int count, cudaStream_t st);

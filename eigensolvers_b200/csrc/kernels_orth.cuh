@@ -32,6 +32,8 @@ struct OrthArgs {
   int s_nrm;       // out: |w'|^2 after the last pass (summed over ranks)
   int s_w;         // in: {Re<x|y>, Im<x|y>, <y|y>} partial dots of the SpMV (this rank), out: summed
   int s_h1, s_h2;  // out: projection coefficients of pass 1 / pass 2  (s_h1 == s_w + 3)
+  int s_lag;       // out: explicitly summed |v_j|^2 of the PREVIOUS step's normalised vector (should be 1;
+                   // its local partial arrives in scal[s_nrm] and rides in this step's all-reduce)
   double eta2;
   // peers (world == 1: unused)
   PeerPtrs pp;
@@ -160,6 +162,7 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
   const int64_t npf = n / W;
   const bool tail_mine = (W == 2) && (n & 1);
   double *p_ww = a.partials + (size_t)ny * MI * NR * gx;  // pass 2: partial |w'|^2 of the by == 0 CTAs
+  double *p_nx = p_ww + 2048;                             // explicit |v_new|^2 partials, one per CTA
   unsigned long long t_prev = 0;
   if (a.trace && c == 0 && threadIdx.x == 0) {
     t_prev = global_ns();
@@ -246,11 +249,13 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
       }
       __threadfence();
       if (a.world > 1) {
-        if (pass == 1)
-          cta_peer_allreduce(a.pp, a.me, a.world, a.scal + a.s_w, 3 + m * NR, a.err);
+        if (pass == 1)  // {lagged |v_j|^2, <x|y>, <y|y>, h}: s_nrm, s_w, s_h1 are contiguous
+          cta_peer_allreduce(a.pp, a.me, a.world, a.scal + a.s_nrm, 4 + m * NR, a.err);
         else
           cta_peer_allreduce(a.pp, a.me, a.world, a.scal + s_h_out, m * NR + 1, a.err);
       }
+      __syncthreads();
+      if (pass == 1 && threadIdx.x == 0) a.scal[a.s_lag] = __ldcg(a.scal + a.s_nrm);
       __syncthreads();
       // |w'|^2 = |w|^2 - sum |h_i|^2
       if (warp == 0) {
@@ -283,7 +288,10 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
           a.host_mb[a.s_flag + t] = __ldcg(a.scal + a.s_flag + t);
         if (two)
           for (int t = threadIdx.x; t < m * NR; t += blockDim.x) a.host_mb[a.s_h2 + t] = __ldcg(a.scal + a.s_h2 + t);
-        if (threadIdx.x == 0) a.host_mb[a.err - a.scal] = __ldcg(a.err);
+        if (threadIdx.x == 0) {
+          a.host_mb[a.err - a.scal] = __ldcg(a.err);
+          a.host_mb[a.s_lag] = __ldcg(a.scal + a.s_lag);
+        }
         __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) st_release_sys(a.host_flag, a.host_seq);
@@ -299,6 +307,7 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
     }
     for (int j = threadIdx.x; j < m * NR; j += blockDim.x) s_h[j] = -__ldcg(a.scal + s_h_out + j);
     __syncthreads();
+    double nx = 0.0;
     for (int64_t ip = (int64_t)c * blockDim.x + threadIdx.x; ip < npf; ip += (int64_t)G * blockDim.x) {
       Pack<T, W> acc = pk_ld_cg<T, W>(wvec, ip);
       for (int j0 = 0; j0 < m; j0 += JB) {
@@ -316,7 +325,10 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
         }
       }
 #pragma unroll
-      for (int w = 0; w < W; ++w) acc.e[w] = Num<T>::scale(acc.e[w], f);
+      for (int w = 0; w < W; ++w) {
+        acc.e[w] = Num<T>::scale(acc.e[w], f);
+        nx += Num<T>::abs2(acc.e[w]);
+      }
       pk_st<T, W>(wvec, ip, acc);
       if (final_pass && a.push_early) pushed |= push_pack<T, W>(a.push, ip, acc);
     }
@@ -326,10 +338,22 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
         Num<T>::fma(acc, Num<T>::from_red(s_h + j * NR), static_cast<const T *>(a.p.v[j])[n - 1]);
       acc = Num<T>::scale(acc, f);
       wvec[n - 1] = acc;
+      nx += Num<T>::abs2(acc);
       if (final_pass && a.push_early) {
         Pack<T, 1> one;
         one.e[0] = acc;
         pushed |= push_pack<T, 1>(a.push, n - 1, one);
+      }
+    }
+    if (final_pass) {
+      const double s = warp_sum(nx);
+      if (lane == 0) s_part[warp][0] = s;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double r = 0.0;
+#pragma unroll
+        for (int w = 0; w < CV_WARPS; ++w) r += s_part[w][0];
+        p_nx[c] = r;
       }
     }
     ORTH_TRACE(2);
@@ -361,26 +385,33 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
       }
     }
   }
-  // ---------------- halo flags: after the LAST CTA has finished its stores --------------------
-  if (a.push.nseg > 0 || a.push.nflag > 0) {
-    if (a.push_early) {
-      if (pushed) __threadfence_system();
-      __syncthreads();
-      __shared__ bool s_last_orth;
-      if (threadIdx.x == 0) {
-        __threadfence();
-        s_last_orth = atomicAdd(a.push.ticket, 1u) == gridDim.x - 1u;
-      }
-      __syncthreads();
-      if (s_last_orth) {
-        __threadfence_system();
-        if (threadIdx.x < a.push.nflag) st_release_sys(a.push.flag_dst[threadIdx.x], a.push.seq);
-        if (threadIdx.x == 0) *a.push.ticket = 0u;
-      }
-    } else {
-      grid_barrier_with(a.bar, [&]() {});
-      grid_halo_push<T>(a.push, wvec);
-    }
-    ORTH_TRACE(7);
+  // ---------------- kernel tail: the LAST CTA to finish sums the explicit |v_new|^2 partials (health
+  // monitor, read by the next step) and raises the neighbours' halo flags -----------------------
+  const bool early = a.push_early && (a.push.nseg > 0 || a.push.nflag > 0);
+  if (pushed) __threadfence_system();
+  __syncthreads();
+  __shared__ bool s_last_orth;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last_orth = atomicAdd(a.push.ticket, 1u) == gridDim.x - 1u;
   }
+  __syncthreads();
+  if (s_last_orth) {
+    __threadfence();
+    if (warp == 0) {
+      double r = ordered_lane_sum(p_nx, G, lane);
+      r = warp_sum(r);
+      if (lane == 0) a.scal[a.s_nrm] = r;  // local partial; summed over ranks by the next step
+    }
+    if (early) {
+      __threadfence_system();
+      if (threadIdx.x < a.push.nflag) st_release_sys(a.push.flag_dst[threadIdx.x], a.push.seq);
+    }
+    if (threadIdx.x == 0) *a.push.ticket = 0u;
+  }
+  if (!a.push_early && (a.push.nseg > 0 || a.push.nflag > 0)) {
+    grid_barrier_with(a.bar, [&]() {});
+    grid_halo_push<T>(a.push, wvec);
+  }
+  ORTH_TRACE(7);
 }

@@ -36,7 +36,8 @@ constexpr int S_NRM = CV_S_SOLVER + 7;     // squared norm of the orthogonalised
 constexpr int S_W = CV_S_SOLVER + 8;       // {Re<x|y>, Im<x|y>, <y|y>} of the fused SpMV
 constexpr int S_H1 = CV_S_SOLVER + 11;     // first-pass projection coefficients
 constexpr int S_H2 = S_H1 + 2 * CV_MAX_PTRS;
-constexpr int S_END = S_H2 + 2 * CV_MAX_PTRS;
+constexpr int S_LAG = S_H2 + 2 * CV_MAX_PTRS + 2;  // explicit |v_j|^2 of the previous step (health monitor)
+constexpr int S_END = S_LAG + 1;
 static_assert(S_END <= (int)CV_N_SCALARS, "solver scalar slots exceed the mailbox");
 
 inline size_t vec_stride_bytes(int64_t n, int cplx_) {
@@ -157,6 +158,10 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
 
   int j_outer = 0;
   bool converged = false;
+  double eta_now = ctx->reorth_eta;  // 0 = never re-orthogonalise (monitor off), >= 1/sqrt(2) = classic
+  // tolerated loss of orthogonality before the switch: three orders below the requested
+  // accuracy, between 1e-10 and 1e-7
+  const double orth_tol = std::min(1e-7, std::max(1e-10, 1e-3 * std::max(rtol, b_norm > 0 ? atol_in / b_norm : 0.0)));
   for (j_outer = 0; j_outer < maxiter; ++j_outer) {
     const double beta_tol = std::max(atol, rtol * b_norm);
     if (beta <= beta_tol && (j_outer > 0 || !cu_slots.empty())) {
@@ -201,9 +206,22 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
       // and the halo push of the new basis vector: ONE fused persistent kernel whose scalars land
       // in the mailbox (kernels_orth.cuh).  The SpMV's dots travel in the same all-reduce.
       bool fused = false;
-      CV_TRY(cv_orth_step_dev(ctx, op, n, cplx_, nb, basis.data(), w, S_FLAG, S_H2, st, &fused));
+      CV_TRY(cv_orth_step_dev(ctx, op, n, cplx_, nb, basis.data(), w, S_FLAG, S_H2, S_LAG, eta_now, st, &fused));
       if (fused) {
         stats->n_sync++;
+        // Health monitor: the previous step normalised v_j with |w'|^2 = |w|^2 - sum|h|^2, which is
+        // exact only while [C,V] is orthonormal.  Its explicitly summed norm arrives one step late;
+        // a deviation from 1 means the optimistic single-pass threshold is letting orthogonality
+        // errors compound (each cancelling step amplifies them), so the rest of this solve uses the
+        // classic "twice is enough" threshold 1/sqrt(2) (as PETSc's refine-if-needed).
+        if (j > 0) {
+          const double dev = fabs(mb[S_LAG] - 1.0);
+          if (dev > stats->orth_loss) stats->orth_loss = dev;
+          if (dev > orth_tol && eta_now > 0.0 && eta_now < 0.70710678118654752) {
+            eta_now = 0.70710678118654752;
+            stats->n_safe++;
+          }
+        }
         for (int i = 0; i < nb; ++i) {
           zc h = cplx_ ? zc(mb[S_H1 + 2 * i], mb[S_H1 + 2 * i + 1]) : zc(mb[S_H1 + i], 0.0);
           if (mb[S_FLAG] != 0.0) h += cplx_ ? zc(mb[S_H2 + 2 * i], mb[S_H2 + 2 * i + 1]) : zc(mb[S_H2 + i], 0.0);
@@ -213,6 +231,13 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
             hcur[i - nc] = h;
         }
         if (mb[S_FLAG] != 0.0) stats->n_reorth++;
+        static const int dbg = getenv("EIGB200_DEBUG") ? atoi(getenv("EIGB200_DEBUG")) : 0;
+        if (dbg && (mb[S_FLAG] != 0.0 || !(mb[S_NRM] > 0) || (dbg > 1 && j_outer >= dbg))) {
+          double q1 = 0, q2 = 0;
+          for (int i = 0; i < nb * NR; ++i) q1 += mb[S_H1 + i] * mb[S_H1 + i], q2 += mb[S_H2 + i] * mb[S_H2 + i];
+          fprintf(stderr, "[orth] outer %d j %d nc %d nb %d ww %.17g sum_h1^2 %.17g flag %g sum_h2^2 %.17g nrm2 %.17g beta %.6g\n",
+                  j_outer, j, nc, nb, mb[S_W + 2], q1, mb[S_FLAG], q2, mb[S_NRM], beta);
+        }
       } else {
         CV_TRY(arnoldi_orth_unfused(ctx, n, cplx_, nc, nb, basis, w, B, ldb, j, hcur, stats, st));
       }

@@ -338,6 +338,8 @@ class CudaVector(AbstractVector):
         rt.stats["syncs"] += stats.n_sync
         rt.stats["outer"] += stats.n_outer
         rt.stats["reorth"] = rt.stats.get("reorth", 0) + stats.n_reorth
+        rt.stats["safe_solves"] = rt.stats.get("safe_solves", 0) + stats.n_safe
+        rt.stats["orth_loss"] = max(rt.stats.get("orth_loss", 0.0), stats.orth_loss)
         rt.last_solve = stats
         if stats.info != 0:  # numpyVector.py:175-177 (turns the warning into an exception)
             warnings.simplefilter('error', UserWarning)

@@ -231,6 +231,9 @@ typedef struct cv_solve_stats {
   int n_reorth;      /* Arnoldi steps that needed the second Gram-Schmidt pass              */
   double resid;      /* last residual norm estimate                                         */
   double b_norm;
+  double orth_loss;  /* max | |v_j|^2 - 1 | seen by the Arnoldi health monitor               */
+  int n_safe;        /* 1 if the solve switched to the classic re-orthogonalisation threshold */
+  int reserved;
 } cv_solve_stats;
 
 size_t cv_solve_workspace_bytes(int64_t n, int cplx, int solver, int m, int k);
