@@ -72,7 +72,7 @@ class DeviceOperator:
 
     @classmethod
     def from_host(cls, H, runtime=None, fmt="auto"):
-        """Upload (this rank's row block of) ``H``.  ``fmt``: 'auto' | 'csr' | 'sell'."""
+        """Upload (this rank's row block of) ``H``.  ``fmt``: 'auto' | 'csr' | 'sell' | 'dia'."""
         from .runtime import Runtime
         rt = runtime or Runtime.get()
         A = cls._as_csr(H)
@@ -80,12 +80,29 @@ class DeviceOperator:
         indptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
         indices = np.ascontiguousarray(A.indices, dtype=np.int32)
         data = np.ascontiguousarray(A.data, dtype=np.float64)
-        gcols, row0 = indices, 0
-        if rt.world > 1:
-            r0, r1 = rt.local_range(A.shape[0])
-            gcols, row0 = indices[int(indptr[r0]):int(indptr[r1])], r0
-            indptr, indices, data = op._shard(indptr, indices, data)
-        return op._finish(indptr, indices, data, fmt, gcols, row0)
+        if rt.world == 1:
+            return op._finish(indptr, indices, data, fmt, indices, 0)
+        r0, r1 = rt.local_range(A.shape[0])
+        lo, hi = int(indptr[r0]), int(indptr[r1])
+        return op._finish_sharded(np.ascontiguousarray(indptr[r0:r1 + 1] - lo), indices[lo:hi], data[lo:hi], r0, r1, fmt)
+
+    def _finish_sharded(self, indptr, gcols, data, r0, r1, fmt):
+        """Row-sharded construction from this rank's block (indptr rebased to 0, GLOBAL column ids).
+        Banded operators go straight to DIA storage: its halo is the contiguous band below/above
+        the block, so the general plan (sorted unique halo columns, renumbered local CSR, gather
+        lists exchanged between ranks — the expensive host part) is never built for them."""
+        rt = self.rt
+        self.n_local, self.row0 = r1 - r0, r0
+        self.nnz = int(indptr[-1])
+        if fmt in ("auto", "dia") and self.shape[0] == self.shape[1]:
+            table = self._dia_table(indptr, gcols, r0, force=(fmt == "dia"))
+            if table is not None and self._build_dia_direct(indptr, gcols, data, r0, table):
+                return self
+            if fmt == "dia":
+                raise ValueError("operator is not banded enough for DIA storage")
+        loc_indptr, loc_indices, loc_data = self._localize(indptr, gcols, data, r0, r1, full=False)
+        return self._finish(loc_indptr, loc_indices, loc_data, "sell" if fmt == "sell" else ("csr" if fmt == "csr" else "auto_nodia"),
+                            gcols, r0)
 
     def _finish(self, indptr, indices, data, fmt, gcols=None, row0=0):
         """Upload the (local) CSR arrays, create the cv_op, register the halo plan, then pick the
@@ -104,38 +121,42 @@ class DeviceOperator:
                                            C.byref(op.handle)))
         if rt.world > 1:
             op._register_halo()
-        if fmt in ("auto", "dia") and op.shape[0] == op.shape[1]:
-            ok = op._build_dia(indptr, indices if gcols is None else gcols, row0, force=(fmt == "dia"))
-            if ok:
+        if fmt in ("auto", "dia") and rt.world == 1 and op.shape[0] == op.shape[1]:
+            table = op._dia_table(indptr, indices, 0, force=(fmt == "dia"))
+            if table is not None and op._attach_dia(table, None, 0):
                 return op
             if fmt == "dia":
                 raise ValueError("operator is not banded enough for DIA storage")
-        if fmt in ("auto", "sell") and n_rows > 0 and op.nnz > 0:
+        if fmt in ("auto", "auto_nodia", "sell") and n_rows > 0 and op.nnz > 0:
             op._build_sell(force=(fmt == "sell"))
         return op
 
     # ---------------------------------------------------------------------------------------
     MAX_DIAG = 64
 
-    def _build_dia(self, indptr, gcols, row0, force=False):
-        """Diagonal storage when every entry sits on one of <= 64 column offsets (stencil and
-        product-basis Hamiltonians).  The offset table comes from a sample of rows on the host;
-        the device fill kernel verifies EVERY entry and the format is dropped if one is off-table.
-        All ranks take the same decision (the table is the union over ranks)."""
-        rt, t = self.rt, self.rt.torch
+    def _dia_table(self, indptr, gcols, row0, force=False):
+        """Offsets col-row of a diagonal layout, or None.  The table comes from a sample of rows on
+        the host (<= 64 distinct offsets: stencil and product-basis Hamiltonians); the device fill
+        kernel later verifies EVERY entry.  Collective: all ranks take the same decision (the table
+        is the union over ranks)."""
+        rt = self.rt
         n_rows = len(indptr) - 1
         if n_rows == 0 and rt.world == 1:
-            return False
-        sample = np.unique(np.concatenate([
-            np.arange(0, min(n_rows, 2048)), np.arange(max(n_rows - 2048, 0), n_rows),
-            np.linspace(0, max(n_rows - 1, 0), num=min(n_rows, 4096), dtype=np.int64)])) if n_rows else np.empty(0, np.int64)
-        offs = set()
-        for r in sample:
-            lo, hi = int(indptr[r]), int(indptr[r + 1])
-            offs.update((gcols[lo:hi].astype(np.int64) - (row0 + int(r))).tolist())
-            if len(offs) > self.MAX_DIAG:
-                break
-        info = (sorted(offs), int(self.nnz), int(n_rows))
+            return None
+        offs = np.empty(0, np.int64)
+        if n_rows:
+            sample = np.unique(np.concatenate([
+                np.arange(0, min(n_rows, 2048)), np.arange(max(n_rows - 2048, 0), n_rows),
+                np.linspace(0, n_rows - 1, num=min(n_rows, 4096), dtype=np.int64)]))
+            starts, stops = indptr[sample], indptr[sample + 1]
+            lens = (stops - starts).astype(np.int64)
+            if lens.sum():
+                pos = np.repeat(starts - np.concatenate(([0], np.cumsum(lens)[:-1])), lens) + np.arange(lens.sum())
+                rows = np.repeat(sample + row0, lens)
+                offs = np.unique(np.asarray(gcols)[pos].astype(np.int64) - rows)
+                if len(offs) > self.MAX_DIAG:
+                    offs = offs[:self.MAX_DIAG + 1]
+        info = (offs.tolist(), int(self.nnz), int(n_rows))
         if rt.world > 1:
             import torch.distributed as dist
             box = [None] * rt.world
@@ -146,17 +167,22 @@ class DeviceOperator:
         nnz_all, rows_all = sum(b[1] for b in box), sum(b[2] for b in box)
         D = len(table)
         if D == 0 or D > self.MAX_DIAG:
-            return False
+            return None
         # 8 bytes per stored slot against 12 per CSR entry; tiny matrices are not worth a format
         if not force and (8.0 * D * rows_all > 0.95 * 12.0 * nnz_all or rows_all < 1024):
-            return False
+            return None
         if max(abs(table[0]), abs(table[-1])) >= 2 ** 31 - 1:
-            return False
+            return None
+        return table
+
+    def _attach_dia(self, table, d_gcols, row0):
+        """Scatter the CSR values into the diagonal layout on the device.  Returns False (all ranks
+        alike) if some entry is off the table; the operator then keeps its previous format."""
+        rt, t = self.rt, self.rt.torch
+        n_rows = self.n_local
+        D = len(table)
         ld = (n_rows + 31) // 32 * 32
         d_val = t.zeros(max(D * ld, 1), dtype=t.float64, device=rt.device)
-        d_gcols = None
-        if rt.world > 1:
-            d_gcols = rt.upload(np.ascontiguousarray(gcols, dtype=np.int32)) if len(gcols) else None
         offs_arr = np.ascontiguousarray(table, dtype=np.int32)
         ok = C.c_int(0)
         _lib.check(rt.lib.cv_op_attach_dia(rt.ctx, self.handle, D, offs_arr.ctypes.data,
@@ -183,6 +209,8 @@ class DeviceOperator:
             off = rt.offsets_for(self.shape[0])
             _lib.check(rt.lib.cv_op_set_dia_halo(rt.ctx, self.handle, off.ctypes.data, halo_lo.data_ptr(),
                                                  halo_hi.data_ptr()))
+            r0, r1 = int(off[rt.rank]), int(off[rt.rank + 1])
+            self.n_halo = min(lo_len, r0) + min(hi_len, self.shape[0] - r1)   # band rows held by other ranks
             if rt.transport == "peer":
                 # neighbours push their boundary rows straight into these buffers over NVLink
                 ptrs, _ = rt.peer_shared_alloc(rt.lib.cv_op_dia_halo_bytes(self.handle))
@@ -191,6 +219,24 @@ class DeviceOperator:
                     arr = (C.c_void_p * rt.world)(*ptrs)
                     _lib.check(rt.lib.cv_op_set_dia_halo_peers(rt.ctx, self.handle,
                                                                C.cast(arr, C.POINTER(C.c_void_p))))
+        return True
+
+    def _build_dia_direct(self, indptr, gcols, data, r0, table):
+        """Sharded DIA without the general halo plan: the CSR arrays on the device keep GLOBAL
+        column ids (only the fill kernel reads them), so CSR/SELL are not available on this handle."""
+        rt, t = self.rt, self.rt.torch
+        n_rows = len(indptr) - 1
+        d_indptr = rt.upload(indptr)
+        d_gcols = rt.upload(np.ascontiguousarray(gcols, dtype=np.int32)) if self.nnz else t.empty(0, dtype=t.int32, device=rt.device)
+        d_data = rt.upload(data) if self.nnz else t.empty(0, dtype=t.float64, device=rt.device)
+        _lib.check(rt.lib.cv_op_create_csr(rt.ctx, n_rows, n_rows, self.nnz, d_indptr.data_ptr(),
+                                           d_gcols.data_ptr(), d_data.data_ptr(), C.byref(self.handle)))
+        if not self._attach_dia(table, d_gcols, r0):
+            rt.lib.cv_op_destroy(self.handle)
+            self.handle = C.c_void_p()
+            return False
+        self._dia_only = True
+        self._keep += [d_indptr, d_gcols, d_data]   # the handle borrows them
         return True
 
     # ---------------------------------------------------------------------------------------
@@ -218,6 +264,9 @@ class DeviceOperator:
         self.format = "sell"
 
     def set_format(self, fmt):
+        if getattr(self, "_dia_only", False) and fmt != "dia":
+            raise NotImplementedError("this sharded operator was built directly in DIA storage; construct it "
+                                      "with fmt='csr' or fmt='sell' to get the general halo plan")
         code = {"csr": _lib.CV_FMT_CSR, "sell": _lib.CV_FMT_SELL, "dia": _lib.CV_FMT_DIA}[fmt]
         if fmt == "sell" and self.padded_nnz == 0:
             self._build_sell(force=True)
@@ -225,13 +274,6 @@ class DeviceOperator:
         self.format = fmt
 
     # -- row-sharded mode --------------------------------------------------------------------
-    def _shard(self, indptr, indices, data):
-        """Slice this rank's row block out of the FULL matrix and renumber its columns."""
-        rt = self.rt
-        off = rt.offsets_for(self.shape[0])
-        r0, r1 = int(off[rt.rank]), int(off[rt.rank + 1])
-        return self._localize(indptr, indices, data, r0, r1, full=True)
-
     def _localize(self, indptr, indices, data, r0, r1, full):
         """Renumber the columns of rows [r0, r1) to [owned | halo] (cv_halo_build, comm.cu).
         `full`: indptr/indices/data describe the whole matrix; otherwise only the row block
@@ -271,10 +313,9 @@ class DeviceOperator:
         indptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
         indices = np.ascontiguousarray(A.indices, dtype=np.int32)
         data = np.ascontiguousarray(A.data, dtype=np.float64)
-        gcols = indices
-        if rt.world > 1:
-            indptr, indices, data = op._localize(indptr, indices, data, r0, r1, full=False)
-        return op._finish(indptr, indices, data, fmt, gcols, r0)
+        if rt.world == 1:
+            return op._finish(indptr, indices, data, fmt, indices, r0)
+        return op._finish_sharded(indptr, indices, data, r0, r1, fmt)
 
     def _register_halo(self):
         """Exchange the halo request lists once (host, torch.distributed) and register the plan."""
