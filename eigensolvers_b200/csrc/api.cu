@@ -923,13 +923,28 @@ static int launch_spmv_fmt(cv_ctx *ctx, cv_op *op, const SpmvArgs<T> &a, cudaStr
     d.halo_hi = static_cast<const T *>(op->peer_halo ? op->halo_hi_cur : op->halo_hi);
     d.lo_len = op->lo_len;
     d.hi_len = op->hi_len;
-    auto kf = k_spmv_dia<T, HALO, EPI, DOTS>;
-    int wave = cv_occ_grid(ctx, (const void *)kf, (int64_t)1 << 40, CV_BLOCK);
-    int64_t need = (op->n_rows + CV_BLOCK - 1) / CV_BLOCK;
-    // with fused dots every CTA ends in a reduction epilogue (~3 us of latency): keep ONE
-    // persistent wave; without, small problems run one row per thread for load balance
-    int grid = (int)((!DOTS && need <= 16 * (int64_t)wave) || need < wave ? need : wave);
-    kf<<<grid, CV_BLOCK, 0, st>>>(d);
+    static const int pair_rows = getenv("EIGB200_DIA_PAIR") ? atoi(getenv("EIGB200_DIA_PAIR")) : 1;
+    bool paired = false;
+    if constexpr (sizeof(T) == 8) {
+      // two rows per thread with 128-bit loads (real vectors, 16-byte aligned x, even leading dimension)
+      if (pair_rows && (((uintptr_t)a.x | (uintptr_t)op->dia_val) & 15) == 0 && (op->dia_ld & 1) == 0 && op->n_rows >= 2) {
+        auto kf = k_spmv_dia2<HALO, EPI, DOTS>;
+        int wave = cv_occ_grid(ctx, (const void *)kf, (int64_t)1 << 40, CV_BLOCK);
+        int64_t need = ((op->n_rows + 1) / 2 + CV_BLOCK - 1) / CV_BLOCK;
+        int grid = (int)((!DOTS && need <= 16 * (int64_t)wave) || need < wave ? need : wave);
+        kf<<<grid, CV_BLOCK, 0, st>>>(d);
+        paired = true;
+      }
+    }
+    if (!paired) {
+      auto kf = k_spmv_dia<T, HALO, EPI, DOTS>;
+      int wave = cv_occ_grid(ctx, (const void *)kf, (int64_t)1 << 40, CV_BLOCK);
+      int64_t need = (op->n_rows + CV_BLOCK - 1) / CV_BLOCK;
+      // with fused dots every CTA ends in a reduction epilogue (~3 us of latency): keep ONE
+      // persistent wave; without, small problems run one row per thread for load balance
+      int grid = (int)((!DOTS && need <= 16 * (int64_t)wave) || need < wave ? need : wave);
+      kf<<<grid, CV_BLOCK, 0, st>>>(d);
+    }
   } else if (op->fmt == CV_FMT_SELL) {
     auto kf = k_spmv_sell<T, HALO, EPI, DOTS>;
     int wave = cv_occ_grid(ctx, (const void *)kf, (int64_t)1 << 40, CV_WARPS);

@@ -83,6 +83,58 @@ __global__ void __launch_bounds__(CV_BLOCK, sizeof(T) == 8 ? (HALO ? 5 : 6) : (H
 }
 
 // ------------------------------------------------------------------------------------------
+// Real vectors, two rows per thread: the value stream of a diagonal and (for even offsets) the x
+// entries of a row pair are ONE 128-bit load each, halving the load-instruction count.  The
+// one-row kernel above issues 50 LDG.64 per row for 25 diagonals and ncu shows its LSU pipe 75 %
+// busy with DRAM at 69 % (profiles/r1_ncu_c3_full_kernels.csv): it is instruction-issue bound
+// before it is bandwidth bound.  Pairs that are misaligned (odd offset) or touch the halo/edge
+// fall back to two 64-bit loads.  Requires x and dia_val 16-byte aligned (ld is a multiple of 32).
+// ------------------------------------------------------------------------------------------
+template <bool HALO>
+__device__ __forceinline__ double2 dia_x2(const DiaArgs<double> &a, int i, int n, double hs) {
+  if (!(i & 1) && i >= 0 && i + 1 < n) return __ldg(reinterpret_cast<const double2 *>(a.s.x + i));
+  return make_double2(dia_x<double, HALO>(a, i, n, hs), dia_x<double, HALO>(a, i + 1, n, hs));
+}
+
+template <bool HALO, bool EPI, bool DOTS>
+__global__ void __launch_bounds__(CV_BLOCK, 4) k_spmv_dia2(const __grid_constant__ DiaArgs<double> a) {
+  constexpr int DB = 4;  // diagonals per load batch (x2 rows x (value + x) = 16 128-bit loads in flight)
+  if (HALO) halo_wait_cta(a.s.wait);
+  const double hs = HALO ? halo_scale(a.s.wait) : 1.0;
+  const int n = (int)a.s.n_rows;
+  const int npair = (n + 1) >> 1;
+  const int stride = gridDim.x * blockDim.x;
+  double d_xy = 0.0, d_yy = 0.0;
+  for (int pr = blockIdx.x * blockDim.x + threadIdx.x; pr < npair; pr += stride) {
+    const int row = pr << 1;
+    const bool two = row + 1 < n;
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;  // (a*: row, b*: row+1) x two accumulators
+    const double *vp = a.dia_val + row;
+    for (int d0 = 0; d0 < a.n_diag; d0 += DB) {
+      double2 v[DB], xv[DB];
+#pragma unroll
+      for (int k = 0; k < DB; ++k) {
+        const bool ok = d0 + k < a.n_diag;
+        // ld is a multiple of 32 and row is even: the pair of values is 16-byte aligned; the slot
+        // of row+1 beyond n is zero padding inside the leading dimension
+        v[k] = ok ? ld_stream2(reinterpret_cast<const double2 *>(vp + (int64_t)(d0 + k) * a.ld)) : make_double2(0.0, 0.0);
+        xv[k] = ok ? dia_x2<HALO>(a, row + a.off[d0 + k], n, hs) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int k = 0; k < DB; k += 2) {
+        a0 = fma(v[k].x, xv[k].x, a0);
+        b0 = fma(v[k].y, xv[k].y, b0);
+        a1 = fma(v[k + 1].x, xv[k + 1].x, a1);
+        b1 = fma(v[k + 1].y, xv[k + 1].y, b1);
+      }
+    }
+    spmv_finish_row<double, EPI, DOTS>(a.s, row, a0 + a1, d_xy, d_yy);
+    if (two) spmv_finish_row<double, EPI, DOTS>(a.s, row + 1, b0 + b1, d_xy, d_yy);
+  }
+  spmv_reduce<double, DOTS>(a.s, d_xy, d_yy);
+}
+
+// ------------------------------------------------------------------------------------------
 // DIA construction from CSR (one-time).  col_global[k] - (row0 + row) must be one of the n_diag
 // offsets (sorted ascending, in shared memory); anything else raises *bad and the caller falls
 // back to SELL.  dia_val must be zero-filled beforehand.
