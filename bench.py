@@ -286,13 +286,17 @@ def run_ours(args, w):
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    marks = [e0]
     for _ in range(args.steps):
         flush.add_(1.0)
         ev, Y, st = one_run(op, guess_dev)
+        marks.append(torch.cuda.Event(enable_timing=True))
+        marks[-1].record()
     e1.record()
     barrier()
     clk = clocks.stop()
     ms = e0.elapsed_time(e1)
+    step_ms = [round(marks[i].elapsed_time(marks[i + 1]), 1) for i in range(args.steps)]
     tt = torch.tensor([ms], dtype=torch.float64, device=rt.device)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -396,7 +400,7 @@ def run_ours(args, w):
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "result": {"converged": converged, "eigenvalues": ev_out, "cumIter": int(st["cumIter"]),
                        "matvecs_per_step": int(matvecs), "true_residual": true_res,
-                       "profiled_step_s": t_prof, "arnoldi_step_kernel_phases": orth_trace,
+                       "profiled_step_s": t_prof, "each_step_ms_rank0": step_ms, "arnoldi_step_kernel_phases": orth_trace,
                        "solves_total": int(rt.stats["solves"]), "solves_switched_to_safe_reorth": int(rt.stats.get("safe_solves", 0)),
                        "max_orthogonality_loss_seen": float(rt.stats.get("orth_loss", 0.0))},
         }

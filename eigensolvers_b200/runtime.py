@@ -41,6 +41,7 @@ class Runtime:
         self._op_cache = {}
         self._tmp = {}
         self._peer_allocs = []
+        self._peer_graveyard = []
         self.stats = {"solves": 0, "matvecs": 0, "syncs": 0, "outer": 0}
 
     # -- singletons ---------------------------------------------------------------------------
@@ -58,6 +59,14 @@ class Runtime:
             inst._workspaces.clear()
             for own, _ in list(inst._peer_allocs):
                 inst.peer_release(own)
+            try:
+                import torch.distributed as dist
+                if inst.world > 1 and dist.is_initialized():
+                    inst.torch.cuda.synchronize(inst.device)
+                    dist.barrier()
+            except Exception:
+                pass
+            inst._drain_graveyard()
             inst.lib.cv_ctx_destroy(inst.ctx)
         cls._instance = None
 
@@ -139,6 +148,7 @@ class Runtime:
         rc = self.lib.cv_peer_alloc(self.ctx, int(nbytes), C.byref(own), handle)
         box = [None] * self.world
         dist.all_gather_object(box, (bytes(handle) if rc == 0 else None, info))
+        self._drain_graveyard()   # every rank is here: nobody touches the retired buffers any more
         infos = [b[1] for b in box]
         ptrs, opened, ok = [None] * self.world, [], all(b[0] is not None for b in box)
         if ok:
@@ -164,18 +174,27 @@ class Runtime:
         return ptrs, infos
 
     def peer_release(self, own_ptr):
-        """Unmap / free one peer_shared_alloc (identified by this rank's own pointer)."""
+        """Retire one peer_shared_alloc (identified by this rank's own pointer).  A peer's last
+        Arnoldi step may still be storing halo rows into this buffer (the push of a vector nobody
+        will multiply any more), so the memory is only parked here; it is unmapped and freed at the
+        next collective allocation, when every rank's host has provably passed its final
+        synchronisation (`_drain_graveyard`)."""
         for i, (own, opened) in enumerate(self._peer_allocs):
             if own == own_ptr:
-                self.torch.cuda.synchronize(self.device)
-                for q in opened:
-                    self.lib.cv_peer_close(self.ctx, C.c_void_p(q))
-                self.lib.cv_peer_free(self.ctx, C.c_void_p(own))
-                del self._peer_allocs[i]
+                self._peer_graveyard.append(self._peer_allocs.pop(i))
                 return
 
+    def _drain_graveyard(self):
+        if not self._peer_graveyard:
+            return
+        self.torch.cuda.synchronize(self.device)
+        for own, opened in self._peer_graveyard:
+            for q in opened:
+                self.lib.cv_peer_close(self.ctx, C.c_void_p(q))
+            self.lib.cv_peer_free(self.ctx, C.c_void_p(own))
+        self._peer_graveyard = []
+
     def _attach_peer_windows(self):
-        self._peer_allocs = []
         if os.environ.get("EIGB200_TRANSPORT", "peer").lower() != "peer" or self.world > 8:
             return
         ptrs, _ = self.peer_shared_alloc(self.lib.cv_peer_window_bytes())

@@ -54,6 +54,12 @@ def main():
             check(f"{name} {fmt} format", op.format == fmt)
             hx = X.applyOp(op).array
             check(f"{name} {fmt} spmv", np.allclose(hx, H @ x, rtol=1e-12, atol=1e-12))
+            # fused Arnoldi step with this format's halo push (gather lists for csr/sell, ranges for dia)
+            sg = 0.9 if name == "lap" else 4.6
+            oo = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 3000, "linear_tol": 1e-9, "linear_atol": 0.0}}
+            wf = CudaVector.solve(op, CudaVector(x, dict(oo)), sg).array
+            resf = np.linalg.norm(x - (sg * wf - H @ wf)) / np.linalg.norm(x)
+            check(f"{name} {fmt} gcrotmk residual {resf:.2e}", resf < 1e-8)
         # row-block construction equals slicing the full matrix
         r0, r1 = rt.local_range(n)
         op2 = DeviceOperator.from_local_rows(H[r0:r1], n)
