@@ -332,7 +332,8 @@ def run_ours(args, w):
     spmv_ms = ms4[0] / max(cnt4[0], 1)
     alg_bytes = op.algorithmic_bytes(False)
     achieved = alg_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": f"k_spmv_{op.format}<double> (fused shift + dots)", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": ("k_spmv_dia2<double> (two rows per thread, fused shift + dots)" if op.format == "dia"
+                           else f"k_spmv_{op.format}<double> (fused shift + dots)"), "achieved": achieved,
                 "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
                 "traffic": TRAFFIC_NCU.get((args.workload, op.format, world)),
