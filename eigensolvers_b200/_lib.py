@@ -23,7 +23,7 @@ class CudaVecError(RuntimeError):
 class SolveStats(C.Structure):
     _fields_ = [("info", C.c_int), ("n_matvec", C.c_int), ("n_outer", C.c_int), ("n_sync", C.c_int),
                 ("n_reorth", C.c_int), ("resid", C.c_double), ("b_norm", C.c_double),
-                ("orth_loss", C.c_double), ("n_safe", C.c_int), ("reserved", C.c_int)]
+                ("orth_loss", C.c_double), ("n_safe", C.c_int), ("n_recycled", C.c_int)]
 
 
 _vp, _i, _i64, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_size_t
@@ -40,6 +40,7 @@ SIGNATURES = {
     "cv_ctx_launch_count": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "cv_ctx_sm_count": (_i, [_vp, _pi]),
     "cv_ctx_set_reorth_eta": (_i, [_vp, _d]),
+    "cv_ctx_set_recycle": (_i, [_vp, _i]),
     "cv_ctx_trace_read": (_i, [_vp, _pd, _i]),
     "cv_ctx_profile": (_i, [_vp, _i]),
     "cv_ctx_profile_read": (_i, [_vp, _pd, C.POINTER(C.c_uint64)]),

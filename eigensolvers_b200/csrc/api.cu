@@ -84,6 +84,13 @@ extern "C" int cv_ctx_launch_count(cv_ctx *ctx, uint64_t *count) {
   return CV_OK;
 }
 
+extern "C" int cv_ctx_set_recycle(cv_ctx *ctx, int enable) {
+  CV_REQUIRE(ctx, "cv_ctx_set_recycle: null context");
+  if (ctx->recycle.enabled != (enable != 0)) ctx->recycle.valid = false;
+  ctx->recycle.enabled = enable != 0;
+  return CV_OK;
+}
+
 extern "C" int cv_ctx_set_reorth_eta(cv_ctx *ctx, double eta) {
   CV_REQUIRE(ctx && eta >= 0.0, "cv_ctx_set_reorth_eta: bad argument");
   ctx->reorth_eta = eta;

@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <math.h>
+#include <vector>
 #include "../../include/cudavec.h"
 
 // ------------------------------------------------------------------------------------------
@@ -80,6 +81,19 @@ struct cv_prof_state {
   uint64_t count[CV_PROF_CLASSES] = {0, 0, 0, 0};
 };
 
+// GCROT recycling across solves (solvers.cu): which (c,u) ring slots of the solver workspace hold
+// vectors that are valid for which operator / shift
+struct cv_op;
+struct cv_recycle_state {
+  bool enabled = false, valid = false;
+  const cv_op *op = nullptr;
+  int cplx = 0, mode = 0, m = 0, k = 0;
+  double sre = 0.0, sim = 0.0;
+  int64_t n = 0;
+  const void *work = nullptr;
+  std::vector<int> cu_slots, free_slots;
+};
+
 struct cv_ctx {
   int device;
   int sms;
@@ -103,6 +117,7 @@ struct cv_ctx {
   // the vector whose halo phase C of the fused step has already pushed (next SpMV skips its push)
   const void *prepushed_x;
   const void *prepushed_op;
+  cv_recycle_state recycle;
   bool push_early;  // fused step pushes unnormalised halo rows from phase B (EIGB200_PUSH_EARLY=0: off)
 };
 

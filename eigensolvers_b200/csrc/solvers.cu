@@ -120,7 +120,18 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
   auto Us = [&](int i) { return ws.vec(1 + nV + (k + 1) + i); };
   std::vector<int> cu_slots;  // ring order: oldest first (scipy `CU` list)
   std::vector<int> free_slots;
-  for (int i = k; i >= 0; --i) free_slots.push_back(i);
+  // Recycling (scipy's CU= argument, _gcrotmk.py:227-236, opt-in through cv_ctx_set_recycle): the
+  // (c,u) pairs a previous solve left in this workspace are valid for the same operator and shift
+  cv_recycle_state &rs = ctx->recycle;
+  const bool reuse = rs.enabled && rs.valid && rs.op == op && rs.cplx == cplx_ && rs.mode == mode && rs.sre == sre &&
+                     rs.sim == sim && rs.n == n && rs.work == (const void *)ws.base && rs.m == m && rs.k == k;
+  rs.valid = false;
+  if (reuse) {
+    cu_slots = rs.cu_slots;
+    free_slots = rs.free_slots;
+  } else {
+    for (int i = k; i >= 0; --i) free_slots.push_back(i);
+  }
 
   // x = x0 or 0;  r = b - A x
   if (x0) {
@@ -149,11 +160,108 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
     return CV_OK;
   }
 
+  std::vector<const void *> basis(CV_MAX_PTRS);
+  if (!cu_slots.empty()) {
+    // (1) Re-orthonormalise the recycled C (scipy does a pivoted QR here, _gcrotmk.py:317-371): the
+    // vectors were built with the optimistic single-pass Gram-Schmidt, and small losses would add up
+    // from solve to solve.  Cholesky QR is enough because C is orthonormal to ~1e-8 at worst:
+    // G = C^H C = R^H R,  C <- C R^-1,  U <- U R^-1 (keeps C = A U).  The V slots are free scratch.
+    int nc0 = (int)cu_slots.size();
+    for (int c = 0; c < nc0; ++c) basis[c] = Cs(cu_slots[c]);
+    std::vector<zc> G((size_t)nc0 * nc0);
+    for (int k0 = 0; k0 < nc0; k0 += 4) {
+      const int bb = std::min(4, nc0 - k0);
+      const void *wp4[4];
+      for (int q = 0; q < bb; ++q) wp4[q] = basis[k0 + q];
+      CV_TRY(cv_tsdot_dev(ctx, n, cplx_, 1, nc0, basis.data(), bb, wp4, CV_S_TS, st));
+      CV_TRY(cv_fetch_scalars(ctx, CV_S_TS, nc0 * bb * NR, st));
+      stats->n_sync++;
+      for (int i = 0; i < nc0; ++i)
+        for (int q = 0; q < bb; ++q)
+          G[(size_t)i * nc0 + k0 + q] = cplx_ ? zc(mb[CV_S_TS + (i * bb + q) * 2], mb[CV_S_TS + (i * bb + q) * 2 + 1])
+                                              : zc(mb[CV_S_TS + i * bb + q], 0.0);
+    }
+    double dev = 0.0;
+    for (int i = 0; i < nc0; ++i)
+      for (int q = 0; q < nc0; ++q) dev = std::max(dev, std::abs(G[(size_t)i * nc0 + q] - zc(i == q ? 1.0 : 0.0)));
+    bool ring_ok = std::isfinite(dev);
+    if (ring_ok && dev > 1e-12) {
+      // upper-triangular R with G = R^H R (Cholesky), then M = R^-1
+      std::vector<zc> Rm((size_t)nc0 * nc0, zc(0)), Mi((size_t)nc0 * nc0, zc(0));
+      for (int jc = 0; jc < nc0 && ring_ok; ++jc) {
+        for (int i = 0; i <= jc; ++i) {
+          zc sacc = G[(size_t)i * nc0 + jc];
+          for (int t = 0; t < i; ++t) sacc -= std::conj(Rm[(size_t)t * nc0 + i]) * Rm[(size_t)t * nc0 + jc];
+          if (i < jc) {
+            Rm[(size_t)i * nc0 + jc] = sacc / Rm[(size_t)i * nc0 + i];
+          } else {
+            if (!(sacc.real() > 0.25)) ring_ok = false;  // far from orthonormal: do not trust the ring
+            Rm[(size_t)i * nc0 + i] = std::sqrt(sacc.real());
+          }
+        }
+      }
+      if (ring_ok) {
+        for (int jc = 0; jc < nc0; ++jc) {  // back-substitution, column by column: R M = I
+          Mi[(size_t)jc * nc0 + jc] = 1.0 / Rm[(size_t)jc * nc0 + jc];
+          for (int i = jc - 1; i >= 0; --i) {
+            zc sacc = 0;
+            for (int t = i + 1; t <= jc; ++t) sacc += Rm[(size_t)i * nc0 + t] * Mi[(size_t)t * nc0 + jc];
+            Mi[(size_t)i * nc0 + jc] = -sacc / Rm[(size_t)i * nc0 + i];
+          }
+        }
+        const int cs2 = cplx_ ? 2 : 1;
+        std::vector<double> cf((size_t)nc0 * nc0 * cs2);
+        for (int i = 0; i < nc0; ++i)
+          for (int q = 0; q < nc0; ++q) {
+            cf[((size_t)i * nc0 + q) * cs2] = Mi[(size_t)i * nc0 + q].real();
+            if (cplx_) cf[((size_t)i * nc0 + q) * cs2 + 1] = Mi[(size_t)i * nc0 + q].imag();
+          }
+        const int chunk = cplx_ ? 4 : 8;
+        for (int which = 0; which < 2; ++which) {
+          std::vector<const void *> src(nc0);
+          std::vector<void *> dst(nc0);
+          for (int c = 0; c < nc0; ++c) {
+            src[c] = which == 0 ? Cs(cu_slots[c]) : Us(cu_slots[c]);
+            dst[c] = V(1 + c);
+          }
+          for (int c0 = 0; c0 < nc0; c0 += chunk) {
+            const int ncol = std::min(chunk, nc0 - c0);
+            CV_TRY(cv_lincomb_launch(ctx, n, cplx_, cplx_, nc0, src.data(), ncol, cf.data(), nc0, c0, dst.data() + c0, -1, st));
+          }
+          for (int c = 0; c < nc0; ++c) CV_TRY(cv_copy(ctx, n, cplx_, dst[c], const_cast<void *>(src[c]), (void *)st));
+        }
+      }
+    }
+    if (!ring_ok) {  // start from an empty ring
+      cu_slots.clear();
+      free_slots.clear();
+      for (int i = k; i >= 0; --i) free_slots.push_back(i);
+      nc0 = 0;
+    }
+    stats->orth_loss = 0.0;
+    if (nc0 > 0) {
+      // (2) x += U C^H r,  r -= C C^H r  (_gcrotmk.py:373-388)
+      for (int c = 0; c < nc0; ++c) basis[c] = Cs(cu_slots[c]);
+      const void *rp[1] = {r};
+      CV_TRY(cv_tsdot_dev(ctx, n, cplx_, 1, nc0, basis.data(), 1, rp, S_H1, st));
+      CV_TRY(cv_tsupdate_dev(ctx, n, cplx_, nc0, basis.data(), S_H1, r, S_BETA, st));
+      CV_TRY(cv_fetch_scalars(ctx, S_H1, nc0 * NR, st));
+      stats->n_sync++;
+      for (int i = 0; i < nc0 * NR; ++i) mb[S_H2 + i] = -mb[S_H1 + i];
+      CV_CUDA(cudaMemcpyAsync(ctx->scalars + S_H2, mb + S_H2, sizeof(double) * nc0 * NR, cudaMemcpyHostToDevice, st));
+      for (int c = 0; c < nc0; ++c) basis[c] = Us(cu_slots[c]);
+      CV_TRY(cv_tsupdate_dev(ctx, n, cplx_, nc0, basis.data(), S_H2, x, -1, st));
+      CV_TRY(cv_fetch_scalars(ctx, S_BETA, 1, st));
+      stats->n_sync++;
+      beta = sqrt(mb[S_BETA]);
+      stats->n_recycled = nc0;
+    }
+  }
+
   const int mlmax = m + k;
   std::vector<zc> Q((size_t)(mlmax + 2) * (mlmax + 2)), R((size_t)(mlmax + 2) * (mlmax + 1));
   std::vector<zc> B((size_t)(k + 1) * (mlmax + 1)), y(mlmax + 2), hy(mlmax + 2), by(k + 1), hcur(mlmax + 2);
   const int ldq = mlmax + 2, ldr = mlmax + 1, ldb = mlmax + 1;
-  std::vector<const void *> basis(CV_MAX_PTRS);
   std::vector<double> coef(2 * 2 * CV_MAX_PTRS);
 
   int j_outer = 0;
@@ -390,6 +498,20 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
   }
   stats->n_outer = converged ? j_outer : std::min(j_outer + 1, maxiter);
   stats->info = converged ? 0 : (j_outer >= maxiter ? maxiter : j_outer + 1);
+  if (rs.enabled) {  // leave the ring for the next solve with this operator and shift
+    rs.valid = true;
+    rs.op = op;
+    rs.cplx = cplx_;
+    rs.mode = mode;
+    rs.sre = sre;
+    rs.sim = sim;
+    rs.n = n;
+    rs.work = ws.base;
+    rs.m = m;
+    rs.k = k;
+    rs.cu_slots = cu_slots;
+    rs.free_slots = free_slots;
+  }
   return CV_OK;
 }
 
@@ -583,6 +705,7 @@ extern "C" int cv_solve(cv_ctx *ctx, cv_op *op, int cplx_, int solver, int rever
       return CV_ERR_UNSUPPORTED;
     }
     CV_REQUIRE(work_bytes >= cv_solve_workspace_bytes(op->n_rows, 0, solver, 0, 0), "cv_solve: workspace too small");
+    ctx->recycle.valid = false;  // MINRES overwrites the workspace the ring lives in
     return minres(ctx, op, mode, sigma_re, (const double *)b, (const double *)x0, (double *)x_out, rtol,
                   maxiter, ws, stats, st);
   }

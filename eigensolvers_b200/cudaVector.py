@@ -328,6 +328,9 @@ class CudaVector(AbstractVector):
         work = rt.workspace(wbytes)
         out = rt.empty(nloc, cplx)
         stats = _lib.SolveStats()
+        # opt-in: keep GCROT's recycled subspace between successive solves with the same H and sigma
+        # (SciPy's CU= argument; the reference does not use it, so the default is off)
+        _lib.check(rt.lib.cv_ctx_set_recycle(rt.ctx, int(bool(options.get("recycle", False)))))
         s = complex(sigma)
         _lib.check(rt.lib.cv_solve(rt.ctx, op.handle, int(cplx), solver, int(bool(reverseGF)), s.real, s.imag,
                                    bt.data_ptr(), None if x0t is None else x0t.data_ptr(), out.data_ptr(),

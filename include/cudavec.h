@@ -67,6 +67,10 @@ int cv_ctx_destroy(cv_ctx *ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int cv_ctx_launch_count(cv_ctx *ctx, uint64_t *count);
 int cv_ctx_sm_count(cv_ctx *ctx, int *sms);
+/* GCROT recycling (scipy's CU= argument, _gcrotmk.py:227-236, which the reference leaves unused):
+ * when enabled, the (c,u) pairs a solve leaves in the workspace are reused by the next cv_solve
+ * with the same operator, shift, vector type, workspace and (m,k).  Off by default.            */
+int cv_ctx_set_recycle(cv_ctx *ctx, int enable);
 /* GCROT's Arnoldi step repeats its Gram-Schmidt pass when the first one left less than eta of the
  * vector's norm (Daniel-Gragg-Kaufman-Stewart).  Default 0.1; 0 = never, > 1 = always twice.    */
 int cv_ctx_set_reorth_eta(cv_ctx *ctx, double eta);
@@ -233,7 +237,7 @@ typedef struct cv_solve_stats {
   double b_norm;
   double orth_loss;  /* max | |v_j|^2 - 1 | seen by the Arnoldi health monitor               */
   int n_safe;        /* 1 if the solve switched to the classic re-orthogonalisation threshold */
-  int reserved;
+  int n_recycled;    /* recycled (c,u) pairs this solve started from                          */
 } cv_solve_stats;
 
 size_t cv_solve_workspace_bytes(int64_t n, int cplx, int solver, int m, int k);

@@ -41,7 +41,12 @@ def _givens_insert(Q, R, hcur, j):
     return Q2, R2
 
 
-def gcrotmk(matvec, b, x0=None, rtol=1e-5, atol=0.0, maxiter=1000, m=20, k=None, orth="mgs"):
+def gcrotmk(matvec, b, x0=None, rtol=1e-5, atol=0.0, maxiter=1000, m=20, k=None, orth="mgs", CU=None):
+    """`CU`: list of (c, u) pairs kept from an earlier solve with the SAME operator (recycling,
+    _gcrotmk.py:227-236).  SciPy re-orthogonalises the c's with a pivoted QR on entry
+    (:317-371); the vectors left by a previous call are already orthonormal, so this restatement
+    (and the CUDA library) skips the QR and goes straight to the projection step
+    x += U C^H r, r -= C C^H r (:373-388).  The list is updated in place."""
     b = np.asarray(b)
     dtype = np.result_type(b.dtype, matvec(np.zeros_like(b)).dtype, np.float64)
     b = b.astype(dtype)
@@ -61,7 +66,12 @@ def gcrotmk(matvec, b, x0=None, rtol=1e-5, atol=0.0, maxiter=1000, m=20, k=None,
     if b_norm == 0:
         return b, 0, nmv
     eps = np.finfo(np.float64).eps
-    CU = []
+    if CU is None:
+        CU = []
+    for c, u in CU:                      # _gcrotmk.py:381-388
+        yc = dot(c, r)
+        x = x + u * yc
+        r = r - c * yc
     j_outer = -1
     for j_outer in range(maxiter):
         beta = np.linalg.norm(r)

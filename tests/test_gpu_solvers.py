@@ -184,3 +184,66 @@ def test_fused_arnoldi_step_both_passes(rt, eta, expect_second_pass, n_odd):
     assert np.linalg.norm(x - x_ref) <= 1e-7 * np.linalg.norm(x_ref)
     if eta > 0:
         assert abs(st.n_matvec - 0) > 0
+
+
+def test_gcrotmk_recycling_across_solves(rt):
+    """Opt-in GCROT recycling (options["linearSystemArgs"]["recycle"] = True; SciPy's CU= argument,
+    unused by the reference): a Lanczos-like sequence of solves with one operator and shift needs
+    about as few matvecs as SciPy with CU and fewer than without recycling; every solve still
+    meets its residual tolerance; a different shift starts from an empty ring."""
+    from eigensolvers_b200 import CudaVector, DeviceOperator, hamiltonians as hm
+    H, om = hm.coupled_oscillators((8, 6, 6, 5))
+    lev = hm.oscillator_levels(om, 0.1, 12)
+    sigma = lev[6] + 0.25 * (lev[7] - lev[6])
+    n = H.shape[0]
+    b0 = np.random.default_rng(2).standard_normal(n)
+    b0 /= np.linalg.norm(b0)
+    op = DeviceOperator.from_host(H)
+
+    def sequence(solver):
+        basis, counts = [b0], []
+        for _ in range(5):
+            x, nmv = solver(basis[-1])
+            assert np.linalg.norm(basis[-1] - (sigma * x - H @ x)) <= 1e-6 * (1 + 1e-6)
+            counts.append(nmv)
+            y = x.copy()
+            for q in basis:
+                y -= (y @ q) * q
+            basis.append(y / np.linalg.norm(y))
+        return counts
+
+    def gpu_solver(recycle):
+        o = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 1000, "linear_tol": 1e-6, "linear_atol": 0.0,
+                                  "recycle": recycle}}
+
+        def solve(b):
+            x = CudaVector.solve(op, CudaVector(b, o), sigma).array
+            return x, rt.last_solve.n_matvec
+        return solve
+
+    CU = []
+
+    def scipy_solve(b):
+        cnt = [0]
+
+        def mv(v):
+            cnt[0] += 1
+            return sigma * v - H @ v
+        lin = spla.LinearOperator((n, n), matvec=mv, dtype=float)
+        x, info = spla.gcrotmk(lin, b, rtol=1e-6, atol=0.0, maxiter=1000, CU=CU, discard_C=False)
+        assert info == 0
+        return x, cnt[0]
+
+    plain = sequence(gpu_solver(False))
+    assert rt.last_solve.n_recycled == 0
+    rec = sequence(gpu_solver(True))
+    assert rt.last_solve.n_recycled > 0
+    ref = sequence(scipy_solve)
+    assert rec[0] == plain[0] or abs(rec[0] - plain[0]) <= 2          # first solve: nothing to recycle yet
+    assert sum(rec) < 0.7 * sum(plain), (rec, plain)
+    assert abs(sum(rec) - sum(ref)) <= 0.2 * sum(ref), (rec, ref)
+    # another shift must not see the old ring
+    o = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 1000, "linear_tol": 1e-6, "linear_atol": 0.0, "recycle": True}}
+    x = CudaVector.solve(op, CudaVector(b0, o), sigma + 0.01).array
+    assert rt.last_solve.n_recycled == 0
+    assert np.linalg.norm(b0 - ((sigma + 0.01) * x - H @ x)) <= 1e-6 * (1 + 1e-6)
