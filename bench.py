@@ -168,12 +168,20 @@ def cpu_sample(w, n_matvecs=40):
         count[0] += 1
         return sigma * x - H @ x
     lin = spla.LinearOperator((n, n), matvec=shifted, dtype=np.float64)
+    try:  # all host threads for the BLAS-1 part, also under torchrun (which exports OMP_NUM_THREADS=1)
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        limiter = None
     t0 = time.perf_counter()
     try:
         spla.gcrotmk(lin, b, None, rtol=w["tol"], atol=0.0, maxiter=1)
     except _SampleDone:
         pass
-    return time.perf_counter() - t0, count[0]
+    dt = time.perf_counter() - t0
+    if limiter is not None:
+        limiter.restore_original_limits()
+    return dt, count[0]
 
 
 def run_reference_arm(args, w):
@@ -191,11 +199,7 @@ def run_reference_arm(args, w):
     per_mv = float(np.mean(times)) / mv
     total = MATVECS_TO_ECONV[args.workload]
     value = per_mv * total / w["nBlock"]
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-    except Exception:
-        threads = 1
+    threads = os.cpu_count() or 1
     sample = (f"{mv} matvecs = the first {mv} Arnoldi steps of one GCROT(20,20) outer cycle of the first shifted solve "
               f"at full N (scipy csr_matvec is serial; BLAS-1 on {threads} thread(s)), {np.mean(times):.2f} s; extrapolated to the "
               f"{total} matvecs one full run needs (GPU-measured count); host has {os.cpu_count()} cores")
@@ -411,11 +415,7 @@ def run_ours(args, w):
         t, mv = cpu_sample(w)
         per_mv = t / mv
         cpu_value = per_mv * matvecs / w["nBlock"]
-        try:
-            from threadpoolctl import threadpool_info
-            threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-        except Exception:
-            threads = 1
+        threads = os.cpu_count() or 1
         cpu = {"value": cpu_value, "unit": "s", "cores": threads, "kind": "port",
                "sample": f"{mv} matvecs = one GCROT(20,20) outer cycle of the first shifted solve at full N "
                          f"(scipy csr_matvec is serial; BLAS-1 on {threads} thread(s)), {t:.2f} s; extrapolated to the "
