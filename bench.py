@@ -150,7 +150,23 @@ class _SampleDone(Exception):
     pass
 
 
-def cpu_sample(w, n_matvecs=40):
+_CPU_THREADS = [None]
+
+
+def cpu_threads(w):
+    """BLAS thread count for the CPU legs: all host cores or one, whichever runs a short sample
+    faster (threaded BLAS-1 on vectors this long can LOSE to one thread on some hosts)."""
+    if _CPU_THREADS[0] is None:
+        best = None
+        for t in sorted({os.cpu_count() or 1, 1}, reverse=True):
+            dt, _ = cpu_sample(w, 6, threads=t)
+            if best is None or dt < best[0]:
+                best = (dt, t)
+        _CPU_THREADS[0] = best[1]
+    return _CPU_THREADS[0]
+
+
+def cpu_sample(w, n_matvecs=40, threads=None):
     """Bounded sample of the reference's CPU path on the same workload: the first `n_matvecs`
     Arnoldi steps (scipy csr_matvec + SciPy's BLAS-1 orthogonalisation) of the first shifted solve
     at full N, through the operator NumpyVector.solve builds (numpyVector.py:152).  40 = one full
@@ -170,7 +186,7 @@ def cpu_sample(w, n_matvecs=40):
     lin = spla.LinearOperator((n, n), matvec=shifted, dtype=np.float64)
     try:  # all host threads for the BLAS-1 part, also under torchrun (which exports OMP_NUM_THREADS=1)
         from threadpoolctl import threadpool_limits
-        limiter = threadpool_limits(limits=os.cpu_count())
+        limiter = threadpool_limits(limits=threads if threads is not None else cpu_threads(w))
     except Exception:
         limiter = None
     t0 = time.perf_counter()
@@ -199,7 +215,7 @@ def run_reference_arm(args, w):
     per_mv = float(np.mean(times)) / mv
     total = MATVECS_TO_ECONV[args.workload]
     value = per_mv * total / w["nBlock"]
-    threads = os.cpu_count() or 1
+    threads = cpu_threads(w)
     sample = (f"{mv} matvecs = the first {mv} Arnoldi steps of one GCROT(20,20) outer cycle of the first shifted solve "
               f"at full N (scipy csr_matvec is serial; BLAS-1 on {threads} thread(s)), {np.mean(times):.2f} s; extrapolated to the "
               f"{total} matvecs one full run needs (GPU-measured count); host has {os.cpu_count()} cores")
@@ -415,7 +431,7 @@ def run_ours(args, w):
         t, mv = cpu_sample(w)
         per_mv = t / mv
         cpu_value = per_mv * matvecs / w["nBlock"]
-        threads = os.cpu_count() or 1
+        threads = cpu_threads(w)
         cpu = {"value": cpu_value, "unit": "s", "cores": threads, "kind": "port",
                "sample": f"{mv} matvecs = one GCROT(20,20) outer cycle of the first shifted solve at full N "
                          f"(scipy csr_matvec is serial; BLAS-1 on {threads} thread(s)), {t:.2f} s; extrapolated to the "
