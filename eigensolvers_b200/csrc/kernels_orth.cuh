@@ -174,10 +174,10 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
     const int s_h_out = pass == 1 ? a.s_h1 : a.s_h2;
     // ---------------- phase A: this CTA's slab of up to MI basis vectors against w ----------
     if (c < gx * ny) {
-      // slabs of MI vectors, the last one partial (m = 33 -> 16+16+1).  Splitting evenly (11+11+11)
-      // was measured SLOWER (dots 90 -> 115 us at N = 2e6): the phase is bandwidth-bound, so idle
-      // CTAs of a short slab cost nothing, while batches of 8+3 loads per thread instead of 8+8
-      // lose memory-level parallelism
+      // slabs of MI vectors, the last one partial (m = 28 -> 16+12).  Splitting evenly was measured
+      // SLOWER at N = 2e6 (dots 89 us -> 115 us with batches of 8+3 loads per thread, 103 us with
+      // even slabs AND even batches 7+7): the phase is limited by loads in flight per thread, so
+      // full batches of 8 matter more than CTAs of a short slab idling at the barrier
       const int by = c / gx, bx = c % gx;
       const int i0 = by * MI;
       const int mi = min(MI, m - i0);
