@@ -42,7 +42,7 @@ WORKLOADS = {
 # Matvec count of one full run of each workload on the GPU path (measured);
 # the CPU arm times a bounded sample and extrapolates with it.
 # DRAM bytes per launch of the dominant kernel from the ncu --set full capture (profiles/README.md)
-TRAFFIC_NCU = {("c3", "dia", 1): 4160061000 + 136101632}
+TRAFFIC_NCU = {("c3", "dia", 1): 4160035000 + 133009920}
 MATVECS_TO_ECONV = {"c3": 4250, "c3mid": 6772, "c3small": 3738, "c2": 9000, "c2small": 3000}
 
 
@@ -357,7 +357,7 @@ def run_ours(args, w):
                 "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
                 "traffic": TRAFFIC_NCU.get((args.workload, op.format, world)),
-                "traffic_source": "profiles/r1_ncu_c3_full_kernels.csv (dram__bytes_read+write per launch)",
+                "traffic_source": "profiles/r1_ncu_c3_final_kernels.csv (dram__bytes_read+write per launch of k_spmv_dia2)",
                 "dram_GBs": (TRAFFIC_NCU[(args.workload, op.format, world)] / (spmv_ms * 1e-3) / 1e9
                              if (args.workload, op.format, world) in TRAFFIC_NCU and spmv_ms > 0 else None),
                 "note": "achieved = SURVEY 8(d) CSR-algorithmic bytes (12 nnz + 20 N) / time; the DIA layout moves fewer "
