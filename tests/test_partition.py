@@ -174,3 +174,41 @@ def test_feast_nodes_distributed_over_two_gloo_ranks():
         p.join(timeout=60)
     assert all(r[1] for r in results), results
     assert results[0][2] == results[1][2]        # both ranks hold identical Ritz values
+
+
+def test_dia_offset_table_host_logic():
+    """DeviceOperator._dia_table (host side of the DIA format decision): the offsets col-row of the
+    banded generators, rejection of unstructured / too-padded matrices, row-block invariance."""
+    import types
+    from eigensolvers_b200 import hamiltonians as hm
+    from eigensolvers_b200.operator import DeviceOperator
+
+    def table(A, row0=0, rows=None, force=False):
+        A = A.tocsr()
+        A.sort_indices()
+        if rows is not None:
+            A = A[rows[0]:rows[1]]
+            row0 = rows[0]
+        op = DeviceOperator.__new__(DeviceOperator)
+        op.rt = types.SimpleNamespace(world=1)
+        op.nnz = int(A.nnz)
+        return op._dia_table(A.indptr.astype(np.int64), A.indices.astype(np.int32), row0, force=force)
+
+    lap = hm.laplacian3d(12)
+    assert table(lap) == [-144, -12, -1, 0, 1, 12, 144]
+    H = hm.coupled_oscillators((12, 10, 10))[0]
+    offs = table(H)
+    strides = (100, 10, 1)
+    expect = {0} | {a * strides[i] + b * strides[i + 1] for i in range(2) for a in (-1, 1) for b in (-1, 1)}
+    assert offs == sorted(expect)
+    # a row block of the same matrix sees (a subset of) the same offsets, relative to GLOBAL rows
+    blk = table(H, rows=(300, 900), force=True)
+    assert set(blk) <= set(offs) and 0 in blk
+    # unstructured sparsity: more than 64 distinct offsets -> no DIA
+    rng = np.random.default_rng(0)
+    R = sp.random(3000, 3000, density=0.004, random_state=rng, format="csr")
+    assert table(R + R.T) is None
+    # heavy basis-edge truncation: padding would cost more than CSR's index stream
+    assert table(hm.coupled_oscillators((6, 5, 4, 4, 3))[0]) is None
+    # tiny matrices are never converted
+    assert table(hm.laplacian3d(5)) is None
