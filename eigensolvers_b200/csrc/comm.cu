@@ -178,19 +178,18 @@ int cv_halo_exchange(cv_ctx *ctx, cv_op *op, bool cplx_, const void *x, cudaStre
 // ------------------------------------------------------------------------------------------
 // DIA halo: the band below / above the owned rows arrives as contiguous ranges (no pack kernel)
 // ------------------------------------------------------------------------------------------
-extern "C" int cv_op_set_dia_halo(cv_ctx *ctx, cv_op *op, const int64_t *offsets, void *halo_lo_dev,
-                                  void *halo_hi_dev) {
-  CV_REQUIRE(ctx && op && offsets, "cv_op_set_dia_halo: null argument");
-  CV_REQUIRE(op->dia_val, "cv_op_set_dia_halo: operator has no DIA storage");
-  CV_REQUIRE((op->lo_len == 0 || halo_lo_dev) && (op->hi_len == 0 || halo_hi_dev), "cv_op_set_dia_halo: null halo buffer");
-  const int P = ctx->world, me = ctx->rank;
+// Pure host integer routine: the exchange plan of the DIA band halo for `rank`.  A rank needs the
+// rows [r0 - lo_len, r0) (lower band) and [r1, r1 + hi_len) (upper band), clipped to [0, N); every
+// contiguous piece owned by one peer is one range.  send: what this rank stores into its peers
+// ({peer, first local row, count, band of the PEER it lands in (0 lower / 1 upper), slot inside that
+// band buffer}); recv: what arrives here ({peer, band, first slot, count}).
+static void dia_plan(const int64_t *offsets, int P, int me, int64_t lo_len, int64_t hi_len,
+                     std::vector<cv_op::Range> &send, std::vector<cv_op::Range> &recv_lo,
+                     std::vector<cv_op::Range> &recv_hi) {
   const int64_t N = offsets[P], r0 = offsets[me], r1 = offsets[me + 1];
-  op->halo_lo = halo_lo_dev;
-  op->halo_hi = halo_hi_dev;
-  op->n_global = N;
-  op->dia_send.clear();
-  op->dia_recv_lo.clear();
-  op->dia_recv_hi.clear();
+  send.clear();
+  recv_lo.clear();
+  recv_hi.clear();
   auto overlap = [](int64_t a0, int64_t a1, int64_t b0, int64_t b1, int64_t &s, int64_t &c) {
     s = a0 > b0 ? a0 : b0;
     int64_t e = a1 < b1 ? a1 : b1;
@@ -201,16 +200,56 @@ extern "C" int cv_op_set_dia_halo(cv_ctx *ctx, cv_op *op, const int64_t *offsets
     const int64_t p0 = offsets[p], p1 = offsets[p + 1];
     int64_t s, c;
     // what p needs from my rows: first the part of p's lower band, then of its upper band
-    overlap(p0 - op->lo_len < 0 ? 0 : p0 - op->lo_len, p0, r0, r1, s, c);
-    if (c > 0) op->dia_send.push_back({p, s - r0, c, 0, s - (p0 - op->lo_len)});
-    overlap(p1, p1 + op->hi_len > N ? N : p1 + op->hi_len, r0, r1, s, c);
-    if (c > 0) op->dia_send.push_back({p, s - r0, c, 1, s - p1});
+    overlap(p0 - lo_len < 0 ? 0 : p0 - lo_len, p0, r0, r1, s, c);
+    if (c > 0) send.push_back({p, s - r0, c, 0, s - (p0 - lo_len)});
+    overlap(p1, p1 + hi_len > N ? N : p1 + hi_len, r0, r1, s, c);
+    if (c > 0) send.push_back({p, s - r0, c, 1, s - p1});
     // what I need from p's rows
-    overlap(r0 - op->lo_len < 0 ? 0 : r0 - op->lo_len, r0, p0, p1, s, c);
-    if (c > 0) op->dia_recv_lo.push_back({p, s - (r0 - op->lo_len), c, 0, 0});
-    overlap(r1, r1 + op->hi_len > N ? N : r1 + op->hi_len, p0, p1, s, c);
-    if (c > 0) op->dia_recv_hi.push_back({p, s - r1, c, 1, 0});
+    overlap(r0 - lo_len < 0 ? 0 : r0 - lo_len, r0, p0, p1, s, c);
+    if (c > 0) recv_lo.push_back({p, s - (r0 - lo_len), c, 0, 0});
+    overlap(r1, r1 + hi_len > N ? N : r1 + hi_len, p0, p1, s, c);
+    if (c > 0) recv_hi.push_back({p, s - r1, c, 1, 0});
   }
+}
+
+extern "C" int cv_dia_halo_plan(const int64_t *offsets, int world, int rank, int64_t lo_len, int64_t hi_len,
+                                int cap, int *n_send, int64_t *send5, int *n_recv, int64_t *recv4) {
+  CV_REQUIRE(offsets && n_send && send5 && n_recv && recv4, "cv_dia_halo_plan: null argument");
+  CV_REQUIRE(world >= 1 && rank >= 0 && rank < world && lo_len >= 0 && hi_len >= 0 && cap >= 0,
+             "cv_dia_halo_plan: bad argument");
+  std::vector<cv_op::Range> send, rlo, rhi;
+  dia_plan(offsets, world, rank, lo_len, hi_len, send, rlo, rhi);
+  CV_REQUIRE((int)send.size() <= cap && (int)(rlo.size() + rhi.size()) <= cap, "cv_dia_halo_plan: capacity %d too small", cap);
+  *n_send = (int)send.size();
+  for (size_t i = 0; i < send.size(); ++i) {
+    send5[5 * i + 0] = send[i].peer;
+    send5[5 * i + 1] = send[i].start;
+    send5[5 * i + 2] = send[i].count;
+    send5[5 * i + 3] = send[i].band;
+    send5[5 * i + 4] = send[i].dst_off;
+  }
+  int k = 0;
+  for (const auto *list : {&rlo, &rhi})
+    for (const auto &r : *list) {
+      recv4[4 * k + 0] = r.peer;
+      recv4[4 * k + 1] = r.band;
+      recv4[4 * k + 2] = r.start;
+      recv4[4 * k + 3] = r.count;
+      ++k;
+    }
+  *n_recv = k;
+  return CV_OK;
+}
+
+extern "C" int cv_op_set_dia_halo(cv_ctx *ctx, cv_op *op, const int64_t *offsets, void *halo_lo_dev,
+                                  void *halo_hi_dev) {
+  CV_REQUIRE(ctx && op && offsets, "cv_op_set_dia_halo: null argument");
+  CV_REQUIRE(op->dia_val, "cv_op_set_dia_halo: operator has no DIA storage");
+  CV_REQUIRE((op->lo_len == 0 || halo_lo_dev) && (op->hi_len == 0 || halo_hi_dev), "cv_op_set_dia_halo: null halo buffer");
+  op->halo_lo = halo_lo_dev;
+  op->halo_hi = halo_hi_dev;
+  op->n_global = offsets[ctx->world];
+  dia_plan(offsets, ctx->world, ctx->rank, op->lo_len, op->hi_len, op->dia_send, op->dia_recv_lo, op->dia_recv_hi);
   return CV_OK;
 }
 

@@ -166,6 +166,12 @@ int cv_op_attach_dia(cv_ctx *ctx, cv_op *op, int n_diag, const int32_t *offsets_
  * contiguous range sends derived from the partition `offsets` (host, world+1).                   */
 int cv_op_set_dia_halo(cv_ctx *ctx, cv_op *op, const int64_t *offsets, void *halo_lo_dev,
                        void *halo_hi_dev);
+/* The same plan as a pure host routine (integer outputs for the bit-exact check against the numpy
+ * oracle): send5[i] = {peer, first local row, count, band at the peer (0 lower, 1 upper), slot in
+ * that band buffer}, recv4[i] = {peer, band, first slot, count} (lower band first); cap = capacity
+ * of both arrays in ranges.                                                                      */
+int cv_dia_halo_plan(const int64_t *offsets, int world, int rank, int64_t lo_len, int64_t hi_len,
+                     int cap, int *n_send, int64_t *send5, int *n_recv, int64_t *recv4);
 /* Peer-memory halo of a DIA operator, after cv_op_set_dia_halo: every rank allocates
  * cv_op_dia_halo_bytes(op) with cv_peer_alloc (same layout on all ranks: two parities of
  * [lower band | upper band]); halo_base[p] = rank p's allocation as mapped here.              */

@@ -212,3 +212,31 @@ def test_dia_offset_table_host_logic():
     assert table(hm.coupled_oscillators((6, 5, 4, 4, 3))[0]) is None
     # tiny matrices are never converted
     assert table(hm.laplacian3d(5)) is None
+
+
+@pytest.mark.parametrize("N,world,lo,hi", [(1000, 2, 110, 110), (1000, 8, 110, 110), (1000, 8, 300, 40),
+                                            (97, 3, 5, 0), (64, 8, 20, 20), (20_000_000, 8, 1_100_000, 1_100_000)])
+def test_dia_halo_plan_bit_exact(N, world, lo, hi):
+    """The DIA band-halo exchange plan (cv_dia_halo_plan, shared with cv_op_set_dia_halo) against the
+    numpy statement: which contiguous row ranges every rank sends / receives, where they land."""
+    import ctypes as C
+    from eigensolvers_b200 import _lib
+    lib = _lib.load()
+    off = part.row_offsets(N, world)
+    np.testing.assert_array_equal(off, po.offsets(N, world))
+    cap = 4 * world
+    for rank in range(world):
+        send5 = np.zeros(5 * cap, dtype=np.int64)
+        recv4 = np.zeros(4 * cap, dtype=np.int64)
+        ns, nr = C.c_int(), C.c_int()
+        _lib.check(lib.cv_dia_halo_plan(off.ctypes.data, world, rank, lo, hi, cap, C.byref(ns), send5.ctypes.data,
+                                        C.byref(nr), recv4.ctypes.data))
+        send = sorted((tuple(int(v) for v in send5[5 * i:5 * i + 5]) for i in range(ns.value)), key=lambda t: (t[0], t[3]))
+        recv = sorted((tuple(int(v) for v in recv4[4 * i:4 * i + 4]) for i in range(nr.value)), key=lambda t: (t[1], t[0]))
+        ref_send, ref_recv = po.dia_halo_plan(off, rank, lo, hi)
+        assert send == ref_send, (rank, send, ref_send)
+        assert recv == ref_recv, (rank, recv, ref_recv)
+        # every row of both bands inside [0, N) is covered exactly once
+        r0, r1 = int(off[rank]), int(off[rank + 1])
+        assert sum(c for p, b, s, c in recv if b == 0) == r0 - max(r0 - lo, 0)
+        assert sum(c for p, b, s, c in recv if b == 1) == min(r1 + hi, N) - r1
