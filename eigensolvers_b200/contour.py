@@ -10,9 +10,15 @@ quirks of the reference's ``feastDiagonalization`` (feast.py:126-244):
 `positiveHalf=True` keeps the Legendre nodes with g_k > 0 only, i.e. nc/2 nodes in the upper
 right quadrant of the contour — kept as is, it is the parity target.
 
-All (node, vector) solves of one iteration are independent.  With `distribute="nodes"` and a
-torch.distributed group, node k is owned by rank k % world: the owner solves, the others skip,
-and the m0 accumulated vectors are summed over ranks once per iteration (H replicated).
+All (node, vector) solves of one iteration are independent (H replicated on every rank, the
+partial contour sums are added over ranks once per iteration):
+  distribute="nodes"   node k is owned by rank k % world (BASELINE config 5: one node per GPU);
+  distribute="tasks"   the nc/2 * m0 (node, vector) solves are spread over the ranks by longest-
+                       processing-time-first with MEASURED costs: nodes close to the real axis need
+                       ~2x the matvecs of the far ones, so whole nodes per GPU leave
+                       GPUs idle.  Iteration 0 uses 1/Im(z) as the cost guess, later iterations the
+                       wall time each solve took in the previous one (all-gathered, so every rank
+                       computes the same assignment).
 """
 import math
 import time
@@ -68,6 +74,25 @@ def updateQ(Q, im0, Qquad_k, k):
     return Q
 
 
+def _assign_tasks(distribute, rank, world, nodes, m0, cost):
+    """The (node, vector) solves this rank performs.  Deterministic: every rank computes the same map."""
+    tasks = [(k, i) for k in range(len(nodes)) for i in range(m0)]
+    if world == 1:
+        return set(tasks)
+    if distribute == "nodes":
+        return {(k, i) for (k, i) in tasks if k % world == rank}
+    if cost is None or any(t not in cost for t in tasks):   # first iteration / subspace size changed
+        cost = {(k, i): 1.0 / max(abs(nodes[k][1].imag), 1e-3 * abs(nodes[0][1].imag) + 1e-300) for (k, i) in tasks}
+    load = [0.0] * world
+    mine = set()
+    for t in sorted(tasks, key=lambda t: (-cost[t], t)):    # longest processing time first
+        r = min(range(world), key=lambda q: (load[q], q))
+        load[r] += cost[t]
+        if r == rank:
+            mine.add(t)
+    return mine
+
+
 def feastDiagonalization(A, Y, nc, quad, eMin, eMax, eConv, maxit, contourEllipseFactor=1.0,
                          writeOut=True, eShift=0.0, convertUnit="au", outFileName=None,
                          summaryFileName=None, distribute=None):
@@ -84,29 +109,44 @@ def feastDiagonalization(A, Y, nc, quad, eMin, eMax, eConv, maxit, contourEllips
                            status, outFileName, summaryFileName)
     printObj.fileHeader()
     rank, world = 0, 1
-    if distribute == "nodes":
+    if distribute not in (None, "nodes", "tasks"):
+        raise ValueError(f"distribute={distribute!r}: expected None, 'nodes' or 'tasks'")
+    if distribute in ("nodes", "tasks"):
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
             rank, world = dist.get_rank(), dist.get_world_size()
+    task_cost = None  # (node, vector) -> cost of that solve, identical on all ranks
 
     ev = None
     ref_ev = None
     for it in range(maxit):
         status["outerIter"] = it
         Q = [None] * N_SUBSPACE
-        first = True
+        nodes = []
         for k in range(len(gk)):
-            status["quadrature"] = k
-            if world > 1 and k % world != rank:
-                continue
             theta = -(np.pi * 0.5) * (gk[k] - 1)  # Polizzi (13)
             z = (eMin + eMax) * 0.5 + eRadius * (math.cos(theta) + contourEllipseFactor * 1.0j * math.sin(theta))
+            nodes.append((theta, z))
+        mine = _assign_tasks(distribute, rank, world, nodes, N_SUBSPACE, task_cost)
+        spent = {}
+        for k, (theta, z) in enumerate(nodes):
+            status["quadrature"] = k
             for im0 in range(N_SUBSPACE):
+                if (k, im0) not in mine:
+                    continue
+                t_task = time.perf_counter()
                 Qk = calculateQuadrature(A, Y[im0], z, eRadius, theta, wk[k], contourEllipseFactor)
-                Q = updateQ(Q, im0, Qk, 0 if first else 1)
-            first = False
+                Q = updateQ(Q, im0, Qk, 0 if Q[im0] is None else 1)
+                spent[(k, im0)] = time.perf_counter() - t_task
         if world > 1:
             Q = typeClass.sumOverRanks(Q, like=Y)
+            if distribute == "tasks":
+                import torch.distributed as dist
+                box = [None] * world
+                dist.all_gather_object(box, spent)
+                task_cost = {}
+                for b in box:
+                    task_cost.update(b)
 
         Smat = typeClass.overlapMatrix(Q)
         Hmat = typeClass.matrixRepresentation(A, Q)

@@ -136,13 +136,15 @@ def test_halo_exchange_two_gloo_ranks():
     assert all(r[2] == 64 for r in results)  # one 8x8 plane of halo on each side of the cut
 
 
-def _feast_worker(rank, world, port, q):
+def _feast_worker(rank, world, port, q, distribute="nodes"):
     import warnings
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=2)          # two workers share the host: do not oversubscribe BLAS
         from eigensolvers_b200.contour import feastDiagonalization
         from oracle.numpy_vector import NumpyVectorOracle as NV
         g = np.load(os.path.join(ROOT, "tests", "golden", "feast_t1.npz"))
@@ -151,7 +153,7 @@ def _feast_worker(rank, world, port, q):
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             ev, vecs, st = feastDiagonalization(g["A"], Y, 8, "legendre", 160.0, 166.0, 1e-10, 20, writeOut=False,
-                                                distribute="nodes")
+                                                distribute=distribute)
         inside = np.sort([e for e in ev if 160.0 <= e <= 166.0])
         ref = np.sort([e for e in g["ev"] if 160.0 <= e <= 166.0])
         q.put((rank, len(inside) == len(ref) and bool(np.allclose(inside, ref, rtol=0, atol=1e-6)), [float(x) for x in inside]))
@@ -159,14 +161,16 @@ def _feast_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_feast_nodes_distributed_over_two_gloo_ranks():
-    """FEAST with the quadrature nodes split over 2 ranks (H replicated, one all-reduce of the m0
-    accumulated vectors per iteration) finds the same eigenvalues as the reference's serial run."""
+@pytest.mark.parametrize("distribute", ["nodes", "tasks"])
+def test_feast_nodes_distributed_over_two_gloo_ranks(distribute):
+    """FEAST with the quadrature nodes (or the individual (node, vector) solves, balanced by measured
+    cost) split over 2 ranks (H replicated, one all-reduce of the m0 accumulated vectors per
+    iteration) finds the same eigenvalues as the reference's serial run."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_feast_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_feast_worker, args=(r, 2, port, q, distribute)) for r in range(2)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in range(2)]
@@ -240,3 +244,21 @@ def test_dia_halo_plan_bit_exact(N, world, lo, hi):
         r0, r1 = int(off[rank]), int(off[rank + 1])
         assert sum(c for p, b, s, c in recv if b == 0) == r0 - max(r0 - lo, 0)
         assert sum(c for p, b, s, c in recv if b == 1) == min(r1 + hi, N) - r1
+
+
+def test_feast_task_assignment_is_balanced_and_deterministic():
+    """contour._assign_tasks: every (node, vector) solve is owned by exactly one rank, all ranks
+    compute the same map, and measured costs balance the load (longest processing time first)."""
+    from eigensolvers_b200.contour import _assign_tasks
+    nodes = [(0.1 * k, complex(1.0, 0.5 / (k + 1))) for k in range(8)]
+    m0, world = 6, 8
+    tasks = {(k, i) for k in range(8) for i in range(m0)}
+    for cost in (None, {(k, i): 1.0 + k for (k, i) in tasks}):
+        owned = [_assign_tasks("tasks", r, world, nodes, m0, cost) for r in range(world)]
+        assert set().union(*owned) == tasks and sum(len(o) for o in owned) == len(tasks)
+        c = cost or {(k, i): 1.0 / abs(nodes[k][1].imag) for (k, i) in tasks}
+        loads = [sum(c[t] for t in o) for o in owned]
+        by_node = [sum(c[t] for t in _assign_tasks("nodes", r, world, nodes, m0, cost)) for r in range(world)]
+        assert max(loads) <= 1.1 * sum(loads) / world        # LPT: within 10 % of the mean here
+        assert max(loads) < max(by_node)                     # whole nodes per rank are worse
+    assert _assign_tasks("tasks", 0, 1, nodes, m0, None) == tasks

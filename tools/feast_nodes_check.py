@@ -27,7 +27,9 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from eigensolvers_b200 import CudaVector, DeviceOperator, Runtime, hamiltonians as hm
     from eigensolvers_b200.contour import feastDiagonalization
-    dims = tuple(int(a) for a in sys.argv[1:]) or (10, 10, 10, 10, 10)
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    distribute = "tasks" if "--tasks" in sys.argv else "nodes"
+    dims = tuple(int(a) for a in args) or (10, 10, 10, 10, 10)
     rt = Runtime.get()                      # unsharded: do NOT call init_distributed()
     H, om = hm.coupled_oscillators(dims, coupling=0.1, seed=1)
     levels = hm.oscillator_levels(om, 0.1, 12, max_quanta=6)
@@ -43,7 +45,7 @@ def main():
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         ev, vecs, st = feastDiagonalization(op, guess, 16, "legendre", eMin, eMax, 1e-8, 12, writeOut=False,
-                                            distribute="nodes")
+                                            distribute=distribute)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     got = np.sort([e for e in ev if eMin < e < eMax])
@@ -51,7 +53,7 @@ def main():
     box = [None] * world
     dist.all_gather_object(box, [float(x) for x in ev])
     ok = ok and all(b == box[0] for b in box)
-    print(f"[rank {rank}] {'PASS' if ok else 'FAIL'} N={H.shape[0]} world={world} iterations={st['outerIter'] + 1} "
+    print(f"[rank {rank}] {'PASS' if ok else 'FAIL'} distribute={distribute} N={H.shape[0]} world={world} iterations={st['outerIter'] + 1} "
           f"seconds={dt:.2f} solves={rt.stats['solves']} matvecs={rt.stats['matvecs']} inside={got.tolist()} "
           f"analytic={inside.tolist()}", flush=True)
     dist.destroy_process_group()
