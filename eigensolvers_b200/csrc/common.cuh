@@ -404,8 +404,10 @@ struct HaloWait {
   unsigned mask;                    // source ranks
   unsigned long long seq;
   double *err;
-  const double *scale_sq;  // non-null: halo entries were pushed UNNORMALISED (fused Arnoldi step);
-                           // multiply them by 1/sqrt(*scale_sq) like the owner did with its rows
+  const double *scale_sq;  // non-null: halo entries were pushed UNNORMALISED and are multiplied by
+                           // 1/sqrt(*scale_sq) on the fly, like the owner did with its rows.  Used by the
+                           // two-barrier form of the fused Arnoldi step (rows pushed before the norm
+                           // was known); the single-barrier form pushes normalised rows and leaves it null
 };
 __device__ __forceinline__ double halo_scale(const HaloWait &w) {
   if (!w.scale_sq) return 1.0;
