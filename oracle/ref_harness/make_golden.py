@@ -15,6 +15,8 @@ Cases:
                reference's calculateQuadrature/updateQ outputs for them
   lap_blk      block Lanczos on a 12^3 Laplacian + potential (C2's generator at small N)
   osc_1        single-vector Lanczos on a 600-dim coupled-oscillator Hamiltonian (C3's generator)
+  feast_osc    FEAST (nc = 16 -> 8 retained nodes, m0 = 4) on the sparse 600-dim oscillator Hamiltonian
+               (C5's structure at small N)
   lanczos_lindep  unittests/test_lanczosLINDEP.py setup (n=1200, loose solves rtol 1e-1, L=100: a
                30-vector Krylov list; with SciPy 1.18 the run converges WITHOUT tripping LINDEP —
                the reference's own test notes "may fail on some machines")
@@ -288,10 +290,28 @@ def case_lindep():
     summary["lanczos_lindep"] = dict(status_scalars(st), n_vectors=len(xf))
 
 
+def case_feast_osc():
+    # BASELINE config 5's structure at small N: FEAST on the sparse coupled-oscillator Hamiltonian,
+    # nc = 16 -> the reference's positiveHalf rule keeps 8 nodes (upper-right quadrant), m0 = 4,
+    # gcrotmk rtol 1e-2 (unittests/test_feast.py:33), window around two analytic levels
+    H, om = hm.coupled_oscillators((6, 5, 5, 4), coupling=0.1, seed=1)
+    lev = hm.oscillator_levels(om, 0.1, 12, max_quanta=6)
+    eMin, eMax = 0.5 * (lev[0] + lev[1]), 0.5 * (lev[2] + lev[3])
+    Q = np.linalg.qr(np.random.default_rng(7).standard_normal((H.shape[0], 4)))[0]
+    Y = [NumpyVector(np.ascontiguousarray(Q[:, i]), opts("gcrotmk", 1e-2, 2000)) for i in range(4)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        evf, uvf, st = ref.feast.feastDiagonalization(H, Y, 16, "legendre", eMin, eMax, 1e-8, 12, writeOut=False)
+    warnings.resetwarnings()
+    save("feast_osc", Q=Q, eMin=eMin, eMax=eMax, ev=evf, vecs=np.array([v.array for v in uvf]), levels=lev)
+    summary["feast_osc"] = dict(outerIter=int(st["outerIter"]), residual=float(st["residual"]),
+                                isConverged=bool(st["isConverged"]))
+
+
 if __name__ == "__main__":
     all_cases = dict(ops=case_ops, solve=case_solve, c1=case_c1, t1=case_t1, blk=case_blk, ho=case_ho,
                      feast=case_feast, fortran=case_fortran, lap_blk=case_lap_blk, osc=case_osc,
-                     lindep=case_lindep)
+                     lindep=case_lindep, feast_osc=case_feast_osc)
     chosen = sys.argv[1:] or list(all_cases)
     if sys.argv[1:] and os.path.exists(os.path.join(GOLD, "summary.json")):
         summary.update(json.load(open(os.path.join(GOLD, "summary.json"))))

@@ -202,6 +202,29 @@ def test_feast_matches_reference():
         assert abs(find_nearest(ev, e)[1] - e) <= 1e-4
 
 
+def test_feast_sparse_oscillator_matches_reference():
+    """C5's structure at small N (sparse H, nc = 16 -> 8 retained nodes, m0 = 4): our FEAST driver on
+    the oracle vector against the unmodified reference's run; the Ritz values inside the window are
+    the analytic oscillator levels."""
+    g = gold("feast_osc")
+    H, om = hm.coupled_oscillators((6, 5, 5, 4), coupling=0.1, seed=1)
+    Y = [NV(np.ascontiguousarray(g["Q"][:, i]), opts("gcrotmk", 1e-2, 2000)) for i in range(4)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ev, vecs, st = feastDiagonalization(H, Y, 16, "legendre", float(g["eMin"]), float(g["eMax"]), 1e-8, 12,
+                                            writeOut=False)
+    ref = summary()["feast_osc"]
+    assert st["outerIter"] == ref["outerIter"]
+    # the complex solves are loose (rtol 1e-2) and their rounding depends on the BLAS thread count:
+    # same trajectory, values equal far below the solver tolerance
+    np.testing.assert_allclose(ev, g["ev"], rtol=1e-9)
+    lev = g["levels"]
+    inside = lev[(lev > g["eMin"]) & (lev < g["eMax"])]
+    got = np.sort([e for e in ev if g["eMin"] < e < g["eMax"]])
+    assert len(got) == len(inside) == 2
+    np.testing.assert_allclose(got, inside, rtol=0, atol=5e-6)
+
+
 def test_fortran_feast_golden_vectors():
     """unittests/test_feast_fortran.py:56-127 against Polizzi's Fortran FEAST numbers
     (data_fortranCode.out), with our quadrature / contour code and the oracle's exact solve."""
