@@ -8,6 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcudavec.so")
 
 CV_OK = 0
+CV_ABI_VERSION = 2
 CV_SPMV_PLAIN, CV_SPMV_SHIFT, CV_SPMV_RSHIFT = 0, 1, 2
 CV_FMT_CSR, CV_FMT_SELL, CV_FMT_DIA = 0, 1, 2
 CV_SOLVER_GCROTMK, CV_SOLVER_MINRES = 0, 1
@@ -43,9 +44,10 @@ SIGNATURES = {
     "cv_ctx_set_recycle": (_i, [_vp, _i]),
     "cv_ctx_trace_read": (_i, [_vp, _pd, _i]),
     "cv_ctx_profile": (_i, [_vp, _i]),
-    "cv_ctx_profile_read": (_i, [_vp, _pd, C.POINTER(C.c_uint64)]),
+    "cv_ctx_profile_read": (_i, [_vp, _i, _pd, C.POINTER(C.c_uint64), _pd]),
     "cv_comm_unique_id": (_i, [_vp]),
     "cv_comm_init": (_i, [_vp, _vp, _i, _i]),
+    "cv_comm_init_peer_only": (_i, [_vp, _i, _i]),
     "cv_comm_finalize": (_i, [_vp]),
     "cv_comm_allreduce": (_i, [_vp, _vp, _i, _vp]),
     "cv_peer_window_bytes": (_sz, []),
@@ -106,8 +108,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError here means header and library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.cv_abi_version() != 1:
-        raise ImportError(f"libcudavec ABI {lib.cv_abi_version()} != 1; rebuild the library")
+    if lib.cv_abi_version() != CV_ABI_VERSION:
+        raise ImportError(f"libcudavec ABI {lib.cv_abi_version()} != {CV_ABI_VERSION}; rebuild the library")
     _lib = lib
     return lib
 

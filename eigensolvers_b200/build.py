@@ -44,7 +44,9 @@ def build(force=False, verbose=False):
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libcudavec.so (see output above)")
-    with open(os.path.join(HERE, "build_ptxas.log"), "w") as fh:
+    logdir = os.path.join(os.path.dirname(HERE), "build")   # git-ignored
+    os.makedirs(logdir, exist_ok=True)
+    with open(os.path.join(logdir, "ptxas.log"), "w") as fh:
         fh.write(res.stderr)
     return LIB
 

@@ -116,6 +116,8 @@ def feastDiagonalization(A, Y, nc, quad, eMin, eMax, eConv, maxit, contourEllips
         if dist.is_available() and dist.is_initialized():
             rank, world = dist.get_rank(), dist.get_world_size()
     task_cost = None  # (node, vector) -> cost of that solve, identical on all ranks
+    profile = {"distribute": distribute, "world": world, "iterations": []}
+    feastDiagonalization.last_profile = profile
 
     ev = None
     ref_ev = None
@@ -128,25 +130,45 @@ def feastDiagonalization(A, Y, nc, quad, eMin, eMax, eConv, maxit, contourEllips
             z = (eMin + eMax) * 0.5 + eRadius * (math.cos(theta) + contourEllipseFactor * 1.0j * math.sin(theta))
             nodes.append((theta, z))
         mine = _assign_tasks(distribute, rank, world, nodes, N_SUBSPACE, task_cost)
-        spent = {}
+        spent, work = {}, {}
+        counter = getattr(typeClass, "matvecCount", None)
         for k, (theta, z) in enumerate(nodes):
             status["quadrature"] = k
             for im0 in range(N_SUBSPACE):
                 if (k, im0) not in mine:
                     continue
                 t_task = time.perf_counter()
+                c0 = counter() if counter else 0
                 Qk = calculateQuadrature(A, Y[im0], z, eRadius, theta, wk[k], contourEllipseFactor)
                 Q = updateQ(Q, im0, Qk, 0 if Q[im0] is None else 1)
                 spent[(k, im0)] = time.perf_counter() - t_task
+                work[(k, im0)] = (counter() - c0) if counter else 0
+        it_prof = {"solve_seconds_this_rank": sum(spent.values()), "matvecs_this_rank": sum(work.values())}
         if world > 1:
-            Q = typeClass.sumOverRanks(Q, like=Y)
+            import torch.distributed as dist
+            t_red = time.perf_counter()
+            Q = typeClass.sumOverRanks(Q, like=Y)          # ONE bucketed all-reduce of the m0 partial sums
+            it_prof["reduction_seconds"] = time.perf_counter() - t_red
+            box = [None] * world
+            dist.all_gather_object(box, (spent, work))
             if distribute == "tasks":
-                import torch.distributed as dist
-                box = [None] * world
-                dist.all_gather_object(box, spent)
                 task_cost = {}
                 for b in box:
-                    task_cost.update(b)
+                    task_cost.update(b[0])
+            busy = [sum(b[0].values()) for b in box]
+            it_prof["busy_seconds_per_rank"] = busy
+            it_prof["idle_fraction"] = 1.0 - (sum(busy) / len(busy)) / max(max(busy), 1e-30)
+            per_node = {}
+            for b in box:
+                for (k, _i), c in b[1].items():
+                    per_node[k] = per_node.get(k, 0) + c
+            it_prof["matvecs_per_node"] = [per_node.get(k, 0) for k in range(len(nodes))]
+        else:
+            per_node = {}
+            for (k, _i), c in work.items():
+                per_node[k] = per_node.get(k, 0) + c
+            it_prof["matvecs_per_node"] = [per_node.get(k, 0) for k in range(len(nodes))]
+        profile["iterations"].append(it_prof)
 
         Smat = typeClass.overlapMatrix(Q)
         Hmat = typeClass.matrixRepresentation(A, Q)

@@ -64,7 +64,7 @@ extern "C" int cv_ctx_create(int device, void *scratch_dev, size_t scratch_bytes
 
 extern "C" int cv_ctx_destroy(cv_ctx *ctx) {
   if (!ctx) return CV_OK;
-  if (ctx->comm) cv_comm_finalize(ctx);
+  if (ctx->comm || ctx->peer) cv_comm_finalize(ctx);
   if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
   if (ctx->prof) {
     if (ctx->prof->created)
@@ -126,12 +126,13 @@ static void prof_drain(cv_prof_state *p) {
   p->used = 0;
 }
 
-cv_prof_scope::cv_prof_scope(cv_ctx *c, int cls, cudaStream_t s) : ctx(c), st(s), slot(-1) {
+cv_prof_scope::cv_prof_scope(cv_ctx *c, int cls, cudaStream_t s, double alg_bytes) : ctx(c), st(s), slot(-1) {
   cv_prof_state *p = c->prof;
   if (!p || !p->enabled) return;
   if (p->used == CV_PROF_POOL) prof_drain(p);
   slot = p->used++;
   p->cls[slot] = cls;
+  p->bytes[cls] += alg_bytes;
   cudaEventRecord(p->start[slot], st);
 }
 
@@ -155,17 +156,23 @@ extern "C" int cv_ctx_profile(cv_ctx *ctx, int enable) {
   return CV_OK;
 }
 
-extern "C" int cv_ctx_profile_read(cv_ctx *ctx, double *ms4, uint64_t *count4) {
-  CV_REQUIRE(ctx && ms4 && count4, "cv_ctx_profile_read: null argument");
-  for (int i = 0; i < CV_PROF_CLASSES; ++i) ms4[i] = 0.0, count4[i] = 0;
+extern "C" int cv_ctx_profile_read(cv_ctx *ctx, int n_classes, double *ms, uint64_t *count, double *bytes) {
+  CV_REQUIRE(ctx && ms && count && bytes, "cv_ctx_profile_read: null argument");
+  CV_REQUIRE(n_classes >= 1 && n_classes <= CV_PROF_CLASSES, "cv_ctx_profile_read: n_classes=%d outside 1..%d",
+             n_classes, CV_PROF_CLASSES);
+  for (int i = 0; i < n_classes; ++i) ms[i] = 0.0, count[i] = 0, bytes[i] = 0.0;
   cv_prof_state *p = ctx->prof;
   if (!p) return CV_OK;
   prof_drain(p);
   for (int i = 0; i < CV_PROF_CLASSES; ++i) {
-    ms4[i] = p->ms[i];
-    count4[i] = p->count[i];
+    if (i < n_classes) {
+      ms[i] = p->ms[i];
+      count[i] = p->count[i];
+      bytes[i] = p->bytes[i];
+    }
     p->ms[i] = 0.0;
     p->count[i] = 0;
+    p->bytes[i] = 0.0;
   }
   return CV_OK;
 }
@@ -396,7 +403,8 @@ template <typename TV, typename TC, typename TY, int W, bool NORM>
 static int launch_lincomb_nc(cv_ctx *ctx, const LcParams &p, int ncol, int grid, double *out_norm,
                              cudaStream_t st) {
   (void)grid;
-  cv_prof_scope prof(ctx, 3, st);
+  // algorithmic bytes: (m + ncol) vectors of n elements
+  cv_prof_scope prof(ctx, 5, st, (double)(p.m + ncol) * (double)p.n * (double)sizeof(TY));
 #define LC(NC)                                                                                     \
   do {                                                                                             \
     auto kf = k_lincomb<TV, TC, TY, W, NC, NORM>;                                                  \
@@ -469,17 +477,41 @@ extern "C" int cv_lincomb(cv_ctx *ctx, int64_t n, int v_cplx, int c_cplx, int m,
                           const void *const *v_ptrs, int ncol, const double *coef_host,
                           void *const *y_ptrs, void *stream) {
   CV_REQUIRE(ctx && v_ptrs && coef_host && y_ptrs, "cv_lincomb: null argument");
-  CV_REQUIRE(m >= 1 && m <= CV_MAX_PTRS, "cv_lincomb: m=%d outside 1..%d", m, CV_MAX_PTRS);
-  CV_REQUIRE(ncol >= 1 && n >= 0, "cv_lincomb: bad shape");
+  CV_REQUIRE(m >= 1 && ncol >= 1 && n >= 0, "cv_lincomb: bad shape");
   if (n == 0) return CV_OK;
   const int cs = c_cplx ? 2 : 1;
+  // Any number of inputs: they are consumed in chunks of <= MCH; from the second chunk on the
+  // partial results re-enter as extra inputs with unit coefficients (a thread reads every input of
+  // an element before it writes the outputs of that element, so in-place accumulation is safe).
+  const int MCH = 96;
   int chunk = c_cplx || v_cplx ? 4 : 8;  // outputs per pass over the inputs
-  while (chunk > 1 && m * chunk * cs > CV_MAX_COEF) chunk >>= 1;
-  CV_REQUIRE(m * chunk * cs <= CV_MAX_COEF, "cv_lincomb: too many coefficients");
+  const int m_launch_max = (m <= MCH ? m : MCH + chunk);
+  while (chunk > 1 && m_launch_max * chunk * cs > CV_MAX_COEF) chunk >>= 1;
+  CV_REQUIRE((m <= MCH ? m : MCH + chunk) * chunk * cs <= CV_MAX_COEF, "cv_lincomb: too many coefficients");
+  CV_REQUIRE(m <= MCH || v_cplx || !c_cplx, "cv_lincomb: complex coefficients on more than %d real inputs", MCH);
+  std::vector<const void *> vp;
+  std::vector<double> cf;
   for (int c0 = 0; c0 < ncol; c0 += chunk) {
-    int nc = ncol - c0 < chunk ? ncol - c0 : chunk;
-    CV_TRY(cv_lincomb_launch(ctx, n, v_cplx, c_cplx, m, v_ptrs, nc, coef_host, ncol, c0, y_ptrs + c0,
-                             -1, (cudaStream_t)stream));
+    const int nc = ncol - c0 < chunk ? ncol - c0 : chunk;
+    for (int j0 = 0; j0 < m; j0 += MCH) {
+      const int mj = m - j0 < MCH ? m - j0 : MCH;
+      const int extra = j0 > 0 ? nc : 0;
+      vp.assign(mj + extra, nullptr);
+      cf.assign((size_t)(mj + extra) * nc * cs, 0.0);
+      for (int j = 0; j < mj; ++j) {
+        vp[j] = v_ptrs[j0 + j];
+        for (int k = 0; k < nc; ++k)
+          for (int c = 0; c < cs; ++c) cf[((size_t)j * nc + k) * cs + c] = coef_host[((size_t)(j0 + j) * ncol + c0 + k) * cs + c];
+      }
+      for (int k = 0; k < extra; ++k) {
+        vp[mj + k] = y_ptrs[c0 + k];
+        cf[((size_t)(mj + k) * nc + k) * cs] = 1.0;
+      }
+      // partial results have the OUTPUT type: complex outputs re-enter as complex inputs
+      const int in_cplx = v_cplx;
+      CV_TRY(cv_lincomb_launch(ctx, n, in_cplx, c_cplx, mj + extra, vp.data(), nc, cf.data(), nc, 0, y_ptrs + c0,
+                               -1, (cudaStream_t)stream));
+    }
   }
   return CV_OK;
 }
@@ -498,7 +530,8 @@ static int launch_tsdot(cv_ctx *ctx, const TsParams &p, int slot, const double *
   int ny = (p.m + MI - 1) / MI;
   int64_t per_slab = (int64_t)MI * p.b * NR;
   {
-    cv_prof_scope prof(ctx, 1, st);
+    // algorithmic bytes: V once, W once per slab of MI vectors
+    cv_prof_scope prof(ctx, 1, st, (double)(p.m + p.b * ny) * (double)p.n * (double)sizeof(T));
     // one resident wave in total: the y-slabs share the SMs
 #define TSD(MI_, B_)                                                                               \
   do {                                                                                             \
@@ -554,18 +587,22 @@ int cv_tsdot_dev(cv_ctx *ctx, int64_t n, int cplx_, int conj, int m, const void 
 extern "C" int cv_tsdot(cv_ctx *ctx, int64_t n, int cplx_, int conj, int m, const void *const *v_ptrs,
                         int b, const void *const *w_ptrs, double *out_host, void *stream) {
   CV_REQUIRE(ctx && v_ptrs && w_ptrs && out_host && n >= 0, "cv_tsdot: bad argument");
-  CV_REQUIRE(m >= 1 && m <= CV_MAX_PTRS && b >= 1, "cv_tsdot: m=%d b=%d out of range", m, b);
+  CV_REQUIRE(m >= 1 && b >= 1, "cv_tsdot: m=%d b=%d out of range", m, b);
   cudaStream_t st = (cudaStream_t)stream;
   const int nr = cplx_ ? 2 : 1;
-  // chunk the right-hand sides by 4; results are assembled as out[(i*b + k)*nr + c]
-  for (int k0 = 0; k0 < b; k0 += 4) {
-    int bb = b - k0 < 4 ? b - k0 : 4;
-    CV_TRY(cv_tsdot_dev(ctx, n, cplx_, conj, m, v_ptrs, bb, w_ptrs + k0, CV_S_TS, st));
-    CV_TRY(cv_fetch_scalars(ctx, CV_S_TS, m * bb * nr, st));
-    for (int i = 0; i < m; ++i)
-      for (int k = 0; k < bb; ++k)
-        for (int c = 0; c < nr; ++c)
-          out_host[((size_t)i * b + k0 + k) * nr + c] = ctx->mailbox[CV_S_TS + (i * bb + k) * nr + c];
+  // any m, any b: V in chunks of CV_MAX_PTRS vectors, right-hand sides in chunks of 4; results are
+  // assembled as out[(i*b + k)*nr + c]
+  for (int i0 = 0; i0 < m; i0 += CV_MAX_PTRS) {
+    const int mm = m - i0 < CV_MAX_PTRS ? m - i0 : CV_MAX_PTRS;
+    for (int k0 = 0; k0 < b; k0 += 4) {
+      int bb = b - k0 < 4 ? b - k0 : 4;
+      CV_TRY(cv_tsdot_dev(ctx, n, cplx_, conj, mm, v_ptrs + i0, bb, w_ptrs + k0, CV_S_TS, st));
+      CV_TRY(cv_fetch_scalars(ctx, CV_S_TS, mm * bb * nr, st));
+      for (int i = 0; i < mm; ++i)
+        for (int k = 0; k < bb; ++k)
+          for (int c = 0; c < nr; ++c)
+            out_host[((size_t)(i0 + i) * b + k0 + k) * nr + c] = ctx->mailbox[CV_S_TS + (i * bb + k) * nr + c];
+    }
   }
   return CV_OK;
 }
@@ -590,7 +627,7 @@ int cv_tsupdate_dev(cv_ctx *ctx, int64_t n, int cplx_, int m, const void *const 
   size_t sh = sizeof(double) * m * (cplx_ ? 2 : 1);
   const double eta2 = ctx->reorth_eta * ctx->reorth_eta;
   {
-    cv_prof_scope prof(ctx, 2, st);
+    cv_prof_scope prof(ctx, 2, st, (double)(m + 2) * (double)n * (cplx_ ? 16.0 : 8.0));
 #define TSU(T, WW, NM)                                                                             \
   do {                                                                                             \
     auto kf = k_tsupdate<T, WW, NM>;                                                               \
@@ -718,7 +755,9 @@ int cv_orth_step_dev(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int m, const 
   CV_REQUIRE(grid >= ny, "orth_step: grid %d smaller than %d slabs", grid, ny);
   void *params[1] = {(void *)&a};
   {
-    cv_prof_scope prof(ctx, 1, st);
+    // algorithmic bytes of the first pass: basis twice (dots, update), w read twice and written once;
+    // a second Gram-Schmidt pass (rare) is added by the solver once the mailbox says it ran
+    cv_prof_scope prof(ctx, 1, st, (double)(2 * m + 3) * (double)n * (cplx_ ? 16.0 : 8.0));
     if (coop) {
       CV_CUDA(cudaLaunchCooperativeKernel(kf, dim3(grid), dim3(CV_BLOCK), params, sh, st));
     } else {
@@ -733,24 +772,29 @@ int cv_orth_step_dev(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int m, const 
 // ------------------------------------------------------------------------------------------
 // Gram-Schmidt against a set (reference semantics, numpyVector.py:121-145)
 // ------------------------------------------------------------------------------------------
+// scalar slots of the chain form a ring: step i only reads the slot of step i-1
+constexpr int CV_GS_RING = 64;
+static inline int gs_slot(int i, int NR) { return CV_S_GS + 2 * NR * (i % CV_GS_RING); }
+
 template <typename T, int W>
 static int gs_chain(cv_ctx *ctx, int64_t n, const T *x_in, int m, const void *const *q, T *x_out,
                     cudaStream_t st) {
   constexpr int NR = Num<T>::NRED;
   auto kf = k_mgs_step<T, W>;
   int grid = CV_KGRID(kf, n / W + 1);
-  cv_prof_scope prof(ctx, 3, st);
+  // algorithmic bytes: every step streams x (read + write), the previous and the current q
+  cv_prof_scope prof(ctx, 4, st, (double)(4 * m + 2) * (double)n * (double)sizeof(T));
   // step i: subtract projection on q[i-1] (coefficients from slot i-1), dots with q[i]
   for (int i = 0; i <= m; ++i) {
     const T *src = (i == 0) ? x_in : x_out;
     const T *qp = (i == 0) ? nullptr : static_cast<const T *>(q[i - 1]);
     const T *qc = (i == m) ? nullptr : static_cast<const T *>(q[i]);
-    const double *tprev = ctx->scalars + CV_S_GS + 2 * NR * (i > 0 ? i - 1 : 0);
-    double *tout = ctx->scalars + CV_S_GS + 2 * NR * i;
+    const double *tprev = ctx->scalars + gs_slot(i > 0 ? i - 1 : 0, NR);
+    double *tout = ctx->scalars + gs_slot(i, NR);
     k_mgs_step<T, W><<<grid, CV_BLOCK, 0, st>>>(n, src, x_out, qp, tprev, qc, ctx->partials,
                                                 ctx->counters, tout);
     CV_TRY(cv_check_launch(ctx, "mgs_step"));
-    CV_TRY(cv_reduce_ranks(ctx, CV_S_GS + 2 * NR * i, 2 * NR, st));
+    CV_TRY(cv_reduce_ranks(ctx, gs_slot(i, NR), 2 * NR, st));
   }
   return CV_OK;
 }
@@ -759,9 +803,10 @@ extern "C" int cv_gs_against_set(cv_ctx *ctx, int64_t n, int cplx_, const void *
                                  const void *const *q_ptrs, double lindep, void *x_out, int *status,
                                  double *innerprod_host, void *stream) {
   CV_REQUIRE(ctx && x_in && x_out && status && innerprod_host, "cv_gs_against_set: null argument");
-  CV_REQUIRE(m >= 0 && m < CV_MAX_PTRS, "cv_gs_against_set: m=%d out of range", m);
+  CV_REQUIRE(m >= 0, "cv_gs_against_set: m=%d out of range", m);
   CV_REQUIRE(m == 0 || q_ptrs, "cv_gs_against_set: null q_ptrs");
   CV_REQUIRE(x_in != x_out, "cv_gs_against_set: out of place only");
+  static_assert(CV_S_GS + 4 * CV_GS_RING <= CV_S_TS, "Gram-Schmidt scalar ring overlaps the tall-skinny slots");
   cudaStream_t st = (cudaStream_t)stream;
   const int NR = cplx_ ? 2 : 1;
   int W = cplx_ ? 1 : 2;
@@ -774,7 +819,7 @@ extern "C" int cv_gs_against_set(cv_ctx *ctx, int64_t n, int cplx_, const void *
     CV_TRY((gs_chain<double, 2>(ctx, n, (const double *)x_in, m, q_ptrs, (double *)x_out, st)));
   else
     CV_TRY((gs_chain<double, 1>(ctx, n, (const double *)x_in, m, q_ptrs, (double *)x_out, st)));
-  const int slot = CV_S_GS + 2 * NR * m;  // innerprod = x.x
+  const int slot = gs_slot(m, NR);  // innerprod = x.x
   CV_TRY(cv_fetch_scalars(ctx, slot, NR, st));
   innerprod_host[0] = ctx->mailbox[slot];
   innerprod_host[1] = cplx_ ? ctx->mailbox[slot + 1] : 0.0;
@@ -803,7 +848,9 @@ extern "C" int cv_op_create_csr(cv_ctx *ctx, int64_t n_rows, int64_t n_cols, int
   CV_REQUIRE(n_rows >= 0 && n_cols >= 0 && nnz >= 0, "cv_op_create_csr: negative size");
   CV_REQUIRE(n_cols < ((int64_t)1 << 31), "cv_op_create_csr: column indices are int32");
   CV_REQUIRE(nnz == 0 || (indices_dev && data_dev), "cv_op_create_csr: null arrays");
+  static uint64_t next_id = 0;
   cv_op *op = new cv_op();
+  op->id = ++next_id;
   op->n_rows = n_rows;
   op->n_cols = n_cols;
   op->nnz = nnz;
@@ -918,7 +965,17 @@ extern "C" int cv_op_info(cv_op *op, int64_t *n_rows, int64_t *nnz, int64_t *pad
 // ------------------------------------------------------------------------------------------
 template <typename T, bool HALO, bool EPI, bool DOTS>
 static int launch_spmv_fmt(cv_ctx *ctx, cv_op *op, const SpmvArgs<T> &a, cudaStream_t st) {
-  cv_prof_scope prof(ctx, 0, st);
+  // Bytes the STORED format must move per launch (x read once, y written once, + u1 when fused):
+  //   DIA  8*D*ld                       (no index stream)
+  //   SELL 12*padded_nnz + 8*n_slices
+  //   CSR  12*nnz + 8*(n_rows+1)
+  // next to SURVEY 8d's format-independent CSR-equivalent figure 12*nnz + 20*N (36*N complex).
+  const double vecb = (double)sizeof(T) * (double)op->n_rows * (2.0 + (EPI && a.u1 ? 1.0 : 0.0));
+  const double matb = op->fmt == CV_FMT_DIA    ? 8.0 * (double)op->n_diag * (double)op->dia_ld
+                      : op->fmt == CV_FMT_SELL ? 12.0 * (double)op->padded_nnz + 8.0 * (double)op->n_slices
+                                               : 12.0 * (double)op->nnz + 8.0 * (double)(op->n_rows + 1);
+  cv_prof_add_bytes(ctx, 6, 12.0 * (double)op->nnz + (sizeof(T) == 16 ? 36.0 : 20.0) * (double)op->n_rows);
+  cv_prof_scope prof(ctx, 0, st, matb + vecb);
   if (op->fmt == CV_FMT_DIA) {
     DiaArgs<T> d;
     d.s = a;
@@ -1008,7 +1065,10 @@ static int launch_spmv_t(cv_ctx *ctx, cv_op *op, int mode, T sigma, const T *x, 
   a.out = dots_slot >= 0 ? ctx->scalars + dots_slot : nullptr;
   a.wait = HaloWait{nullptr, 0u, 0ull, nullptr, nullptr};
   const bool dia = op->fmt == CV_FMT_DIA;
-  const bool halo = dia ? (ctx->world > 1 && (op->lo_len > 0 || op->hi_len > 0)) : op->n_halo > 0;
+  // a rank takes part in the exchange when it RECEIVES (n_halo > 0) or only SENDS (structurally
+  // one-sided couplings, an empty row block): the same predicate as cv_orth_step_dev
+  const bool halo = dia ? (ctx->world > 1 && (op->lo_len > 0 || op->hi_len > 0))
+                        : (op->n_halo > 0 || (!op->send_off.empty() && op->send_off.back() > 0));
   const bool dots = dots_slot >= 0;
   if (halo) {
     if (dia)
@@ -1021,6 +1081,13 @@ static int launch_spmv_t(cv_ctx *ctx, cv_op *op, int mode, T sigma, const T *x, 
     }
   }
   int rc;
+  if (op->n_rows == 0) {  // nothing to compute here, but the collectives above/below must still happen
+    if (dots) {
+      CV_CUDA(cudaMemsetAsync(ctx->scalars + dots_slot, 0, 3 * sizeof(double), st));
+      CV_TRY(cv_reduce_ranks(ctx, dots_slot, 3, st));
+    }
+    return CV_OK;
+  }
 #define GO(H, E, D) rc = launch_spmv_fmt<T, H, E, D>(ctx, op, a, st)
   if (halo) {
     if (epi) { if (dots) GO(true, true, true); else GO(true, true, false); }
@@ -1040,7 +1107,7 @@ int cv_spmv_dev(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double 
                 cudaStream_t st) {
   CV_REQUIRE(mode >= 0 && mode <= 2, "spmv: mode %d", mode);
   CV_REQUIRE(x != y, "spmv: x and y must not alias");
-  if (op->n_rows == 0) return CV_OK;
+  if (op->n_rows == 0 && ctx->world == 1) return CV_OK;
   if (cplx_)
     return launch_spmv_t<cplx>(ctx, op, mode, make_cplx(sre, sim), (const cplx *)x, (cplx *)y, alpha,
                                beta1, (const cplx *)u1, epi, dots_slot, st);
@@ -1075,7 +1142,7 @@ extern "C" int cv_spmv_dots(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double 
 extern "C" int cv_extend_columns(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int m,
                                  const void *const *v_ptrs, void *ket_tmp, double *s_col_host,
                                  double *h_col_host, void *stream) {
-  CV_REQUIRE(ctx && v_ptrs && m >= 1 && m <= CV_MAX_PTRS, "cv_extend_columns: bad argument");
+  CV_REQUIRE(ctx && v_ptrs && m >= 1, "cv_extend_columns: bad argument");
   CV_REQUIRE(s_col_host || h_col_host, "cv_extend_columns: nothing to compute");
   CV_REQUIRE(!h_col_host || (op && ket_tmp), "cv_extend_columns: operator column needs op and ket_tmp");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1089,16 +1156,19 @@ extern "C" int cv_extend_columns(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, i
                        nullptr, false, -1, st));
     w[b++] = ket_tmp;
   }
-  CV_TRY(cv_tsdot_dev(ctx, n, cplx_, 1, m, v_ptrs, b, w, CV_S_TS, st));
-  CV_TRY(cv_fetch_scalars(ctx, CV_S_TS, m * b * nr, st));
-  for (int i = 0; i < m; ++i) {
-    int k = 0;
-    if (s_col_host) {
-      for (int c = 0; c < nr; ++c) s_col_host[i * nr + c] = ctx->mailbox[CV_S_TS + (i * b + k) * nr + c];
-      ++k;
+  for (int i0 = 0; i0 < m; i0 += CV_MAX_PTRS) {  // any m: V in chunks of CV_MAX_PTRS vectors
+    const int mm = m - i0 < CV_MAX_PTRS ? m - i0 : CV_MAX_PTRS;
+    CV_TRY(cv_tsdot_dev(ctx, n, cplx_, 1, mm, v_ptrs + i0, b, w, CV_S_TS, st));
+    CV_TRY(cv_fetch_scalars(ctx, CV_S_TS, mm * b * nr, st));
+    for (int i = 0; i < mm; ++i) {
+      int k = 0;
+      if (s_col_host) {
+        for (int c = 0; c < nr; ++c) s_col_host[(i0 + i) * nr + c] = ctx->mailbox[CV_S_TS + (i * b + k) * nr + c];
+        ++k;
+      }
+      if (h_col_host)
+        for (int c = 0; c < nr; ++c) h_col_host[(i0 + i) * nr + c] = ctx->mailbox[CV_S_TS + (i * b + k) * nr + c];
     }
-    if (h_col_host)
-      for (int c = 0; c < nr; ++c) h_col_host[i * nr + c] = ctx->mailbox[CV_S_TS + (i * b + k) * nr + c];
   }
   return CV_OK;
 }

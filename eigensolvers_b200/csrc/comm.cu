@@ -98,6 +98,14 @@ extern "C" int cv_comm_init(cv_ctx *ctx, const void *id128, int rank, int world)
   return CV_OK;
 }
 
+extern "C" int cv_comm_init_peer_only(cv_ctx *ctx, int rank, int world) {
+  CV_REQUIRE(ctx && world >= 1 && rank >= 0 && rank < world, "cv_comm_init_peer_only: bad argument");
+  CV_REQUIRE(world <= CV_MAX_WORLD, "cv_comm_init_peer_only: world=%d exceeds %d", world, CV_MAX_WORLD);
+  ctx->rank = rank;
+  ctx->world = world;
+  return CV_OK;
+}
+
 extern "C" int cv_comm_finalize(cv_ctx *ctx) {
   if (ctx && ctx->comm) {
     if (ctx->comm->comm) g_nccl.CommDestroy(ctx->comm->comm);
@@ -116,7 +124,7 @@ extern "C" int cv_comm_allreduce(cv_ctx *ctx, double *buf_dev, int count, void *
   CV_REQUIRE(ctx && buf_dev && count >= 0, "cv_comm_allreduce: bad argument");
   if (ctx->world == 1 || count == 0) return CV_OK;
   if (ctx->peer) return cv_peer_allreduce(ctx, buf_dev, count, (cudaStream_t)stream);
-  CV_REQUIRE(ctx->comm, "cv_comm_allreduce: communicator not initialised");
+  CV_REQUIRE(ctx->comm, "cv_comm_allreduce: neither a peer-memory window nor an NCCL communicator is attached");
   CV_NCCL(g_nccl.AllReduce(buf_dev, buf_dev, (size_t)count, ncclFloat64_, ncclSum_, ctx->comm->comm,
                            (cudaStream_t)stream));
   return CV_OK;

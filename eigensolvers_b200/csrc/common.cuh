@@ -69,7 +69,12 @@ constexpr int CV_COUNTER_PUSH = 63;  // ticket of the halo push kernel inside ct
 constexpr int CV_COUNTER_BAR = 60;   // {arrivals, generation} of the fused Arnoldi step's grid barrier
 
 // optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline)
-constexpr int CV_PROF_CLASSES = 4;  // 0 spmv, 1 tsdot, 2 tsupdate, 3 other vector kernels
+// classes: 0 fused SpMV, 1 fused Arnoldi step / tall-skinny dot, 2 tall-skinny update, 3 other
+// vector kernels, 4 Gram-Schmidt against a set, 5 linear combinations, 6 (no launches) the SpMV's
+// CSR-equivalent bytes 12 nnz + 20 N next to class 0's bytes of the format actually stored, 7 spare.
+// `bytes` accumulates the ALGORITHMIC bytes of the timed launches (SURVEY 8d formulas, stated at
+// each launch site) so that GB/s = bytes / ms is reproducible from one bench line.
+constexpr int CV_PROF_CLASSES = 8;
 constexpr int CV_PROF_POOL = 2048;  // event pairs kept in flight before they are drained
 struct cv_prof_state {
   bool enabled = false;
@@ -77,8 +82,9 @@ struct cv_prof_state {
   int cls[CV_PROF_POOL];
   int used = 0;
   bool created = false;
-  double ms[CV_PROF_CLASSES] = {0, 0, 0, 0};
-  uint64_t count[CV_PROF_CLASSES] = {0, 0, 0, 0};
+  double ms[CV_PROF_CLASSES] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t count[CV_PROF_CLASSES] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double bytes[CV_PROF_CLASSES] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 // GCROT recycling across solves (solvers.cu): which (c,u) ring slots of the solver workspace hold
@@ -86,7 +92,7 @@ struct cv_prof_state {
 struct cv_op;
 struct cv_recycle_state {
   bool enabled = false, valid = false;
-  const cv_op *op = nullptr;
+  uint64_t op_id = 0;  // cv_op::id (monotonic), not the pointer: a new operator may reuse the address
   int cplx = 0, mode = 0, m = 0, k = 0;
   double sre = 0.0, sim = 0.0;
   int64_t n = 0;
@@ -126,9 +132,12 @@ struct cv_prof_scope {
   cv_ctx *ctx;
   cudaStream_t st;
   int slot;
-  cv_prof_scope(cv_ctx *c, int cls, cudaStream_t s);
+  cv_prof_scope(cv_ctx *c, int cls, cudaStream_t s, double alg_bytes = 0.0);
   ~cv_prof_scope();
 };
+inline void cv_prof_add_bytes(cv_ctx *ctx, int cls, double b) {
+  if (ctx->prof && ctx->prof->enabled) ctx->prof->bytes[cls] += b;
+}
 
 inline int cv_grid_for(const cv_ctx *ctx, int64_t work_items, int items_per_cta) {
   int64_t need = (work_items + items_per_cta - 1) / items_per_cta;

@@ -8,6 +8,7 @@
 #include "kernels_orth.cuh"
 
 struct cv_op {
+  uint64_t id = 0;  // unique per created operator (recycling state is keyed on it)
   int64_t n_rows = 0, n_cols = 0, nnz = 0;
   // CSR (borrowed device arrays)
   const int64_t *indptr = nullptr;
@@ -40,6 +41,7 @@ struct cv_op {
   // peer-memory transport: halo buffers live in IPC-exported allocations, double-buffered by the
   // parity of the exchange sequence number; *_cur point at the parity the next SpMV reads
   bool peer_halo = false;
+  unsigned long long halo_count = 0;     // exchanges of THIS operator so far (parity of its halo buffers)
   std::vector<void *> peer_base;         // [world] base of every rank's halo allocation (own at [rank])
   std::vector<int64_t> peer_stride;      // [world] bytes between the two parities (general halo)
   std::vector<int64_t> peer_dst_off;     // [world] element offset of MY block inside peer p's halo

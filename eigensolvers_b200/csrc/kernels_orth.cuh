@@ -135,6 +135,32 @@ __device__ __forceinline__ bool push_pack(const PushArgs &a, int64_t ip, const P
   return any;
 }
 
+// Phase A splits the basis into slabs of <= MI vectors (the accumulators of one thread) and gives
+// every slab a share of the CTAs PROPORTIONAL to its load count (mi vectors + w per row).  With equal
+// shares the CTAs of a partial last slab (m = 28 -> 16 + 12) finished early and idled at the barrier
+// while the full slab's CTAs carried 16/14 of the even load: the dot phase ran 14 % below the update
+// phase's rate for fewer bytes (profiles/r1).
+struct SlabMap {
+  int ny;
+  int start[CV_MAX_PTRS / 16 + 2];  // first CTA of slab by; start[ny] = G
+};
+__host__ __device__ inline void orth_slab_map(int m, int G, int MI, SlabMap &s) {
+  s.ny = (m + MI - 1) / MI;
+  const int total = m + s.ny;
+  int acc = 0;
+  for (int by = 0; by < s.ny; ++by) {
+    s.start[by] = acc;
+    const int mi = (m - by * MI) < MI ? (m - by * MI) : MI;
+    int g = (int)(((long long)G * (mi + 1)) / total);
+    if (g < 1) g = 1;
+    const int remaining = s.ny - 1 - by;  // at least one CTA for each later slab
+    if (acc + g > G - remaining) g = G - remaining - acc;
+    if (by == s.ny - 1) g = G - acc;
+    acc += g;
+  }
+  s.start[s.ny] = G;
+}
+
 #define ORTH_TRACE(slot)                                  \
   do {                                                    \
     if (a.trace && c == 0 && threadIdx.x == 0) {          \
@@ -157,12 +183,15 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
   const int64_t n = a.p.n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   T *wvec = static_cast<T *>(const_cast<void *>(a.p.w[0]));
-  const int ny = (m + MI - 1) / MI;
-  const int gx = G / ny;  // >= 1: the launcher makes G >= ny
+  __shared__ SlabMap s_map;  // the launcher makes G >= ny
+  if (threadIdx.x == 0) orth_slab_map(m, G, MI, s_map);
+  __syncthreads();
+  int my_by = 0;
+  while (my_by + 1 < s_map.ny && c >= s_map.start[my_by + 1]) ++my_by;
   const int64_t npf = n / W;
   const bool tail_mine = (W == 2) && (n & 1);
-  double *p_ww = a.partials + (size_t)ny * MI * NR * gx;  // pass 2: partial |w'|^2 of the by == 0 CTAs
-  double *p_nx = p_ww + 2048;                             // explicit |v_new|^2 partials, one per CTA
+  double *p_ww = a.partials + (size_t)MI * NR * G;  // pass 2: partial |w'|^2 of the by == 0 CTAs
+  double *p_nx = p_ww + 2048;                       // explicit |v_new|^2 partials, one per CTA
   unsigned long long t_prev = 0;
   if (a.trace && c == 0 && threadIdx.x == 0) {
     t_prev = global_ns();
@@ -173,12 +202,13 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
   for (int pass = 1; pass <= 2; ++pass) {
     const int s_h_out = pass == 1 ? a.s_h1 : a.s_h2;
     // ---------------- phase A: this CTA's slab of up to MI basis vectors against w ----------
-    if (c < gx * ny) {
-      // slabs of MI vectors, the last one partial (m = 28 -> 16+12).  Splitting evenly was measured
-      // SLOWER at N = 2e6 (dots 89 us -> 115 us with batches of 8+3 loads per thread, 103 us with
-      // even slabs AND even batches 7+7): the phase is limited by loads in flight per thread, so
-      // full batches of 8 matter more than CTAs of a short slab idling at the barrier
-      const int by = c / gx, bx = c % gx;
+    {
+      // slabs of MI vectors, the last one partial (m = 28 -> 16+12).  Splitting the VECTORS evenly was
+      // measured SLOWER at N = 2e6 (dots 89 us -> 115 us with batches of 8+3 loads per thread, 103 us
+      // with even slabs AND even batches 7+7): the phase is limited by loads in flight per thread, so
+      // the slabs keep full batches of 8 and the CTA shares are balanced instead (SlabMap)
+      const int by = my_by, bx = c - s_map.start[my_by];
+      const int gx = s_map.start[my_by + 1] - s_map.start[my_by];
       const int i0 = by * MI;
       const int mi = min(MI, m - i0);
       const bool want_ww = pass == 2 && by == 0;
@@ -232,7 +262,7 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
         s_vals[v] = s;
       }
       __syncthreads();
-      double *pslab = a.partials + (size_t)by * MI * NR * gx;
+      double *pslab = a.partials + (size_t)MI * NR * s_map.start[by];
       for (int v = threadIdx.x; v < mi * NR; v += blockDim.x) pslab[(size_t)v * gx + bx] = s_vals[v];
       if (want_ww && threadIdx.x == 0) p_ww[bx] = s_vals[MI * NR];
     }
@@ -241,13 +271,14 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
       for (int v = warp; v < m * NR; v += CV_WARPS) {
         const int by = (v / NR) / MI;
         const int local = v - by * MI * NR;
-        const double *pp = a.partials + ((size_t)by * MI * NR + local) * gx;
+        const int gx = s_map.start[by + 1] - s_map.start[by];
+        const double *pp = a.partials + (size_t)MI * NR * s_map.start[by] + (size_t)local * gx;
         double r = ordered_lane_sum(pp, gx, lane);
         r = warp_sum(r);
         if (lane == 0) a.scal[s_h_out + v] = r;
       }
       if (pass == 2 && warp == 0) {
-        double r = ordered_lane_sum(p_ww, gx, lane);
+        double r = ordered_lane_sum(p_ww, s_map.start[1], lane);
         r = warp_sum(r);
         if (lane == 0) a.scal[s_h_out + m * NR] = r;  // travels with h2 in one all-reduce
       }

@@ -169,14 +169,20 @@ const PeerPtrs *cv_peer_ptrs(cv_ctx *ctx) { return ctx->peer ? &ctx->peer->pp : 
 int cv_peer_plan_exchange(cv_ctx *ctx, cv_op *op, bool cplx_, PushArgs *a, int64_t *total_out) {
   cv_peer_state *s = ctx->peer;
   CV_REQUIRE(s && op->peer_halo, "peer halo exchange without peer buffers");
-  const unsigned long long seq = ++s->halo_seq;
-  const int par = (int)(seq & 1ull);
+  const unsigned long long seq = ++s->halo_seq;   // flags: one sequence for all operators (all ranks issue the same)
+  const int par = (int)(++op->halo_count & 1ull);  // buffers: double-buffered PER OPERATOR, so two operators
+                                                   // used alternately (H, Hsolve) still alternate parities
   const size_t eb = cplx_ ? 16 : 8;
   a->nseg = 0;
   a->nflag = 0;
   a->seq = seq;
   a->ticket = ctx->counters + CV_COUNTER_PUSH;
-  unsigned src_mask = 0, dst_mask = 0;
+  // Flags travel in BOTH directions between any two ranks that exchange data in EITHER direction:
+  // a sender may only start exchange k+2 (which overwrites the parity buffer of exchange k at its
+  // peer) after that peer has published exchange k+1, i.e. after the peer's SpMV k has finished
+  // (stream order).  With flags only along the data this held for symmetric patterns alone; a
+  // structurally one-sided coupling (or an asymmetric band) would let the sender run ahead.
+  unsigned send_mask = 0, recv_mask = 0;
   int64_t total = 0;
   if (op->fmt == CV_FMT_DIA) {
     const size_t lo_b = dia_lo_bytes(op), par_b = lo_b + dia_hi_bytes(op);
@@ -189,13 +195,10 @@ int cv_peer_plan_exchange(cv_ctx *ctx, cv_op *op, bool cplx_, PushArgs *a, int64
       g.src_start = r.start;
       g.count = r.count;
       total += r.count;
-      if (!((dst_mask >> r.peer) & 1u)) {
-        dst_mask |= 1u << r.peer;
-        a->flag_dst[a->nflag++] = &s->pp.win[r.peer]->halo_flag[ctx->rank];
-      }
+      send_mask |= 1u << r.peer;
     }
-    for (const auto &r : op->dia_recv_lo) src_mask |= 1u << r.peer;
-    for (const auto &r : op->dia_recv_hi) src_mask |= 1u << r.peer;
+    for (const auto &r : op->dia_recv_lo) recv_mask |= 1u << r.peer;
+    for (const auto &r : op->dia_recv_hi) recv_mask |= 1u << r.peer;
     char *own = static_cast<char *>(op->peer_base[ctx->rank]) + (size_t)par * par_b;
     op->halo_lo_cur = own;
     op->halo_hi_cur = own + lo_b;
@@ -212,12 +215,15 @@ int cv_peer_plan_exchange(cv_ctx *ctx, cv_op *op, bool cplx_, PushArgs *a, int64
         g.src_start = 0;
         g.count = ns;
         total += ns;
-        a->flag_dst[a->nflag++] = &s->pp.win[p]->halo_flag[ctx->rank];
+        send_mask |= 1u << p;
       }
-      if (nr > 0) src_mask |= 1u << p;
+      if (nr > 0) recv_mask |= 1u << p;
     }
     op->halo_cur = static_cast<char *>(op->peer_base[ctx->rank]) + (size_t)par * op->peer_stride[ctx->rank];
   }
+  const unsigned src_mask = send_mask | recv_mask;
+  for (int p = 0; p < ctx->world; ++p)
+    if ((src_mask >> p) & 1u) a->flag_dst[a->nflag++] = &s->pp.win[p]->halo_flag[ctx->rank];
   op->wait.flags = s->pp.win[ctx->rank]->halo_flag;
   op->wait.mask = src_mask;
   op->wait.seq = seq;

@@ -123,7 +123,7 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
   // Recycling (scipy's CU= argument, _gcrotmk.py:227-236, opt-in through cv_ctx_set_recycle): the
   // (c,u) pairs a previous solve left in this workspace are valid for the same operator and shift
   cv_recycle_state &rs = ctx->recycle;
-  const bool reuse = rs.enabled && rs.valid && rs.op == op && rs.cplx == cplx_ && rs.mode == mode && rs.sre == sre &&
+  const bool reuse = rs.enabled && rs.valid && rs.op_id == op->id && rs.cplx == cplx_ && rs.mode == mode && rs.sre == sre &&
                      rs.sim == sim && rs.n == n && rs.work == (const void *)ws.base && rs.m == m && rs.k == k;
   rs.valid = false;
   if (reuse) {
@@ -338,7 +338,10 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
           else
             hcur[i - nc] = h;
         }
-        if (mb[S_FLAG] != 0.0) stats->n_reorth++;
+        if (mb[S_FLAG] != 0.0) {
+          stats->n_reorth++;
+          cv_prof_add_bytes(ctx, 1, (double)(2 * nb + 2) * (double)n * (cplx_ ? 16.0 : 8.0));  // second pass
+        }
         static const int dbg = getenv("EIGB200_DEBUG") ? atoi(getenv("EIGB200_DEBUG")) : 0;
         if (dbg && (mb[S_FLAG] != 0.0 || !(mb[S_NRM] > 0) || (dbg > 1 && j_outer >= dbg))) {
           double q1 = 0, q2 = 0;
@@ -461,7 +464,7 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
       const int W = cplx_ ? 1 : 2;
       int grid = cplx_ ? cv_occ_grid(ctx, (const void *)k_gcrot_update<cplx, 1>, n / W + 1, CV_BLOCK)
                        : cv_occ_grid(ctx, (const void *)k_gcrot_update<double, 2>, n / W + 1, CV_BLOCK);
-      cv_prof_scope prof(ctx, 3, st);
+      cv_prof_scope prof(ctx, 3, st, 11.0 * (double)n * (cplx_ ? 16.0 : 8.0));  // scale_dot 5 + update 6 vectors
       if (cplx_) {
         k_gcrot_scale_dot<cplx, 1><<<grid, CV_BLOCK, 0, st>>>(n, ctx->scalars + S_CX + 1, (cplx *)Cs(slot_new),
                                                              (cplx *)Us(slot_new), (const cplx *)r,
@@ -500,7 +503,7 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
   stats->info = converged ? 0 : (j_outer >= maxiter ? maxiter : j_outer + 1);
   if (rs.enabled) {  // leave the ring for the next solve with this operator and shift
     rs.valid = true;
-    rs.op = op;
+    rs.op_id = op->id;
     rs.cplx = cplx_;
     rs.mode = mode;
     rs.sre = sre;

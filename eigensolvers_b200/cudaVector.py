@@ -32,12 +32,27 @@ class _NpzCheckpoint:
         self._vec = vec
 
     def saveToHDF5(self, filename, additionalInformation=None):
+        """Same call as TTNS.saveToHDF5; format: numpy .npz (h5py is not a dependency) holding
+        `array`, `eigencoefficients`, `eigenvalues` and the status dict as a JSON string.  In
+        row-sharded mode the gather is collective and rank 0 alone writes the file."""
+        import json
         info = additionalInformation or {}
         payload = {"array": self._vec.array}
         for key in ("eigencoefficients", "eigenvalues"):
             if key in info:
                 payload[key] = np.asarray(info[key])
-        np.savez(str(filename) + ".npz", **payload)
+        if "status" in info:
+            def plain(v):
+                if isinstance(v, (np.generic,)):
+                    return v.item()
+                if isinstance(v, np.ndarray):
+                    return v.tolist()
+                if isinstance(v, (list, tuple)):
+                    return [plain(x) for x in v]
+                return v
+            payload["status"] = json.dumps({k: plain(v) for k, v in dict(info["status"]).items()}, default=str)
+        if Runtime.get().rank == 0:
+            np.savez(str(filename) + ".npz", **payload)
 
 
 class CudaVector(AbstractVector):
@@ -122,6 +137,10 @@ class CudaVector(AbstractVector):
         import torch.distributed as dist
         off = rt.offsets_for(self._n_global)
         sizes = [int(off[p + 1] - off[p]) for p in range(rt.world)]
+        if dist.get_backend() != "nccl":   # rendezvous-only group (gloo): gather host copies
+            parts = [None] * rt.world
+            dist.all_gather_object(parts, self._t.cpu().numpy())
+            return np.concatenate(parts)
         width = max(sizes)  # NCCL all_gather needs equal contributions: pad to the largest block
         mine = rt.empty(width, self._cplx)
         mine[:self._nloc] = self._t
@@ -131,6 +150,12 @@ class CudaVector(AbstractVector):
         dist.all_gather_into_tensor(gathered, mine)
         host = gathered.cpu().numpy().reshape(rt.world, width)
         return np.concatenate([host[p, :sizes[p]] for p in range(rt.world)])
+
+    @property
+    def local_array(self):
+        """Host copy of THIS rank's row block only (the whole vector when not sharded): the
+        device-to-host read of a sharded result without the all-gather of `.array`."""
+        return self._t.cpu().numpy()
 
     @property
     def ttns(self):
@@ -270,9 +295,7 @@ class CudaVector(AbstractVector):
         outs = [rt.empty(n, out_cplx) for _ in range(k)]
         vp, _k1 = _lib.ptr_array([t.data_ptr() for t in tens])
         yp, _k2 = _lib.ptr_array([t.data_ptr() for t in outs])
-        # chunks of <= 128 inputs: accumulate by feeding the partial result back as an input
-        if m > 120:
-            raise NotImplementedError("linear combinations of more than 120 vectors")
+        # any m: libcudavec accumulates inputs beyond 96 in further passes
         _lib.check(rt.lib.cv_lincomb(rt.ctx, n, int(out_cplx), int(c_cplx), m, vp, k,
                                      coef.ctypes.data_as(C.POINTER(C.c_double)), yp, rt.stream))
         opts, ng = vectors[0].options, vectors[0]._n_global
@@ -443,22 +466,37 @@ class CudaVector(AbstractVector):
         return overlap
 
     @staticmethod
+    def matvecCount():
+        """Operator applications performed by the shifted solves of this process so far."""
+        return Runtime.get().stats["matvecs"]
+
+    @staticmethod
     def sumOverRanks(vectors, like=None):
         """FEAST with one quadrature node per GPU (contour.py, distribute="nodes"): every rank holds
         the partial contour sum of ITS nodes in full-length vectors (H replicated, runtime NOT in
-        row-sharded mode); one NCCL all-reduce per subspace vector adds them up in place."""
+        row-sharded mode).  The m0 partial sums travel in ONE bucket: one NCCL all-reduce of m0*N
+        doubles per FEAST iteration instead of m0 separate calls; the results are views
+        into the bucket."""
         import torch.distributed as dist
         rt = Runtime.get()
+        t = rt.torch
         if rt.world != 1:
             raise RuntimeError("node-distributed FEAST needs an unsharded runtime (do not call init_distributed)")
-        out = []
+        ref = next((v for v in vectors if v is not None), None)
+        if ref is None:
+            ref = like[0]
+        n, m0 = ref._nloc, len(vectors)
+        bucket = t.zeros(m0 * n, dtype=t.float64, device=rt.device)
         for i, v in enumerate(vectors):
-            if v is None:  # this rank owned no node
-                ref = like[i]
-                t = rt.torch.zeros(ref._nloc, dtype=rt.torch.float64, device=rt.device)
-                v = CudaVector._wrap(t, ref.options, ref._n_global)
-            dist.all_reduce(v._t)
-            out.append(v)
+            if v is not None:  # None: this rank owned no node for vector i
+                if v._cplx:
+                    raise TypeError("sumOverRanks: the contour sums are real (feast.py:91-92)")
+                bucket[i * n:(i + 1) * n].copy_(v._t)
+        dist.all_reduce(bucket)
+        out = []
+        for i in range(m0):
+            proto = vectors[i] if vectors[i] is not None else like[i]
+            out.append(CudaVector._wrap(bucket[i * n:(i + 1) * n], proto.options, proto._n_global))
         return out
 
     def extendBoth(operator, vectors, overlap, opMat):

@@ -112,22 +112,34 @@ class Runtime:
 
     # -- row-sharded mode ----------------------------------------------------------------------
     def init_distributed(self):
-        """Join the NCCL communicator of an already initialised torch.distributed group."""
+        """Enter row-sharded mode over an already initialised torch.distributed group (any backend:
+        the group is only used for rendezvous and object exchange).  Ranks on distinct GPUs get an
+        NCCL communicator (fall-back transport) plus the peer-memory windows; ranks that SHARE a GPU
+        (the 2-process parity tests on one device: NCCL refuses duplicate GPUs, CUDA IPC does not)
+        run on the peer-memory transport alone."""
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return self
         if self.world > 1:
             return self
         rank, world = dist.get_rank(), dist.get_world_size()
-        uid = (C.c_char * 128)()
-        if rank == 0:
-            _lib.check(self.lib.cv_comm_unique_id(uid))
-        box = [bytes(uid)]
-        dist.broadcast_object_list(box, src=0)
-        uid = (C.c_char * 128).from_buffer_copy(box[0])
-        _lib.check(self.lib.cv_comm_init(self.ctx, uid, rank, world))
+        ids = [None] * world
+        props = self.torch.cuda.get_device_properties(self.device)
+        gpu_id = str(getattr(props, "uuid", None) or getattr(props, "pci_bus_id", self.device_index))
+        dist.all_gather_object(ids, (os.uname().nodename, gpu_id))
+        shared_gpu = len(set(ids)) < world
+        if shared_gpu:
+            _lib.check(self.lib.cv_comm_init_peer_only(self.ctx, rank, world))
+        else:
+            uid = (C.c_char * 128)()
+            if rank == 0:
+                _lib.check(self.lib.cv_comm_unique_id(uid))
+            box = [bytes(uid)]
+            dist.broadcast_object_list(box, src=0)
+            uid = (C.c_char * 128).from_buffer_copy(box[0])
+            _lib.check(self.lib.cv_comm_init(self.ctx, uid, rank, world))
         self.rank, self.world = rank, world
-        self._attach_peer_windows()
+        self._attach_peer_windows(required=shared_gpu)
         return self
 
     # -- peer-memory transport (csrc/peer.cu) ---------------------------------------------------
@@ -194,11 +206,14 @@ class Runtime:
             self.lib.cv_peer_free(self.ctx, C.c_void_p(own))
         self._peer_graveyard = []
 
-    def _attach_peer_windows(self):
-        if os.environ.get("EIGB200_TRANSPORT", "peer").lower() != "peer" or self.world > 8:
+    def _attach_peer_windows(self, required=False):
+        if not required and (os.environ.get("EIGB200_TRANSPORT", "peer").lower() != "peer" or self.world > 8):
             return
         ptrs, _ = self.peer_shared_alloc(self.lib.cv_peer_window_bytes())
         if ptrs is None:
+            if required:
+                raise RuntimeError("ranks share a GPU, so NCCL is unavailable, and CUDA IPC peer mapping failed: "
+                                   + self.lib.cv_last_error().decode())
             import warnings
             warnings.warn("CUDA IPC peer mapping unavailable: collectives stay on NCCL "
                           f"({self.lib.cv_last_error().decode()})")
@@ -215,19 +230,53 @@ class Runtime:
         return int(off[self.rank]), int(off[self.rank + 1])
 
     # -- operator cache -------------------------------------------------------------------------
+    @staticmethod
+    def _fingerprint(H):
+        """Cheap content fingerprint of a host matrix: storage addresses, sizes and a strided sample
+        of the values.  The reference evaluates `H @ x` on every call (numpyVector.py:100,152), so an
+        in-place edit of H (H.data *= ..., H -= shift*I, ndarray writes) must not be served from a
+        stale device copy; the sample catches whole-array edits, `invalidate_operator` is the
+        explicit route for anything finer."""
+        try:
+            import scipy.sparse as sp
+            if sp.issparse(H):
+                d = H.data
+                parts = [H.shape, int(H.nnz), d.ctypes.data,
+                         getattr(getattr(H, "indices", None), "ctypes", None) and H.indices.ctypes.data]
+            else:
+                d = np.asarray(H).reshape(-1)
+                parts = [np.shape(H), d.ctypes.data]
+            if d.size:
+                step = max(1, d.size // 4096)
+                parts += [float(d[::step].sum()), float(d[0]), float(d[-1])]
+            return tuple(parts)
+        except Exception:
+            return None
+
+    def invalidate_operator(self, H=None):
+        """Drop the cached device copy of `H` (all cached operators when H is None) — call after
+        editing a matrix in place."""
+        if H is None:
+            self._op_cache.clear()
+        else:
+            self._op_cache.pop(id(H), None)
+
     def operator_for(self, H):
-        """Device operator for a host matrix, cached by object identity."""
+        """Device operator for a host matrix, cached by object identity + content fingerprint."""
         from .operator import DeviceOperator
         if isinstance(H, DeviceOperator):
             return H
+        if getattr(H, "_is_device_operator", False):   # e.g. KroneckerSumOperator
+            return H
         key = id(H)
+        fp = self._fingerprint(H)
         hit = self._op_cache.get(key)
-        if hit is not None and hit[0]() is H:
+        if hit is not None and hit[0]() is H and hit[2] == fp:
             return hit[1]
         op = DeviceOperator.from_host(H, runtime=self)
         try:
             ref = weakref.ref(H, lambda _r, k=key, cache=self._op_cache: cache.pop(k, None))
         except TypeError:  # object without weakref support: keep it alive with the cache entry
             ref = (lambda obj: (lambda: obj))(H)
-        self._op_cache[key] = (ref, op)
+        self._op_cache[key] = (ref, op, fp)
         return op

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CV_ABI_VERSION 1
+#define CV_ABI_VERSION 2
 
 #define CV_OK 0
 #define CV_ERR_CUDA 1        /* a CUDA runtime call failed                              */
@@ -78,17 +78,25 @@ int cv_ctx_set_reorth_eta(cv_ctx *ctx, double eta);
  * [1] barrier + all-reduce, [2] update/normalise/push, [3] barrier before a second pass,
  * [5] launches, [6] passes, [7] halo flags / late push.  Synchronises the device.             */
 int cv_ctx_trace_read(cv_ctx *ctx, double *out16, int reset);
-/* Optional kernel timing with CUDA events on the launching stream, per kernel class
- * (0 = fused SpMV, 1 = tall-skinny dot, 2 = tall-skinny update, 3 = other vector kernels).
- * cv_ctx_profile_read synchronises, returns accumulated milliseconds and launch counts
- * (arrays of 4) and resets the accumulators.                                               */
+/* Optional kernel timing with CUDA events on the launching stream, per kernel class:
+ *   0 fused SpMV   1 fused Arnoldi step / tall-skinny dot   2 tall-skinny update   3 other vector
+ *   kernels   4 Gram-Schmidt against a set   5 linear combinations   6 (bytes only) the SpMV's
+ *   CSR-equivalent bytes 12 nnz + 20 N, next to class 0's bytes of the stored format   7 spare.
+ * cv_ctx_profile_read synchronises, returns for the first n_classes (<= 8) classes the accumulated
+ * milliseconds, launch counts and ALGORITHMIC bytes (SURVEY 8d formulas) of the timed launches,
+ * and resets the accumulators: achieved GB/s = bytes / ms.                                      */
 int cv_ctx_profile(cv_ctx *ctx, int enable);
-int cv_ctx_profile_read(cv_ctx *ctx, double *ms4, uint64_t *count4);
+int cv_ctx_profile_read(cv_ctx *ctx, int n_classes, double *ms, uint64_t *count, double *bytes);
 
 /* ---- distributed mode (row-sharded H) -------------------------------------- */
 /* 128-byte NCCL unique id, created on rank 0 and broadcast by the host language. */
 int cv_comm_unique_id(void *id128);
 int cv_comm_init(cv_ctx *ctx, const void *id128, int rank, int world);
+/* Row-sharded mode WITHOUT an NCCL communicator: every collective must then go through the
+ * peer-memory transport (cv_comm_attach_peers).  For ranks that share one device (NCCL refuses
+ * duplicate GPUs; CUDA IPC works between processes on the same device) — used by the 2-process
+ * parity tests that run on a single GPU.                                                     */
+int cv_comm_init_peer_only(cv_ctx *ctx, int rank, int world);
 int cv_comm_finalize(cv_ctx *ctx);
 /* Sum `count` doubles in place over all ranks (device buffer); no-op for world 1. */
 int cv_comm_allreduce(cv_ctx *ctx, double *buf_dev, int count, void *stream);
@@ -208,18 +216,20 @@ int cv_normalize(cv_ctx *ctx, int64_t n, int cplx, void *x, double *norm_host, v
 /* Y_k = sum_j coef[j*ncol + k] V_j, k < ncol: one pass over the m inputs for all outputs
  * (linearCombination numpyVector.py:105-119 as driven by basisTransformation
  * util_funcs.py:208-231).  coef is a HOST array, row-major m x ncol, interleaved re/im when
- * c_cplx.  Outputs must not alias inputs.                                                  */
+ * c_cplx.  Outputs must not alias inputs.  Any m (inputs beyond 96 are accumulated in further
+ * passes) and any ncol (8 real / 4 complex outputs per pass).                              */
 int cv_lincomb(cv_ctx *ctx, int64_t n, int v_cplx, int c_cplx, int m, const void *const *v_ptrs,
                int ncol, const double *coef_host, void *const *y_ptrs, void *stream);
 /* C[i*b + k] = sum conj?(V_i) W_k : overlapMatrix / matrixRepresentation / pick
- * (numpyVector.py:180-203, util_funcs.py:321-322).  out is HOST, re/im interleaved if cplx. */
+ * (numpyVector.py:180-203, util_funcs.py:321-322).  out is HOST, re/im interleaved if cplx.
+ * Any m and b (chunks of 128 vectors x 4 right-hand sides per launch).                      */
 int cv_tsdot(cv_ctx *ctx, int64_t n, int cplx, int conj, int m, const void *const *v_ptrs,
              int b, const void *const *w_ptrs, double *out_host, void *stream);
 
 /* Sequential modified Gram-Schmidt of x against qs with UNCONJUGATED products and division by
  * q.q, then the LINDEP test x.x > lindep and normalisation (numpyVector.py:121-145).
  * status: 0 = ok (x_out normalised), 1 = linearly dependent (reference returns None).
- * innerprod_host[0..1] = x.x after projection.                                             */
+ * innerprod_host[0..1] = x.x after projection.  Any m (the reference has no cap either).    */
 int cv_gs_against_set(cv_ctx *ctx, int64_t n, int cplx, const void *x_in, int m,
                       const void *const *q_ptrs, double lindep, void *x_out, int *status,
                       double *innerprod_host, void *stream);

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in header_symbols():
         assert hasattr(lib, name), name
-    assert lib.cv_abi_version() == 1
+    assert lib.cv_abi_version() == 2
     assert lib.cv_ctx_scratch_bytes() > 0
     assert isinstance(lib.cv_last_error(), bytes)
 

@@ -267,18 +267,20 @@ def test_c3_oscillator_2e6_against_analytic_levels(rt):
 def test_c2_block_laplacian_1e6_properties(rt):
     """BASELINE config 2 at full size (100^3 Laplacian + random potential, 4 orthogonal guesses,
     test_lanczosBlock-style options): the block converges, the four Ritz pairs have small true
-    residuals, the Ritz vectors are orthonormal and the values bracket sigma like the spectrum
-    measured once with shift-invert ARPACK on the same operator (tools/c2_levels.py)."""
+    residuals, the Ritz vectors are orthonormal and the values are the four levels closest to sigma
+    of the spectrum computed on the CPU with scipy.sparse.linalg.eigsh (ARPACK, which="SA";
+    tools/c2_levels_cpu.py -> tests/golden/c2_levels_100.json — no GPU code involved)."""
     from eigensolvers_b200 import CudaVector, DeviceOperator, hamiltonians as hm
     H = hm.laplacian3d(100, seed=2, W=1.0)
-    sigma = 0.49075197166174706
+    with open(os.path.join(GOLD, "c2_levels_100.json")) as fh:
+        cpu = json.load(fh)
+    sigma = cpu["sigma_k10"]
     o = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 5000, "linear_tol": 1e-4, "linear_atol": 1e-4}}
     guess = hm.orthonormal_block(H.shape[0], 4, seed=3)
     op = DeviceOperator.from_host(H)
     ev, vecs, st = _run(op, [CudaVector(g, dict(o)) for g in guess], sigma, 12, 20, 1e-8)
     assert st["isConverged"]
-    levels = np.array([0.489609364521, 0.489799711054, 0.490025498196, 0.490606676969, 0.491846854308,
-                       0.491963188964, 0.492481772977])
+    levels = np.array(cpu["levels"])
     near = np.sort(levels[np.argsort(abs(levels - sigma))[:4]])
     np.testing.assert_allclose(np.sort(ev[:4]), near, rtol=0, atol=2e-7)
     S = CudaVector.overlapMatrix(vecs[:4])
