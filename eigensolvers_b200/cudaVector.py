@@ -492,7 +492,12 @@ class CudaVector(AbstractVector):
                 if v._cplx:
                     raise TypeError("sumOverRanks: the contour sums are real (feast.py:91-92)")
                 bucket[i * n:(i + 1) * n].copy_(v._t)
-        dist.all_reduce(bucket)
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(bucket)
+        else:  # rendezvous-only group (gloo, ranks sharing one GPU in the tests): stage through the host
+            host = bucket.cpu()
+            dist.all_reduce(host)
+            bucket.copy_(host)
         out = []
         for i in range(m0):
             proto = vectors[i] if vectors[i] is not None else like[i]

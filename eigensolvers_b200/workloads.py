@@ -29,11 +29,16 @@ WORKLOADS = {
     "c2": dict(kind="lap", n=100, nBlock=4, L=12, maxit=20, eConv=1e-8, tol=1e-4, sigma=None,
                deviation="L=12 instead of BASELINE's 6 (sigma sits in a dense part of the spectrum)"),
     "c2small": dict(kind="lap", n=24, nBlock=4, L=10, maxit=20, eConv=1e-8, tol=1e-4, sigma=None),
-    "c4": dict(kind="osc_lindep", dims=(25, 20, 10, 10, 10, 10, 10), nBlock=2, level=8, L=100, maxit=2, eConv=1e-12,
+    # eConv is out of reach on purpose (unittests/test_lanczosLINDEP.py uses 1e-12 with solves at rtol 1e-1
+    # for the same reason): the first outer iteration grows the Krylov list to L*nBlock = 200 vectors,
+    # the restart then hands near-exact Ritz vectors to the solves, Gram-Schmidt returns None and the
+    # driver aborts with NaN eigenvalues (inexact_Lanczos.py:337-345,356-359) — a fixed amount of work
+    # that stresses orthogonalize_against_set / extend* / the m = 200 back-transformation
+    "c4": dict(kind="osc_lindep", dims=(25, 20, 10, 10, 10, 10, 10), nBlock=2, level=8, L=100, maxit=2, eConv=1e-15,
                tol=1e-1),
-    "c4mid": dict(kind="osc_lindep", dims=(25, 20, 10, 10, 10, 10), nBlock=2, level=8, L=100, maxit=2, eConv=1e-12,
+    "c4mid": dict(kind="osc_lindep", dims=(25, 20, 10, 10, 10, 10), nBlock=2, level=8, L=100, maxit=2, eConv=1e-15,
                   tol=1e-1),
-    "c4small": dict(kind="osc_lindep", dims=(10, 8, 6, 5), nBlock=2, level=8, L=100, maxit=2, eConv=1e-12, tol=1e-1),
+    "c4small": dict(kind="osc_lindep", dims=(10, 8, 6, 5), nBlock=2, level=8, L=100, maxit=2, eConv=1e-15, tol=1e-1),
     "c5": dict(kind="osc_feast", dims=(20, 10, 10, 10, 10, 10, 10), m0=6, nc=16, levels=(7, 9), maxit=3, eConv=1e-6,
                tol=1e-2, nBlock=3),
     "c5mid": dict(kind="osc_feast", dims=(20, 10, 10, 10, 10, 10), m0=6, nc=16, levels=(7, 9), maxit=3, eConv=1e-6,

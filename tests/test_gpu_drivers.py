@@ -290,6 +290,40 @@ def test_c2_block_laplacian_1e6_properties(rt):
         assert np.linalg.norm(H @ x - ev[i] * x) < 2e-4
 
 
+def test_c4_lindep_stress_vs_oracle(rt):
+    """BASELINE config 4 at reduced N (eigensolvers_b200/workloads.py `c4small`, the generator of the
+    N = 5e7 workload): two orthogonal near-parallel guesses, solves at rtol 1e-1, L = 100.
+    (a) one outer iteration without convergence: the Krylov list reaches 200 vectors — beyond the
+        128-pointer launch limit, so Gram-Schmidt, extend*, overlapMatrix and the 200 x 200
+        back-transformation all take their chunked paths — and the picked Ritz pairs agree with the
+        CPU oracle's on the same inputs;
+    (b) with a second outer iteration Gram-Schmidt returns None right after the restart and the
+        driver aborts with NaN eigenvalues at the same (outer, inner, iBlock, cumIter) as the oracle."""
+    from eigensolvers_b200 import CudaVector
+    from eigensolvers_b200.workloads import build_workload, solver_options
+    from oracle.numpy_vector import NumpyVectorOracle as NV
+    w = build_workload("c4small")
+    o = solver_options(w)
+    H = w["H"]
+    ev, vecs, st = _run(H, [CudaVector(g.copy(), dict(o)) for g in w["guesses"]], w["sigma"], 100, 1, 1e-15)
+    ev_o, vecs_o, st_o = _run(H, [NV(g.copy(), dict(o)) for g in w["guesses"]], w["sigma"], 100, 1, 1e-15)
+    assert len(vecs) == len(vecs_o) == 200 and st["cumIter"] == st_o["cumIter"] == 99
+    # solves at rtol 1e-1: the oracle's own Ritz pairs have true residuals 6e-5 / 2e-4 here, so two
+    # runs with different inexact-solve trajectories agree to ~residual^2 in the values
+    np.testing.assert_allclose(ev[:2], ev_o[:2], rtol=1e-6)
+    for i in range(2):
+        x = vecs[i].array
+        assert np.linalg.norm(H @ x - ev[i] * x) < 1e-3
+        assert _overlap(x, vecs_o[i].array) >= 1 - 1e-4
+    S = CudaVector.overlapMatrix(vecs)
+    np.testing.assert_allclose(S, np.eye(200), atol=1e-6)
+    ev, vecs, st = _run(H, [CudaVector(g.copy(), dict(o)) for g in w["guesses"]], w["sigma"], 100, 2, 1e-15)
+    ev_o, vecs_o, st_o = _run(H, [NV(g.copy(), dict(o)) for g in w["guesses"]], w["sigma"], 100, 2, 1e-15)
+    assert np.all(np.isnan(ev_o)) and np.all(np.isnan(ev)) and len(ev) == len(ev_o)
+    for k in ("outerIter", "innerIter", "iBlock", "cumIter"):
+        assert st[k] == st_o[k], (k, st[k], st_o[k])
+
+
 def test_feast_sparse_oscillator_against_analytic_levels(rt):
     """C5's structure at reduced N (1e5): FEAST on the sparse oscillator Hamiltonian with complex
     shifted solves (nc = 16 -> the reference's 8 retained nodes), window around two analytic levels."""

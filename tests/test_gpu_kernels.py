@@ -260,3 +260,56 @@ def test_matrix_representation_and_extension(rt, kind):
     S2, M2 = CudaVector.extendBoth(H, vs, S1, M1)
     np.testing.assert_allclose(S2, S, atol=1e-9)
     np.testing.assert_allclose(M2, M, atol=1e-9)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_more_vectors_than_one_launch_takes(rt, cplx):
+    """The reference has no cap on the length of the Krylov list (L*nBlock = 200 in
+    unittests/test_lanczosLINDEP.py's set-up); a launch takes 128 pointers, so linear combinations,
+    tall-skinny products, Gram-Schmidt and the extend* columns chunk internally (m = 150, 257)."""
+    from eigensolvers_b200 import CudaVector
+    n = 3001
+    for m in (150, 257):
+        V = np.stack([_rand(n, cplx, 1000 + i) for i in range(m)], axis=1) / np.sqrt(n)
+        vs = [CudaVector(V[:, i].copy()) for i in range(m)]
+        rng = np.random.default_rng(m)
+        C = rng.standard_normal((m, 3)) + (1j * rng.standard_normal((m, 3)) if cplx else 0)
+        ys = CudaVector.linearCombinationBlock(vs, C)                       # numpyVector.py:105-119
+        for k in range(3):
+            np.testing.assert_allclose(ys[k].array, V @ C[:, k], rtol=1e-11, atol=1e-12)
+        one = CudaVector.linearCombination(vs, C[:, 0])
+        np.testing.assert_allclose(one.array, V @ C[:, 0], rtol=1e-11, atol=1e-12)
+        S = CudaVector.overlapMatrix(vs)                                    # :192-203
+        np.testing.assert_allclose(S, V.conj().T @ V, rtol=1e-10, atol=1e-12)
+        S1 = CudaVector.overlapMatrix(vs[:-1])
+        np.testing.assert_allclose(CudaVector.extendOverlapMatrix(vs, S1), S, atol=1e-9)   # :223-238
+        H = sp.diags([np.linspace(1, 2, n)], [0]).tocsr()
+        M = CudaVector.matrixRepresentation(H, vs)
+        M1 = CudaVector.matrixRepresentation(H, vs[:-1])
+        np.testing.assert_allclose(CudaVector.extendMatrixRepresentation(H, vs, M1), M, atol=1e-9)  # :205-221
+        x = _rand(n, cplx, 7)
+        ref = x.copy()
+        for i in range(m):                                                  # :121-145
+            q = V[:, i]
+            ref = ref - q * (np.dot(ref, q) / np.dot(q, q))
+        ref = ref / np.sqrt(np.dot(ref, ref))
+        out = CudaVector.orthogonalize_against_set(CudaVector(x), vs)
+        np.testing.assert_allclose(out.array, ref, rtol=1e-9, atol=1e-11)
+
+
+def test_operator_cache_sees_in_place_edits(rt):
+    """the reference evaluates H @ x on every call, so an in-place edit of H must not be
+    served from a stale device copy."""
+    from eigensolvers_b200 import CudaVector
+    H = _sym_sparse(600, 0.01, 3)
+    x = np.arange(600.0)
+    X = CudaVector(x)
+    np.testing.assert_allclose(X.applyOp(H).array, H @ x, rtol=1e-13, atol=1e-10)
+    H.data *= 1.5
+    np.testing.assert_allclose(X.applyOp(H).array, H @ x, rtol=1e-13, atol=1e-10)
+    A = np.diag(np.arange(1.0, 51.0))
+    Xd = CudaVector(np.ones(50))
+    np.testing.assert_allclose(Xd.applyOp(A).array, A @ np.ones(50), rtol=1e-13)
+    A[3, 7] = A[7, 3] = 2.0
+    rt.invalidate_operator(A)       # single-entry edits: the explicit route
+    np.testing.assert_allclose(Xd.applyOp(A).array, A @ np.ones(50), rtol=1e-13)
