@@ -42,6 +42,8 @@ SIGNATURES = {
     "cv_ctx_sm_count": (_i, [_vp, _pi]),
     "cv_ctx_set_reorth_eta": (_i, [_vp, _d]),
     "cv_ctx_set_recycle": (_i, [_vp, _i]),
+    "cv_ctx_set_option": (_i, [_vp, C.c_char_p, _d]),
+    "cv_arnoldi_step": (_i, [_vp, _vp, _i64, _i, _i, _pvp, _vp, _d, _d, _pd, _vp]),
     "cv_ctx_trace_read": (_i, [_vp, _pd, _i]),
     "cv_ctx_profile": (_i, [_vp, _i]),
     "cv_ctx_profile_read": (_i, [_vp, _i, _pd, C.POINTER(C.c_uint64), _pd]),

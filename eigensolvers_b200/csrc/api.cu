@@ -50,6 +50,7 @@ extern "C" int cv_ctx_create(int device, void *scratch_dev, size_t scratch_bytes
   c->prepushed_x = nullptr;
   c->prepushed_op = nullptr;
   c->push_early = getenv("EIGB200_PUSH_EARLY") ? atoi(getenv("EIGB200_PUSH_EARLY")) != 0 : true;
+  c->slab_mode = getenv("EIGB200_SLAB") ? atoi(getenv("EIGB200_SLAB")) : 1;
   c->launches = 0;
   c->prof = nullptr;
   c->reorth_eta = getenv("EIGB200_REORTH_ETA") ? atof(getenv("EIGB200_REORTH_ETA")) : 0.1;
@@ -94,6 +95,22 @@ extern "C" int cv_ctx_set_recycle(cv_ctx *ctx, int enable) {
 extern "C" int cv_ctx_set_reorth_eta(cv_ctx *ctx, double eta) {
   CV_REQUIRE(ctx && eta >= 0.0, "cv_ctx_set_reorth_eta: bad argument");
   ctx->reorth_eta = eta;
+  return CV_OK;
+}
+
+extern "C" int cv_ctx_set_option(cv_ctx *ctx, const char *name, double value) {
+  CV_REQUIRE(ctx && name, "cv_ctx_set_option: null argument");
+  if (!strcmp(name, "reorth_eta")) {
+    CV_REQUIRE(value >= 0.0, "cv_ctx_set_option: reorth_eta must be >= 0");
+    ctx->reorth_eta = value;
+  } else if (!strcmp(name, "slab_mode")) {
+    ctx->slab_mode = value != 0.0;
+  } else if (!strcmp(name, "push_early")) {
+    ctx->push_early = value != 0.0;
+  } else {
+    cv_set_error("cv_ctx_set_option: unknown option '%s'", name);
+    return CV_ERR_ARG;
+  }
   return CV_OK;
 }
 
@@ -717,6 +734,7 @@ int cv_orth_step_dev(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int m, const 
   a.push.seq = 0;
   a.push.ticket = ctx->counters + CV_COUNTER_PUSH;
   a.push_early = 0;
+  a.slab_mode = ctx->slab_mode;
   if (ctx->world > 1) {
     a.pp = *cv_peer_ptrs(ctx);
     const bool dia = op->fmt == CV_FMT_DIA;

@@ -125,6 +125,7 @@ struct cv_ctx {
   const void *prepushed_op;
   cv_recycle_state recycle;
   bool push_early;  // fused step pushes unnormalised halo rows from phase B (EIGB200_PUSH_EARLY=0: off)
+  int slab_mode;    // dot-phase work split of the fused Arnoldi step (kernels_orth.cuh SlabMap; EIGB200_SLAB)
 };
 
 // RAII bracket: records an event pair around the launches issued inside its scope

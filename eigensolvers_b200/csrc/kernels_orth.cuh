@@ -42,6 +42,7 @@ struct OrthArgs {
   PushArgs push;   // nseg == 0 && nflag == 0: nothing to push
   int push_early;  // all segments are contiguous ranges: phase B stores the new rows into the peers'
                    // halo buffers as it produces them; otherwise (gather lists) a late push follows
+  int slab_mode;     // phase A work split, see SlabMap
   int publish_late;  // debug: hand the scalars to the host at the END of the kernel
   double *trace;   // [16] accumulated phase times of CTA 0 in ns (tools/orth_trace.py)
   // host mailbox
@@ -136,21 +137,33 @@ __device__ __forceinline__ bool push_pack(const PushArgs &a, int64_t ip, const P
 }
 
 // Phase A splits the basis into slabs of <= MI vectors (the accumulators of one thread) and gives
-// every slab a share of the CTAs PROPORTIONAL to its load count (mi vectors + w per row).  With equal
-// shares the CTAs of a partial last slab (m = 28 -> 16 + 12) finished early and idled at the barrier
-// while the full slab's CTAs carried 16/14 of the even load: the dot phase ran 14 % below the update
-// phase's rate for fewer bytes (profiles/r1).
+// every slab a share of the CTAs PROPORTIONAL to its load count (mi vectors + w per row).
+//   mode 0  full slabs of MI and a remainder (m = 28 -> 16 + 12, m = 33 -> 16 + 16 + 1), loads in
+//           batches of LB: the remainder slab's threads keep few loads in flight (one vector + w at
+//           m = 33), so its CTAs run far below the bandwidth their share assumes and the whole grid
+//           waits for them at the barrier;
+//   mode 1  slabs as even as possible (33 -> 11 + 11 + 11) and, inside a slab of more than LB
+//           vectors, two load batches of equal size (11 -> 6 + 5 instead of 8 + 3): every thread of
+//           the grid has the same, balanced number of loads in flight.
 struct SlabMap {
   int ny;
   int start[CV_MAX_PTRS / 16 + 2];  // first CTA of slab by; start[ny] = G
+  int i0[CV_MAX_PTRS / 16 + 2];     // first basis vector of slab by; i0[ny] = m
 };
-__host__ __device__ inline void orth_slab_map(int m, int G, int MI, SlabMap &s) {
+__host__ __device__ inline void orth_slab_map(int m, int G, int MI, int mode, SlabMap &s) {
   s.ny = (m + MI - 1) / MI;
+  const int base = m / s.ny, rem = m % s.ny;
+  int at = 0;
+  for (int by = 0; by < s.ny; ++by) {
+    s.i0[by] = at;
+    at += mode ? base + (by < rem ? 1 : 0) : ((m - by * MI) < MI ? (m - by * MI) : MI);
+  }
+  s.i0[s.ny] = m;
   const int total = m + s.ny;
   int acc = 0;
   for (int by = 0; by < s.ny; ++by) {
     s.start[by] = acc;
-    const int mi = (m - by * MI) < MI ? (m - by * MI) : MI;
+    const int mi = s.i0[by + 1] - s.i0[by];
     int g = (int)(((long long)G * (mi + 1)) / total);
     if (g < 1) g = 1;
     const int remaining = s.ny - 1 - by;  // at least one CTA for each later slab
@@ -184,7 +197,7 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   T *wvec = static_cast<T *>(const_cast<void *>(a.p.w[0]));
   __shared__ SlabMap s_map;  // the launcher makes G >= ny
-  if (threadIdx.x == 0) orth_slab_map(m, G, MI, s_map);
+  if (threadIdx.x == 0) orth_slab_map(m, G, MI, a.slab_mode, s_map);
   __syncthreads();
   int my_by = 0;
   while (my_by + 1 < s_map.ny && c >= s_map.start[my_by + 1]) ++my_by;
@@ -209,8 +222,11 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
       // the slabs keep full batches of 8 and the CTA shares are balanced instead (SlabMap)
       const int by = my_by, bx = c - s_map.start[my_by];
       const int gx = s_map.start[my_by + 1] - s_map.start[my_by];
-      const int i0 = by * MI;
-      const int mi = min(MI, m - i0);
+      const int i0 = s_map.i0[by];
+      const int mi = s_map.i0[by + 1] - i0;
+      // two load batches: vectors [0, half) accumulate in acc[0..LB), vectors [half, mi) in acc[LB..2LB)
+      // (static register indices; only the pointer selection depends on `half`)
+      const int half = (a.slab_mode && mi > LB) ? (mi + 1) / 2 : (mi < LB ? mi : LB);
       const bool want_ww = pass == 2 && by == 0;
       T acc[MI];
       double ww = 0.0;
@@ -219,16 +235,18 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
       for (int64_t ip = (int64_t)bx * blockDim.x + threadIdx.x; ip < npf; ip += (int64_t)gx * blockDim.x) {
         const Pack<T, W> wv = pk_ld_cg<T, W>(wvec, ip);
 #pragma unroll
-        for (int ib = 0; ib < MI; ib += LB) {
+        for (int b = 0; b < MI / LB; ++b) {
           Pack<T, W> vv[LB];
 #pragma unroll
-          for (int l = 0; l < LB; ++l)
-            vv[l] = (ib + l < mi) ? pk_ld<T, W, false>(static_cast<const T *>(a.p.v[i0 + ib + l]), ip)
-                                  : pk_zero<T, W>();
+          for (int l = 0; l < LB; ++l) {
+            const int idx = b ? half + l : l;
+            const bool ok = b ? idx < mi : l < half;
+            vv[l] = ok ? pk_ld<T, W, false>(static_cast<const T *>(a.p.v[i0 + idx]), ip) : pk_zero<T, W>();
+          }
 #pragma unroll
           for (int l = 0; l < LB; ++l)
 #pragma unroll
-            for (int w = 0; w < W; ++w) Num<T>::fmac(acc[ib + l], vv[l].e[w], wv.e[w]);
+            for (int w = 0; w < W; ++w) Num<T>::fmac(acc[b * LB + l], vv[l].e[w], wv.e[w]);
         }
         if (want_ww) {
 #pragma unroll
@@ -237,7 +255,12 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
       }
       if (tail_mine && bx == 0 && threadIdx.x == 0) {
         const T wt = ld_cg(wvec + (n - 1));
-        for (int i = 0; i < mi; ++i) Num<T>::fmac(acc[i], static_cast<const T *>(a.p.v[i0 + i])[n - 1], wt);
+#pragma unroll
+        for (int sl = 0; sl < MI; ++sl) {
+          const int idx = sl < LB ? sl : half + (sl - LB);
+          const bool ok = sl < LB ? sl < half : idx < mi;
+          if (ok) Num<T>::fmac(acc[sl], static_cast<const T *>(a.p.v[i0 + idx])[n - 1], wt);
+        }
         if (want_ww) ww += Num<T>::abs2(wt);
       }
 #pragma unroll
@@ -263,14 +286,19 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
       }
       __syncthreads();
       double *pslab = a.partials + (size_t)MI * NR * s_map.start[by];
-      for (int v = threadIdx.x; v < mi * NR; v += blockDim.x) pslab[(size_t)v * gx + bx] = s_vals[v];
+      for (int v = threadIdx.x; v < mi * NR; v += blockDim.x) {
+        const int i = v / NR, k = v - i * NR;
+        const int sl = i < half ? i : LB + (i - half);  // accumulator slot of vector i
+        pslab[(size_t)v * gx + bx] = s_vals[sl * NR + k];
+      }
       if (want_ww && threadIdx.x == 0) p_ww[bx] = s_vals[MI * NR];
     }
     ORTH_TRACE(0);
     grid_barrier_with(a.bar, [&]() {
       for (int v = warp; v < m * NR; v += CV_WARPS) {
-        const int by = (v / NR) / MI;
-        const int local = v - by * MI * NR;
+        int by = 0;
+        while (v / NR >= s_map.i0[by + 1]) ++by;
+        const int local = v - s_map.i0[by] * NR;
         const int gx = s_map.start[by + 1] - s_map.start[by];
         const double *pp = a.partials + (size_t)MI * NR * s_map.start[by] + (size_t)local * gx;
         double r = ordered_lane_sum(pp, gx, lane);

@@ -672,6 +672,34 @@ int minres(cv_ctx *ctx, cv_op *op, int mode, double sigma, const double *b, cons
 
 }  // namespace
 
+// The fused Arnoldi step on caller-owned vectors (tests, micro-benchmarks): exactly the launch GCROT's
+// inner loop issues after every operator application.
+extern "C" int cv_arnoldi_step(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int m, const void *const *basis,
+                               void *w, double ww, double eta, double *out_host, void *stream) {
+  CV_REQUIRE(ctx && basis && w && out_host, "cv_arnoldi_step: null argument");
+  CV_REQUIRE(m >= 1 && m <= CV_MAX_PTRS, "cv_arnoldi_step: m=%d outside 1..%d", m, CV_MAX_PTRS);
+  CV_REQUIRE(ctx->world == 1 || op, "cv_arnoldi_step: the sharded step needs the operator (halo push plan)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int NR = cplx_ ? 2 : 1;
+  double *mb = ctx->mailbox;
+  // the SpMV normally leaves {Re<x|y>, Im<x|y>, <y|y>} (this rank's part) in S_W..S_W+2
+  mb[S_W] = mb[S_W + 1] = 0.0;
+  mb[S_W + 2] = ww;
+  mb[S_NRM] = 0.0;
+  CV_CUDA(cudaMemcpyAsync(ctx->scalars + S_NRM, mb + S_NRM, 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+  bool fused = false;
+  CV_TRY(cv_orth_step_dev(ctx, op, n, cplx_, m, basis, w, S_FLAG, S_H2, S_LAG, eta, st, &fused));
+  if (!fused) {
+    cv_set_error("cv_arnoldi_step: the fused step is disabled in this configuration (EIGB200_FUSED=0 or NCCL transport)");
+    return CV_ERR_UNSUPPORTED;
+  }
+  CV_CUDA(cudaStreamSynchronize(st));
+  out_host[0] = mb[S_FLAG];
+  out_host[1] = mb[S_NRM];
+  for (int i = 0; i < m * NR; ++i) out_host[2 + i] = mb[S_H1 + i] + (mb[S_FLAG] != 0.0 ? mb[S_H2 + i] : 0.0);
+  return CV_OK;
+}
+
 extern "C" size_t cv_solve_workspace_bytes(int64_t n, int cplx_, int solver, int m, int k) {
   size_t stride = vec_stride_bytes(n, cplx_);
   if (solver == CV_SOLVER_MINRES) return stride * 5;

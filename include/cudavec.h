@@ -74,6 +74,9 @@ int cv_ctx_set_recycle(cv_ctx *ctx, int enable);
 /* GCROT's Arnoldi step repeats its Gram-Schmidt pass when the first one left less than eta of the
  * vector's norm (Daniel-Gragg-Kaufman-Stewart).  Default 0.1; 0 = never, > 1 = always twice.    */
 int cv_ctx_set_reorth_eta(cv_ctx *ctx, double eta);
+/* Tuning switches by name: "reorth_eta" (as above), "slab_mode" (dot-phase work split of the fused
+ * Arnoldi step: 0 full slabs + remainder, 1 even slabs with balanced load batches), "push_early". */
+int cv_ctx_set_option(cv_ctx *ctx, const char *name, double value);
 /* Accumulated phase times (ns, as seen by CTA 0) of the fused Arnoldi-step kernel: [0] dots,
  * [1] barrier + all-reduce, [2] update/normalise/push, [3] barrier before a second pass,
  * [5] launches, [6] passes, [7] halo flags / late push.  Synchronises the device.             */
@@ -255,6 +258,15 @@ typedef struct cv_solve_stats {
   int n_safe;        /* 1 if the solve switched to the classic re-orthogonalisation threshold */
   int n_recycled;    /* recycled (c,u) pairs this solve started from                          */
 } cv_solve_stats;
+
+/* One fused Arnoldi orthogonalisation step (GCROT's inner loop, _gcrotmk.py:112-141) on caller
+ * vectors: h = basis^H w (classical Gram-Schmidt, repeated when the first pass kept less than eta of
+ * |w|), w <- (w - basis h)/|w'|, one kernel.  ww = |w|^2 of this rank's rows (the fused SpMV supplies
+ * it inside cv_solve).  out_host: [0] 1.0 if the second pass ran, [1] |w'|^2, [2..] h (m values,
+ * re/im interleaved if cplx).  op may be NULL on a single GPU (sharded: the operator whose halo the
+ * step pushes).  For tests and micro-benchmarks; cv_solve launches the same kernel.              */
+int cv_arnoldi_step(cv_ctx *ctx, cv_op *op, int64_t n, int cplx, int m, const void *const *basis,
+                    void *w, double ww, double eta, double *out_host, void *stream);
 
 size_t cv_solve_workspace_bytes(int64_t n, int cplx, int solver, int m, int k);
 /* Solve (sigma I - H) x = b (reverse: (H - sigma I) x = b) with the device restatement of
