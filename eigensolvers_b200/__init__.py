@@ -6,7 +6,7 @@ Importing the package does not touch the GPU; the first CudaVector does.
 """
 from .vector_api import AbstractVector, LINDEP_DEFAULT_VALUE  # noqa: F401
 
-__all__ = ["AbstractVector", "LINDEP_DEFAULT_VALUE", "CudaVector", "DeviceOperator", "Runtime"]
+__all__ = ["AbstractVector", "LINDEP_DEFAULT_VALUE", "CudaVector", "DeviceOperator", "KroneckerSumOperator", "Runtime"]
 
 
 def __getattr__(name):
@@ -16,6 +16,9 @@ def __getattr__(name):
     if name == "DeviceOperator":
         from .operator import DeviceOperator
         return DeviceOperator
+    if name == "KroneckerSumOperator":
+        from .kronecker import KroneckerSumOperator
+        return KroneckerSumOperator
     if name == "Runtime":
         from .runtime import Runtime
         return Runtime

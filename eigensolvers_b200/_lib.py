@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "libcudavec.so")
 CV_OK = 0
 CV_ABI_VERSION = 2
 CV_SPMV_PLAIN, CV_SPMV_SHIFT, CV_SPMV_RSHIFT = 0, 1, 2
-CV_FMT_CSR, CV_FMT_SELL, CV_FMT_DIA = 0, 1, 2
+CV_FMT_CSR, CV_FMT_SELL, CV_FMT_DIA, CV_FMT_KRON = 0, 1, 2, 3
 CV_SOLVER_GCROTMK, CV_SOLVER_MINRES = 0, 1
 CV_ERR_NAMES = {1: "CUDA", 2: "ARG", 3: "UNSUPPORTED", 4: "NUMERIC", 5: "COMM"}
 
@@ -68,6 +68,7 @@ SIGNATURES = {
     "cv_op_set_halo": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "cv_op_create_csr": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _pvp]),
     "cv_op_destroy": (_i, [_vp]),
+    "cv_op_create_kron": (_i, [_vp, _i64, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i64, _i64, _pvp]),
     "cv_op_sell_widths": (_i, [_vp, _vp, _vp, _vp]),
     "cv_op_attach_sell": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "cv_op_attach_dia": (_i, [_vp, _vp, _i, _vp, _vp, _i64, _vp, _i64, _pi, _vp]),

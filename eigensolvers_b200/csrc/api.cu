@@ -737,7 +737,7 @@ int cv_orth_step_dev(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int m, const 
   a.slab_mode = ctx->slab_mode;
   if (ctx->world > 1) {
     a.pp = *cv_peer_ptrs(ctx);
-    const bool dia = op->fmt == CV_FMT_DIA;
+    const bool dia = cv_op_banded(op);
     const bool halo = dia ? (op->lo_len > 0 || op->hi_len > 0) : (op->n_halo > 0 || (!op->send_off.empty() && op->send_off.back() > 0));
     if (halo && op->peer_halo) {
       CV_TRY(cv_peer_plan_exchange(ctx, op, cplx_ != 0, &a.push, nullptr));
@@ -882,6 +882,72 @@ extern "C" int cv_op_create_csr(cv_ctx *ctx, int64_t n_rows, int64_t n_cols, int
   return CV_OK;
 }
 
+extern "C" int cv_op_create_kron(cv_ctx *ctx, int64_t n_rows, int64_t row0, int ndim, const int32_t *dims, int nterm,
+                                 const int32_t *terms7, const double *coef, const double *tab_val_dev,
+                                 const int32_t *tab_col_dev, int tab_len, const double *dtab_dev,
+                                 const int32_t *dtab_off, int dtab_len, int64_t max_offset, int64_t nnz_equiv,
+                                 cv_op **out) {
+  CV_REQUIRE(ctx && out && dims && dtab_dev && dtab_off, "cv_op_create_kron: null argument");
+  CV_REQUIRE(ndim >= 1 && ndim <= KR_MAX_DIM, "cv_op_create_kron: ndim=%d outside 1..%d", ndim, KR_MAX_DIM);
+  CV_REQUIRE(nterm >= 0 && nterm <= KR_MAX_TERMS, "cv_op_create_kron: %d product terms, at most %d", nterm, KR_MAX_TERMS);
+  CV_REQUIRE(nterm == 0 || (terms7 && coef && tab_val_dev && tab_col_dev), "cv_op_create_kron: null term tables");
+  CV_REQUIRE(tab_len >= 0 && tab_len <= KR_MAX_TAB && dtab_len >= 1 && dtab_len <= KR_MAX_DTAB,
+             "cv_op_create_kron: tables of %d / %d entries exceed %d / %d", tab_len, dtab_len, KR_MAX_TAB, KR_MAX_DTAB);
+  CV_REQUIRE(n_rows >= 0 && row0 >= 0 && max_offset >= 0, "cv_op_create_kron: negative size");
+  static uint64_t next_kron_id = (uint64_t)1 << 40;
+  cv_op *op = new cv_op();
+  cv_op::Kron &q = op->kron;
+  long long N = 1;
+  for (int d = ndim - 1; d >= 0; --d) {
+    CV_REQUIRE(dims[d] >= 1 && dims[d] <= 256, "cv_op_create_kron: dims[%d]=%d outside 1..256", d, dims[d]);
+    q.dims[d] = dims[d];
+    q.stride[d] = N;
+    N *= dims[d];
+    int sh = 32;
+    while (((unsigned long long)1 << (sh - 32)) < (unsigned long long)dims[d]) ++sh;
+    q.shift[d] = sh;
+    q.magic[d] = (((unsigned long long)1 << sh) / (unsigned long long)dims[d]) + 1ull;
+    q.dtab_off[d] = dtab_off[d];
+    CV_REQUIRE(dtab_off[d] >= 0 && dtab_off[d] + dims[d] <= dtab_len, "cv_op_create_kron: diagonal table of mode %d out of range", d);
+  }
+  for (int d = ndim; d < KR_MAX_DIM; ++d) q.dims[d] = 1, q.stride[d] = 0, q.magic[d] = 0, q.shift[d] = 0, q.dtab_off[d] = 0;
+  CV_REQUIRE(N < ((long long)1 << 31), "cv_op_create_kron: product basis of %lld states exceeds int32 rows", N);
+  CV_REQUIRE(row0 + n_rows <= N, "cv_op_create_kron: rows [%lld, %lld) outside the product basis", (long long)row0,
+             (long long)(row0 + n_rows));
+  for (int t = 0; t < nterm; ++t) {
+    KronTerm &k = q.term[t];
+    k.mode_a = terms7[7 * t + 0];
+    k.mode_b = terms7[7 * t + 1];
+    k.tab_a = terms7[7 * t + 2];
+    k.tab_b = terms7[7 * t + 3];
+    k.w_a = terms7[7 * t + 4];
+    k.w_b = terms7[7 * t + 5];
+    k.coef = coef[t];
+    CV_REQUIRE(k.mode_a >= 0 && k.mode_a < ndim && k.mode_b >= -1 && k.mode_b < ndim && k.mode_b != k.mode_a,
+               "cv_op_create_kron: term %d has modes (%d, %d)", t, k.mode_a, k.mode_b);
+    CV_REQUIRE(k.w_a >= 1 && k.tab_a >= 0 && k.tab_a + k.w_a * dims[k.mode_a] <= tab_len, "cv_op_create_kron: term %d table A out of range", t);
+    CV_REQUIRE(k.mode_b < 0 || (k.w_b >= 1 && k.tab_b >= 0 && k.tab_b + k.w_b * dims[k.mode_b] <= tab_len),
+               "cv_op_create_kron: term %d table B out of range", t);
+  }
+  q.ndim = ndim;
+  q.nterm = nterm;
+  q.tab_val = tab_val_dev;
+  q.tab_col = tab_col_dev;
+  q.dtab = dtab_dev;
+  q.tab_len = tab_len;
+  q.dtab_len = dtab_len;
+  op->id = ++next_kron_id;
+  op->n_rows = n_rows;
+  op->n_cols = n_rows;
+  op->nnz = nnz_equiv;
+  op->row0 = row0;
+  op->lo_len = (int)max_offset;
+  op->hi_len = (int)max_offset;
+  op->fmt = CV_FMT_KRON;
+  *out = op;
+  return CV_OK;
+}
+
 extern "C" int cv_op_destroy(cv_op *op) {
   delete op;
   return CV_OK;
@@ -901,6 +967,9 @@ extern "C" int cv_op_attach_sell(cv_ctx *ctx, cv_op *op, const int64_t *slice_pt
                                  void *stream) {
   CV_REQUIRE(ctx && op && slice_ptr_dev, "cv_op_attach_sell: null argument");
   CV_REQUIRE(padded_nnz == 0 || (sell_col_dev && sell_val_dev), "cv_op_attach_sell: null storage");
+  CV_REQUIRE(padded_nnz % 64 == 0, "cv_op_attach_sell: slice widths must be even (padded_nnz %% 64 == 0)");
+  CV_REQUIRE(((uintptr_t)sell_val_dev & 15) == 0 && ((uintptr_t)sell_col_dev & 7) == 0,
+             "cv_op_attach_sell: value / column storage must be 16- / 8-byte aligned");
   int64_t ns = (op->n_rows + 31) / 32;
   op->n_slices = ns;
   op->slice_ptr = slice_ptr_dev;
@@ -963,7 +1032,9 @@ extern "C" int cv_op_attach_dia(cv_ctx *ctx, cv_op *op, int n_diag, const int32_
 
 extern "C" int cv_op_set_format(cv_op *op, int fmt) {
   CV_REQUIRE(op, "cv_op_set_format: null operator");
-  CV_REQUIRE(fmt == CV_FMT_CSR || (fmt == CV_FMT_SELL && op->slice_ptr) || (fmt == CV_FMT_DIA && op->dia_val),
+  CV_REQUIRE(op->fmt != CV_FMT_KRON || fmt == CV_FMT_KRON, "cv_op_set_format: a matrix-free operator has no stored format");
+  CV_REQUIRE(fmt == CV_FMT_CSR || (fmt == CV_FMT_SELL && op->slice_ptr) || (fmt == CV_FMT_DIA && op->dia_val) ||
+                 (fmt == CV_FMT_KRON && op->fmt == CV_FMT_KRON),
              "cv_op_set_format: format %d not available", fmt);
   op->fmt = fmt;
   return CV_OK;
@@ -990,6 +1061,7 @@ static int launch_spmv_fmt(cv_ctx *ctx, cv_op *op, const SpmvArgs<T> &a, cudaStr
   // next to SURVEY 8d's format-independent CSR-equivalent figure 12*nnz + 20*N (36*N complex).
   const double vecb = (double)sizeof(T) * (double)op->n_rows * (2.0 + (EPI && a.u1 ? 1.0 : 0.0));
   const double matb = op->fmt == CV_FMT_DIA    ? 8.0 * (double)op->n_diag * (double)op->dia_ld
+                      : op->fmt == CV_FMT_KRON ? 0.0  // matrix-free: tables of a few KB in shared memory
                       : op->fmt == CV_FMT_SELL ? 12.0 * (double)op->padded_nnz + 8.0 * (double)op->n_slices
                                                : 12.0 * (double)op->nnz + 8.0 * (double)(op->n_rows + 1);
   cv_prof_add_bytes(ctx, 6, 12.0 * (double)op->nnz + (sizeof(T) == 16 ? 36.0 : 20.0) * (double)op->n_rows);
@@ -1027,6 +1099,35 @@ static int launch_spmv_fmt(cv_ctx *ctx, cv_op *op, const SpmvArgs<T> &a, cudaStr
       int grid = (int)((!DOTS && need <= 16 * (int64_t)wave) || need < wave ? need : wave);
       kf<<<grid, CV_BLOCK, 0, st>>>(d);
     }
+  } else if (op->fmt == CV_FMT_KRON) {
+    KronArgs<T> k;
+    k.s = a;
+    const cv_op::Kron &q = op->kron;
+    k.ndim = q.ndim;
+    k.nterm = q.nterm;
+    for (int d = 0; d < KR_MAX_DIM; ++d) {
+      k.dims[d] = q.dims[d];
+      k.dtab_off[d] = q.dtab_off[d];
+      k.stride[d] = q.stride[d];
+      k.magic[d] = q.magic[d];
+      k.shift[d] = q.shift[d];
+    }
+    for (int t = 0; t < q.nterm; ++t) k.term[t] = q.term[t];
+    k.tab_val = q.tab_val;
+    k.tab_col = q.tab_col;
+    k.dtab = q.dtab;
+    k.tab_len = q.tab_len;
+    k.dtab_len = q.dtab_len;
+    k.row0 = op->row0;
+    k.halo_lo = static_cast<const T *>(op->peer_halo ? op->halo_lo_cur : op->halo_lo);
+    k.halo_hi = static_cast<const T *>(op->peer_halo ? op->halo_hi_cur : op->halo_hi);
+    k.lo_len = op->lo_len;
+    k.hi_len = op->hi_len;
+    auto kf = k_spmv_kron<T, HALO, EPI, DOTS>;
+    int wave = cv_occ_grid(ctx, (const void *)kf, (int64_t)1 << 40, CV_BLOCK);
+    int64_t need = (op->n_rows + CV_BLOCK - 1) / CV_BLOCK;
+    int grid = (int)(need < wave ? need : wave);  // every CTA stages the tables: one persistent wave
+    kf<<<grid, CV_BLOCK, 0, st>>>(k);
   } else if (op->fmt == CV_FMT_SELL) {
     auto kf = k_spmv_sell<T, HALO, EPI, DOTS>;
     int wave = cv_occ_grid(ctx, (const void *)kf, (int64_t)1 << 40, CV_WARPS);
@@ -1082,7 +1183,7 @@ static int launch_spmv_t(cv_ctx *ctx, cv_op *op, int mode, T sigma, const T *x, 
   a.counter = ctx->counters;
   a.out = dots_slot >= 0 ? ctx->scalars + dots_slot : nullptr;
   a.wait = HaloWait{nullptr, 0u, 0ull, nullptr, nullptr};
-  const bool dia = op->fmt == CV_FMT_DIA;
+  const bool dia = cv_op_banded(op);
   // a rank takes part in the exchange when it RECEIVES (n_halo > 0) or only SENDS (structurally
   // one-sided couplings, an empty row block): the same predicate as cv_orth_step_dev
   const bool halo = dia ? (ctx->world > 1 && (op->lo_len > 0 || op->hi_len > 0))

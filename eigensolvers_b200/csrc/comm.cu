@@ -252,7 +252,7 @@ extern "C" int cv_dia_halo_plan(const int64_t *offsets, int world, int rank, int
 extern "C" int cv_op_set_dia_halo(cv_ctx *ctx, cv_op *op, const int64_t *offsets, void *halo_lo_dev,
                                   void *halo_hi_dev) {
   CV_REQUIRE(ctx && op && offsets, "cv_op_set_dia_halo: null argument");
-  CV_REQUIRE(op->dia_val, "cv_op_set_dia_halo: operator has no DIA storage");
+  CV_REQUIRE(op->dia_val || op->fmt == CV_FMT_KRON, "cv_op_set_dia_halo: operator has neither DIA storage nor a Kronecker form");
   CV_REQUIRE((op->lo_len == 0 || halo_lo_dev) && (op->hi_len == 0 || halo_hi_dev), "cv_op_set_dia_halo: null halo buffer");
   op->halo_lo = halo_lo_dev;
   op->halo_hi = halo_hi_dev;

@@ -5,6 +5,7 @@
 #include "kernels_vec.cuh"
 #include "kernels_spmv.cuh"
 #include "kernels_dia.cuh"
+#include "kernels_kron.cuh"
 #include "kernels_orth.cuh"
 
 struct cv_op {
@@ -33,6 +34,16 @@ struct cv_op {
   struct Range { int peer; int64_t start, count; int band; int64_t dst_off; };
   std::vector<Range> dia_send, dia_recv_lo, dia_recv_hi;
   int64_t row0 = 0, n_global = 0;
+  // matrix-free Kronecker-sum operator (kernels_kron.cuh): geometry + terms; tables are borrowed device arrays
+  struct Kron {
+    int ndim = 0, nterm = 0, tab_len = 0, dtab_len = 0;
+    int dims[KR_MAX_DIM], dtab_off[KR_MAX_DIM], shift[KR_MAX_DIM];
+    long long stride[KR_MAX_DIM];
+    unsigned long long magic[KR_MAX_DIM];
+    KronTerm term[KR_MAX_TERMS];
+    const double *tab_val = nullptr, *dtab = nullptr;
+    const int *tab_col = nullptr;
+  } kron;
   // row-sharded mode: columns >= n_cols - n_halo address the halo buffer
   int64_t n_halo = 0;
   const int32_t *send_idx = nullptr;
@@ -48,6 +59,9 @@ struct cv_op {
   void *halo_cur = nullptr, *halo_lo_cur = nullptr, *halo_hi_cur = nullptr;
   HaloWait wait = {nullptr, 0u, 0ull, nullptr, nullptr};  // what the next sharded SpMV polls (mask 0: nothing)
 };
+
+// formats whose off-block x entries live in the two contiguous band buffers (halo_lo / halo_hi)
+inline bool cv_op_banded(const cv_op *op) { return op->fmt == CV_FMT_DIA || op->fmt == CV_FMT_KRON; }
 
 int cv_check_launch(cv_ctx *ctx, const char *what);
 

@@ -1,0 +1,156 @@
+// kernels_kron.cuh — MATRIX-FREE fused shifted operator application for sum-of-products
+// (Kronecker-sum) Hamiltonians
+//
+//     H = sum_s  c_s  (x)_d  h_{d,s}            h_{d,s} = small 1-D matrices, identity where absent
+//
+// the form the reference's physics Hamiltonians have before they are assembled
+// (unittests/test_lanczosBlockTTNS.py:21-35 `operatorSumOfProduct`; examples/*.op files): mode
+// energies sum_i w_i (n_i + 1/2) are single-factor diagonal terms, couplings c q_i q_j are
+// two-factor terms with tridiagonal q.  SURVEY 8f.3.
+//
+// Nothing of the N x N matrix is stored: the value of every entry is a product of one or two
+// 1-D table entries selected by the mixed-radix digits of the row index, and the column is
+// row + sum_f (col_f - digit_f) * stride_f.  Per launch the kernel moves x once and y once
+// (16 N bytes, fp64) instead of the 8*D*ld + 16 N of diagonal storage or 12 nnz + 20 N of CSR.
+//
+// Tables (device arrays, staged in shared memory by every CTA):
+//   single-factor DIAGONAL terms are pre-summed on the host into one per-mode table
+//       dtab[dtab_off[d] + n_d],   diag(row) = sum_d dtab[..]
+//   every other factor is stored row-wise in ELL form with width w (<= its max non-zeros per row):
+//       tab_col[off + n*w + j], tab_val[off + n*w + j]   (padding: val 0, col n)
+// A term touches w_a (x w_b) entries of x per row; the loops run in 2 x 2 blocks so that four
+// independent gathers are in flight per term (q_i q_j has exactly 2 x 2 entries per row).
+//
+// Row-sharded mode: like the DIA kernel, x entries below / above the owned block live in two
+// contiguous band buffers (lo_len = hi_len = largest |column - row|) filled by the same halo
+// push; rows are decoded from their GLOBAL index row0 + row.
+#pragma once
+#include "kernels_spmv.cuh"
+
+constexpr int KR_MAX_DIM = 8;      // modes
+constexpr int KR_MAX_TERMS = 40;   // product terms (after the diagonal single-factor ones were merged)
+constexpr int KR_MAX_TAB = 2048;   // entries of all ELL tables together (shared memory: 12 B each)
+constexpr int KR_MAX_DTAB = 512;   // entries of the merged diagonal tables
+
+struct KronTerm {
+  int mode_a, mode_b;  // mode_b = -1: single factor
+  int tab_a, tab_b;    // first entry of the factor's ELL table
+  int w_a, w_b;        // ELL widths
+  double coef;
+};
+
+template <typename T>
+struct KronArgs {
+  SpmvArgs<T> s;  // x, y, mode, sigma, epilogue and reduction fields
+  int ndim, nterm;
+  int dims[KR_MAX_DIM];
+  int dtab_off[KR_MAX_DIM];
+  long long stride[KR_MAX_DIM];
+  unsigned long long magic[KR_MAX_DIM];  // floor(2^sh / dim) + 1: n / dim == (n * magic) >> sh for n < 2^31
+  int shift[KR_MAX_DIM];
+  KronTerm term[KR_MAX_TERMS];
+  const double *tab_val;
+  const int *tab_col;
+  const double *dtab;
+  int tab_len, dtab_len;
+  long long row0;
+  const T *halo_lo, *halo_hi;
+  int lo_len, hi_len;
+};
+
+template <typename T, bool HALO>
+__device__ __forceinline__ T kron_x(const KronArgs<T> &a, long long i, int n, double hs) {
+  if (HALO) {
+    if (i < 0) {
+      i += a.lo_len;
+      return Num<T>::scale(ld_gather(a.halo_lo + (i < 0 ? 0 : i)), hs);
+    }
+    if (i >= n) {
+      i -= n;
+      return Num<T>::scale(ld_gather(a.halo_hi + (i >= a.hi_len ? a.hi_len - 1 : i)), hs);
+    }
+    return ld_gather(a.s.x + i);
+  }
+  i = i < 0 ? 0 : (i >= n ? n - 1 : i);  // only reachable through zero padding values
+  return ld_gather(a.s.x + i);
+}
+
+template <typename T, bool HALO, bool EPI, bool DOTS>
+__global__ void __launch_bounds__(CV_BLOCK, sizeof(T) == 8 ? 4 : 3) k_spmv_kron(const __grid_constant__ KronArgs<T> a) {
+  __shared__ double s_val[KR_MAX_TAB];
+  __shared__ int s_col[KR_MAX_TAB];
+  __shared__ double s_dtab[KR_MAX_DTAB];
+  for (int i = threadIdx.x; i < a.tab_len; i += blockDim.x) {
+    s_val[i] = a.tab_val[i];
+    s_col[i] = a.tab_col[i];
+  }
+  for (int i = threadIdx.x; i < a.dtab_len; i += blockDim.x) s_dtab[i] = a.dtab[i];
+  if (HALO) halo_wait_cta(a.s.wait);  // ends in __syncthreads()
+  else __syncthreads();
+  const double hs = HALO ? halo_scale(a.s.wait) : 1.0;
+  const int n = (int)a.s.n_rows;
+  const int stride = gridDim.x * blockDim.x;
+  T d_xy = Num<T>::zero();
+  double d_yy = 0.0;
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride) {
+    // mixed-radix digits of the global row index, 8 bits each, last mode fastest
+    unsigned long long digits = 0ull;
+    double diag = 0.0;
+    {
+      unsigned rem = (unsigned)(a.row0 + row);
+#pragma unroll
+      for (int d = KR_MAX_DIM - 1; d >= 0; --d) {
+        if (d < a.ndim) {
+          const unsigned q = (unsigned)(((unsigned long long)rem * a.magic[d]) >> a.shift[d]);
+          const unsigned dg = rem - q * (unsigned)a.dims[d];
+          rem = q;
+          digits |= (unsigned long long)dg << (8 * d);
+          diag += s_dtab[a.dtab_off[d] + (int)dg];
+        }
+      }
+    }
+    T acc0 = Num<T>::scale(ld_gather(a.s.x + row), diag), acc1 = Num<T>::zero();
+    for (int t = 0; t < a.nterm; ++t) {
+      const KronTerm &k = a.term[t];
+      const int na = (int)((digits >> (8 * k.mode_a)) & 0xFFull);
+      const long long sa = a.stride[k.mode_a];
+      const int ra = k.tab_a + na * k.w_a;
+      if (k.mode_b < 0) {
+        for (int ja = 0; ja < k.w_a; ja += 2) {
+          const bool two = ja + 1 < k.w_a;
+          const double v0 = k.coef * s_val[ra + ja], v1 = two ? k.coef * s_val[ra + ja + 1] : 0.0;
+          const long long o0 = (long long)(s_col[ra + ja] - na) * sa;
+          const long long o1 = two ? (long long)(s_col[ra + ja + 1] - na) * sa : 0ll;
+          const T x0 = kron_x<T, HALO>(a, row + o0, n, hs), x1 = kron_x<T, HALO>(a, row + o1, n, hs);
+          Num<T>::fmar(acc0, v0, x0);
+          Num<T>::fmar(acc1, v1, x1);
+        }
+      } else {
+        const int nb = (int)((digits >> (8 * k.mode_b)) & 0xFFull);
+        const long long sb = a.stride[k.mode_b];
+        const int rb = k.tab_b + nb * k.w_b;
+        for (int ja = 0; ja < k.w_a; ja += 2) {
+          const bool a2 = ja + 1 < k.w_a;
+          const double va0 = k.coef * s_val[ra + ja], va1 = a2 ? k.coef * s_val[ra + ja + 1] : 0.0;
+          const long long oa0 = (long long)(s_col[ra + ja] - na) * sa;
+          const long long oa1 = a2 ? (long long)(s_col[ra + ja + 1] - na) * sa : 0ll;
+          for (int jb = 0; jb < k.w_b; jb += 2) {
+            const bool b2 = jb + 1 < k.w_b;
+            const double vb0 = s_val[rb + jb], vb1 = b2 ? s_val[rb + jb + 1] : 0.0;
+            const long long ob0 = (long long)(s_col[rb + jb] - nb) * sb;
+            const long long ob1 = b2 ? (long long)(s_col[rb + jb + 1] - nb) * sb : 0ll;
+            // four independent gathers
+            const T x00 = kron_x<T, HALO>(a, row + oa0 + ob0, n, hs), x01 = kron_x<T, HALO>(a, row + oa0 + ob1, n, hs);
+            const T x10 = kron_x<T, HALO>(a, row + oa1 + ob0, n, hs), x11 = kron_x<T, HALO>(a, row + oa1 + ob1, n, hs);
+            Num<T>::fmar(acc0, va0 * vb0, x00);
+            Num<T>::fmar(acc1, va0 * vb1, x01);
+            Num<T>::fmar(acc0, va1 * vb0, x10);
+            Num<T>::fmar(acc1, va1 * vb1, x11);
+          }
+        }
+      }
+    }
+    spmv_finish_row<T, EPI, DOTS>(a.s, row, Num<T>::add(acc0, acc1), d_xy, d_yy);
+  }
+  spmv_reduce<T, DOTS>(a.s, d_xy, d_yy);
+}

@@ -89,11 +89,19 @@ __device__ __forceinline__ void spmv_reduce(const SpmvArgs<T> &a, T d_xy, double
 }
 
 // ------------------------------------------------------------------------------------------
-// SELL-32: one warp per slice, one thread per row, 4-way unrolled so that each thread keeps
-// 8 streaming loads + 4 gathers in flight.
+// SELL-32x2: one warp per 32-row slice, one thread per row.  Inside a slice the columns are stored
+// in PAIRS: entry (row lane, column 2p+e) lives at base + (p*32 + lane)*2 + e, so a thread fetches
+// two values with ONE 128-bit load and their two column indices with ONE 64-bit load, and a warp's
+// loads are contiguous 512 B / 256 B segments.  (Scalar loads cost 3 load instructions per
+// non-zero — value, index, gathered x — and the LSU issue rate, not DRAM, bounded the kernel:
+// the one-row DIA kernel showed the same signature, profiles/r1_ncu_c3_full_kernels.csv.  Pairs
+// bring it to 2 per non-zero.)  Slice widths are even (host rounds up); padding entries have
+// value 0 and point at the row's own column.  x is gathered through L1/L2: neighbouring rows of
+// stencil / product-basis Hamiltonians hit the same lines; general sparsity has no reusable tile
+// to stage.  Two pairs per iteration: 4 streaming loads + 4 gathers in flight per thread.
 // ------------------------------------------------------------------------------------------
 template <typename T, bool HALO, bool EPI, bool DOTS>
-__global__ void __launch_bounds__(CV_BLOCK, sizeof(T) == 8 ? 8 : 5)
+__global__ void __launch_bounds__(CV_BLOCK, sizeof(T) == 8 ? 6 : 4)
     k_spmv_sell(const __grid_constant__ SpmvArgs<T> a) {
   if (HALO) halo_wait_cta(a.wait);
   const int lane = threadIdx.x & 31;
@@ -105,27 +113,26 @@ __global__ void __launch_bounds__(CV_BLOCK, sizeof(T) == 8 ? 8 : 5)
   double d_yy = 0.0;
   for (int s = warp0; s < n_slices; s += nwarps) {
     const int64_t base = __ldg(a.slice_ptr + s);
-    const int width = (int)((__ldg(a.slice_ptr + s + 1) - base) >> 5);
-    const double *vp = a.sell_val + base + lane;
-    const int32_t *cp = a.sell_col + base + lane;
+    const int npair = (int)((__ldg(a.slice_ptr + s + 1) - base) >> 6);  // width / 2
+    const double2 *vp = reinterpret_cast<const double2 *>(a.sell_val + base) + lane;
+    const int2 *cp = reinterpret_cast<const int2 *>(a.sell_col + base) + lane;
     T acc0 = Num<T>::zero(), acc1 = Num<T>::zero();
-    int j = 0;
-    for (; j + 4 <= width; j += 4) {
-      int c0 = ld_stream(cp + (j + 0) * 32), c1 = ld_stream(cp + (j + 1) * 32);
-      int c2 = ld_stream(cp + (j + 2) * 32), c3 = ld_stream(cp + (j + 3) * 32);
-      double v0 = ld_stream(vp + (j + 0) * 32), v1 = ld_stream(vp + (j + 1) * 32);
-      double v2 = ld_stream(vp + (j + 2) * 32), v3 = ld_stream(vp + (j + 3) * 32);
-      T x0 = spmv_gather<T, HALO>(a, c0), x1 = spmv_gather<T, HALO>(a, c1);
-      T x2 = spmv_gather<T, HALO>(a, c2), x3 = spmv_gather<T, HALO>(a, c3);
-      Num<T>::fmar(acc0, v0, x0);
-      Num<T>::fmar(acc1, v1, x1);
-      Num<T>::fmar(acc0, v2, x2);
-      Num<T>::fmar(acc1, v3, x3);
+    int p = 0;
+    for (; p + 2 <= npair; p += 2) {
+      const int2 c0 = ld_stream2(cp + (p + 0) * 32), c1 = ld_stream2(cp + (p + 1) * 32);
+      const double2 v0 = ld_stream2(vp + (p + 0) * 32), v1 = ld_stream2(vp + (p + 1) * 32);
+      const T x00 = spmv_gather<T, HALO>(a, c0.x), x01 = spmv_gather<T, HALO>(a, c0.y);
+      const T x10 = spmv_gather<T, HALO>(a, c1.x), x11 = spmv_gather<T, HALO>(a, c1.y);
+      Num<T>::fmar(acc0, v0.x, x00);
+      Num<T>::fmar(acc1, v0.y, x01);
+      Num<T>::fmar(acc0, v1.x, x10);
+      Num<T>::fmar(acc1, v1.y, x11);
     }
-    for (; j < width; ++j) {
-      int c0 = ld_stream(cp + j * 32);
-      double v0 = ld_stream(vp + j * 32);
-      Num<T>::fmar(acc0, v0, spmv_gather<T, HALO>(a, c0));
+    if (p < npair) {
+      const int2 c0 = ld_stream2(cp + p * 32);
+      const double2 v0 = ld_stream2(vp + p * 32);
+      Num<T>::fmar(acc0, v0.x, spmv_gather<T, HALO>(a, c0.x));
+      Num<T>::fmar(acc1, v0.y, spmv_gather<T, HALO>(a, c0.y));
     }
     const int row = s * 32 + lane;
     if (row < (int)a.n_rows) spmv_finish_row<T, EPI, DOTS>(a, row, Num<T>::add(acc0, acc1), d_xy, d_yy);
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(CV_BLOCK)
   const int64_t warp0 = (int64_t)blockIdx.x * CV_WARPS + (threadIdx.x >> 5);
   for (int64_t s = warp0; s < n_slices; s += (int64_t)gridDim.x * CV_WARPS) {
     const int64_t base = slice_ptr[s];
-    const int width = (int)((slice_ptr[s + 1] - base) >> 5);
+    const int width = (int)((slice_ptr[s + 1] - base) >> 5);  // even: the caller rounds the widths up
     const int64_t row = s * 32 + lane;
     int64_t rs = 0, len = 0;
     if (row < n_rows) {
@@ -204,7 +211,7 @@ __global__ void __launch_bounds__(CV_BLOCK)
     // padding points at a column that is certainly valid and already cached by this row
     int32_t pad_col = (int32_t)(row < n_rows ? (row < n_cols ? row : n_cols - 1) : 0);
     for (int j = 0; j < width; ++j) {
-      int64_t dst = base + (int64_t)j * 32 + lane;
+      int64_t dst = base + ((int64_t)(j >> 1) * 32 + lane) * 2 + (j & 1);  // pair-interleaved (k_spmv_sell)
       if (j < len) {
         sell_col[dst] = indices[rs + j];
         sell_val[dst] = data[rs + j];

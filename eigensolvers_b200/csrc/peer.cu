@@ -184,7 +184,7 @@ int cv_peer_plan_exchange(cv_ctx *ctx, cv_op *op, bool cplx_, PushArgs *a, int64
   // structurally one-sided coupling (or an asymmetric band) would let the sender run ahead.
   unsigned send_mask = 0, recv_mask = 0;
   int64_t total = 0;
-  if (op->fmt == CV_FMT_DIA) {
+  if (cv_op_banded(op)) {
     const size_t lo_b = dia_lo_bytes(op), par_b = lo_b + dia_hi_bytes(op);
     for (const auto &r : op->dia_send) {
       CV_REQUIRE(a->nseg < 2 * CV_MAX_WORLD, "DIA halo: too many send ranges");

@@ -5,7 +5,8 @@ ndarrays (stored as CSR with every entry).
 
 Layout in HBM (single GPU, N rows, nnz non-zeros, P padded non-zeros):
     indptr  int64[N+1]   indices int32[nnz]   data float64[nnz]          (CSR)
-    slice_ptr int64[N/32+1]   sell_col int32[P]   sell_val float64[P]    (SELL-32)
+    slice_ptr int64[N/32+1]   sell_col int32[P]   sell_val float64[P]    (SELL-32x2: 32-row slices, even widths,
+                                                                          entry (lane, 2p+e) at base + (p*32+lane)*2 + e)
 In row-sharded mode each rank holds rows [r_p, r_{p+1}) with columns renumbered to
 [0, n_loc) (owned) ++ [n_loc, n_loc + n_halo) (halo, sorted by global column = grouped by owner).
 """
@@ -202,24 +203,29 @@ class DeviceOperator:
         self.padded_nnz = D * n_rows
         self.format = "dia"
         if rt.world > 1:
-            lo_len, hi_len = max(0, -int(table[0])), max(0, int(table[-1]))
-            halo_lo = t.zeros(2 * max(lo_len, 1), dtype=t.float64, device=rt.device)
-            halo_hi = t.zeros(2 * max(hi_len, 1), dtype=t.float64, device=rt.device)
-            self._keep += [halo_lo, halo_hi]
-            off = rt.offsets_for(self.shape[0])
-            _lib.check(rt.lib.cv_op_set_dia_halo(rt.ctx, self.handle, off.ctypes.data, halo_lo.data_ptr(),
-                                                 halo_hi.data_ptr()))
-            r0, r1 = int(off[rt.rank]), int(off[rt.rank + 1])
-            self.n_halo = min(lo_len, r0) + min(hi_len, self.shape[0] - r1)   # band rows held by other ranks
-            if rt.transport == "peer":
-                # neighbours push their boundary rows straight into these buffers over NVLink
-                ptrs, _ = rt.peer_shared_alloc(rt.lib.cv_op_dia_halo_bytes(self.handle))
-                if ptrs is not None:
-                    self._peer_owned.append(ptrs[rt.rank])
-                    arr = (C.c_void_p * rt.world)(*ptrs)
-                    _lib.check(rt.lib.cv_op_set_dia_halo_peers(rt.ctx, self.handle,
-                                                               C.cast(arr, C.POINTER(C.c_void_p))))
+            self._setup_band_halo(max(0, -int(table[0])), max(0, int(table[-1])))
         return True
+
+    def _setup_band_halo(self, lo_len, hi_len):
+        """Row-sharded banded operator (DIA storage or the matrix-free Kronecker form): the x entries
+        below / above the owned block arrive in two contiguous band buffers; with the peer transport
+        the neighbours push their boundary rows straight into them over NVLink."""
+        rt, t = self.rt, self.rt.torch
+        halo_lo = t.zeros(2 * max(lo_len, 1), dtype=t.float64, device=rt.device)
+        halo_hi = t.zeros(2 * max(hi_len, 1), dtype=t.float64, device=rt.device)
+        self._keep += [halo_lo, halo_hi]
+        off = rt.offsets_for(self.shape[0])
+        _lib.check(rt.lib.cv_op_set_dia_halo(rt.ctx, self.handle, off.ctypes.data, halo_lo.data_ptr(),
+                                             halo_hi.data_ptr()))
+        r0, r1 = int(off[rt.rank]), int(off[rt.rank + 1])
+        self.n_halo = min(lo_len, r0) + min(hi_len, self.shape[0] - r1)   # band rows held by other ranks
+        if rt.transport == "peer":
+            ptrs, _ = rt.peer_shared_alloc(rt.lib.cv_op_dia_halo_bytes(self.handle))
+            if ptrs is not None:
+                self._peer_owned.append(ptrs[rt.rank])
+                arr = (C.c_void_p * rt.world)(*ptrs)
+                _lib.check(rt.lib.cv_op_set_dia_halo_peers(rt.ctx, self.handle,
+                                                           C.cast(arr, C.POINTER(C.c_void_p))))
 
     def _build_dia_direct(self, indptr, gcols, data, r0, table):
         """Sharded DIA without the general halo plan: the CSR arrays on the device keep GLOBAL
@@ -247,6 +253,7 @@ class DeviceOperator:
         widths = t.empty(n_slices, dtype=t.int32, device=rt.device)
         _lib.check(rt.lib.cv_op_sell_widths(rt.ctx, self.handle, widths.data_ptr(), rt.stream))
         w = widths.cpu().numpy().astype(np.int64)
+        w = (w + 1) // 2 * 2          # SELL-32x2: columns are stored in pairs (128-bit value loads)
         slice_ptr = np.zeros(n_slices + 1, dtype=np.int64)
         np.cumsum(w * 32, out=slice_ptr[1:])
         padded = int(slice_ptr[-1])

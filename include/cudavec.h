@@ -48,6 +48,7 @@ extern "C" {
 #define CV_FMT_CSR 0
 #define CV_FMT_SELL 1     /* sliced ELL, slice height 32 */
 #define CV_FMT_DIA 2      /* one dense value stream per distinct column offset (banded structure) */
+#define CV_FMT_KRON 3     /* matrix-free sum of Kronecker products of small 1-D matrices           */
 
 /* linear solvers (numpyVector.py:160-163) */
 #define CV_SOLVER_GCROTMK 0
@@ -157,9 +158,11 @@ int cv_op_create_csr(cv_ctx *ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
                      const int64_t *indptr_dev, const int32_t *indices_dev,
                      const double *data_dev, cv_op **out);
 int cv_op_destroy(cv_op *op);
-/* sliced-ELL: (1) per-slice widths (max row length of each 32-row slice) into widths_dev,
- * (2) caller scans them into slice_ptr (int64, n_slices+1, element offsets) and supplies
- * storage, (3) the fill kernel lays the matrix out column-major inside each slice.          */
+/* sliced-ELL (SELL-32x2): (1) per-slice widths (max row length of each 32-row slice) into
+ * widths_dev, (2) the caller rounds them up to EVEN numbers, scans 32*width into slice_ptr (int64,
+ * n_slices+1, element offsets) and supplies storage (values 16-byte, columns 8-byte aligned),
+ * (3) the fill kernel lays every slice out in column PAIRS: entry (row r, column 2p+e) at
+ * slice_ptr[s] + (p*32 + r)*2 + e, so the SpMV reads two values per 128-bit load.            */
 int cv_op_sell_widths(cv_ctx *ctx, cv_op *op, int32_t *widths_dev, void *stream);
 int cv_op_attach_sell(cv_ctx *ctx, cv_op *op, const int64_t *slice_ptr_dev, int64_t padded_nnz,
                       int32_t *sell_col_dev, double *sell_val_dev, void *stream);
@@ -188,6 +191,20 @@ int cv_dia_halo_plan(const int64_t *offsets, int world, int rank, int64_t lo_len
  * [lower band | upper band]); halo_base[p] = rank p's allocation as mapped here.              */
 size_t cv_op_dia_halo_bytes(cv_op *op);
 int cv_op_set_dia_halo_peers(cv_ctx *ctx, cv_op *op, void *const *halo_base /* world */);
+/* Matrix-free sum-of-products operator  H = sum_s coef_s (x)_d h_{d,s}  on the product basis with
+ * `dims` (last mode fastest) — the form of the reference's physics Hamiltonians before assembly
+ * (unittests/test_lanczosBlockTTNS.py:21-35).  Nothing of the N x N matrix is stored.  This rank
+ * applies the rows [row0, row0 + n_rows).  Single-factor DIAGONAL terms arrive pre-summed per mode in
+ * dtab_dev (dtab_off[d] + digit); every other factor is an ELL table of width w (tab_col_dev /
+ * tab_val_dev from entry `tab`; padding: value 0, column = row).  terms7[7*t..] = {mode_a, mode_b
+ * (-1: single factor), tab_a, tab_b, w_a, w_b, 0}, coef[t].  max_offset = largest |column - row| (the
+ * band a row-sharded rank needs from its neighbours; halo set-up as for DIA: cv_op_set_dia_halo,
+ * cv_op_set_dia_halo_peers), nnz_equiv = non-zeros of the equivalent CSR (bookkeeping only).      */
+int cv_op_create_kron(cv_ctx *ctx, int64_t n_rows, int64_t row0, int ndim, const int32_t *dims, int nterm,
+                      const int32_t *terms7, const double *coef, const double *tab_val_dev,
+                      const int32_t *tab_col_dev, int tab_len, const double *dtab_dev,
+                      const int32_t *dtab_off, int dtab_len, int64_t max_offset, int64_t nnz_equiv,
+                      cv_op **out);
 int cv_op_set_format(cv_op *op, int fmt);
 int cv_op_info(cv_op *op, int64_t *n_rows, int64_t *nnz, int64_t *padded_nnz, int *fmt);
 

@@ -313,3 +313,73 @@ def test_operator_cache_sees_in_place_edits(rt):
     A[3, 7] = A[7, 3] = 2.0
     rt.invalidate_operator(A)       # single-entry edits: the explicit route
     np.testing.assert_allclose(Xd.applyOp(A).array, A @ np.ones(50), rtol=1e-13)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_kronecker_sum_operator(rt, cplx):
+    """Matrix-free sum-of-products operator (unittests/test_lanczosBlockTTNS.py:21-35 is the
+    reference's template for such Hamiltonians) against the same operator assembled with scipy.sparse.kron:
+    diagonal and dense single-factor terms, two-factor terms with odd table widths, all three shift modes."""
+    from eigensolvers_b200 import CudaVector, KroneckerSumOperator, _lib
+    rng = np.random.default_rng(11)
+    dims = (5, 4, 6, 3)
+
+    def band(d, bw):
+        h = rng.standard_normal((d, d))
+        h = h + h.T
+        for i in range(d):
+            for j in range(d):
+                if abs(i - j) > bw:
+                    h[i, j] = 0.0
+        return h
+    terms = [(1.3, {0: np.diag(rng.standard_normal(5))}), (0.7, {2: np.diag(rng.standard_normal(6))}),
+             (0.5, {1: band(4, 3)}),                       # dense single factor (width 4)
+             (-0.8, {3: band(3, 1)}),                      # tridiagonal single factor (width 3: odd)
+             (0.25, {0: band(5, 1), 1: band(4, 1)}),       # 3 x 3 entries per row
+             (0.4, {1: band(4, 2), 3: band(3, 0)}),        # 4-wide x diagonal
+             (-0.3, {0: band(5, 2), 3: band(3, 2)})]       # 5 x 3, non-adjacent modes
+    op = KroneckerSumOperator(dims, terms)
+    H = op.to_csr()
+    n = H.shape[0]
+    assert op.shape == (n, n) and op.format == "kron"
+    x = _rand(n, cplx, 5)
+    X = CudaVector(x)
+    np.testing.assert_allclose(X.applyOp(op).array, H @ x, rtol=1e-13, atol=1e-13)
+    y = rt.empty(n, int(cplx))
+    for mode, want in ((_lib.CV_SPMV_SHIFT, 0.37 * x - H @ x), (_lib.CV_SPMV_RSHIFT, H @ x - 0.37 * x)):
+        _lib.check(rt.lib.cv_spmv(rt.ctx, op.handle, int(cplx), mode, 0.37, 0.0, X._ptr, y.data_ptr(), rt.stream))
+        np.testing.assert_allclose(y.cpu().numpy(), want, rtol=1e-13, atol=1e-13)
+    M = CudaVector.matrixRepresentation(op, [X, CudaVector(_rand(n, cplx, 6))])
+    assert M.shape == (2, 2) and abs(M[0, 0] - np.vdot(x, H @ x)) <= 1e-11 * abs(M[0, 0])
+
+
+def test_kronecker_oscillator_equals_assembled_path(rt):
+    """The matrix-free twin of BASELINE config 3's generator: identical to the assembled CSR->DIA path to
+    1e-13 relative in the product, and the same Lanczos eigenpair through the shifted solves."""
+    import warnings
+    from eigensolvers_b200 import CudaVector, DeviceOperator, KroneckerSumOperator, hamiltonians as hm
+    from eigensolvers_b200.hostmath import calculateTarget
+    from eigensolvers_b200.lanczos import inexactLanczosDiagonalization
+    dims = (12, 10, 8, 6, 5)
+    H, om = hm.coupled_oscillators(dims, coupling=0.1, seed=1)
+    dia = DeviceOperator.from_host(H)
+    assert dia.format == "dia"
+    kron = KroneckerSumOperator.coupled_oscillators(dims, coupling=0.1, seed=1)
+    assert kron.nnz == H.nnz and kron.max_offset == int(np.max(np.abs(dia.dia_offsets)))
+    x = _rand(H.shape[0], False, 9)
+    X = CudaVector(x)
+    a, b = X.applyOp(kron).array, X.applyOp(dia).array
+    assert np.max(np.abs(a - b)) <= 1e-13 * np.max(np.abs(b))
+    levels = hm.oscillator_levels(om, 0.1, 40, max_quanta=6)
+    sigma = float(calculateTarget(levels, 8))
+    o = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 5000, "linear_tol": 1e-4, "linear_atol": 0.0}}
+    out = []
+    for op in (kron, dia):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out.append(inexactLanczosDiagonalization(op, CudaVector(x, dict(o)), sigma, 8, 20, 1e-10, writeOut=False))
+        warnings.resetwarnings()
+    (ev_k, Y_k, st_k), (ev_d, Y_d, st_d) = out
+    assert st_k["isConverged"] and st_d["isConverged"]
+    assert abs(ev_k[0] - ev_d[0]) <= 1e-10 * abs(ev_d[0])
+    assert abs(np.vdot(Y_k[0].array, Y_d[0].array)) >= 1 - 1e-8
