@@ -422,17 +422,23 @@ def run_ours(args, w):
     else:
         ev_out = [float(x) for x in np.sort(ev_arr[:w["nBlock"]])]
 
+    feast_profile = getattr(drv, "last_profile", None) if feast else None
+
     # ---- profiled step: per-launch durations (CUDA events on the stream) and algorithmic bytes per class
-    _lib.check(rt.lib.cv_ctx_profile(rt.ctx, 1))
-    read_profile(rt)
-    t_prof = time.perf_counter()
-    one_run(op, guess_dev)
-    torch.cuda.synchronize()
-    t_prof = time.perf_counter() - t_prof
-    pms, pcnt, pby = read_profile(rt)
-    _lib.check(rt.lib.cv_ctx_profile(rt.ctx, 0))
+    if args.no_profile:
+        t_prof, pms, pcnt, pby = 1.0, [0.0] * 8, [0] * 8, [0.0] * 8
+    else:
+        _lib.check(rt.lib.cv_ctx_profile(rt.ctx, 1))
+        read_profile(rt)
+        t_prof = time.perf_counter()
+        one_run(op, guess_dev)
+        torch.cuda.synchronize()
+        t_prof = time.perf_counter() - t_prof
+        pms, pcnt, pby = read_profile(rt)
+        _lib.check(rt.lib.cv_ctx_profile(rt.ctx, 0))
     peak, peak_src = measured_peak()
     share = {PROF_NAMES[i]: pms[i] / (t_prof * 1e3) for i in range(6)}
+    share["host_and_launch_gaps"] = max(0.0, 1.0 - sum(share.values()))   # reference driver's host work (m x m eigh, ...)
     fmt = op.format
     cplx_note = " (complex128 vectors)" if feast else ""
     roof_orth = roofline_entry(
@@ -465,12 +471,33 @@ def run_ours(args, w):
         h2d = world * (nnz_total * 12 + (w["N"] + 1) * 8 + len(guesses_p) * w["N"] * 8)   # replicated inputs
     n_out = len(ev_out) if feast else w["nBlock"]
     d2h = max(n_out, 1) * w["N"] * 8 * (world if feast else 1)                        # each rank reads its own rows
+    feast_tasks = None
+    if feast and world > 1 and args.feast_tasks:
+        # informational: the same FEAST run with the (node, vector) solves spread by measured cost
+        try:
+            vecs_t = [CudaVector._wrap(g.clone(), dict(opts), w["N"]) for g in guess_dev]
+            barrier()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                evt, Yt, stt = drv(op, vecs_t, w["nc"], "legendre", w["eMin"], w["eMax"], w["eConv"], w["maxit"],
+                                   writeOut=False, distribute="tasks")
+            warnings.resetwarnings()
+            q1.record()
+            barrier()
+            feast_tasks = {"seconds": reduce_max(q0.elapsed_time(q1)) * 1e-3, "iterations": int(stt["outerIter"]) + 1,
+                           "profile": getattr(drv, "last_profile", None)}
+            del vecs_t, Yt
+        except Exception as e:
+            feast_tasks = {"error": f"{type(e).__name__}: {e}"}
     del op
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     host_vecs = []
-    for _ in range(args.steps):
+    ev2 = ev
+    for _ in range(0 if args.no_e2e else args.steps):
         flush.add_(1.0)
         op2 = make_operator()                                                # H2D of the Hamiltonian
         gd = [CudaVector(g, dict(opts))._t for g in guesses_p]               # H2D of the guesses
@@ -479,7 +506,7 @@ def run_ours(args, w):
         del op2
     e3.record()
     barrier()
-    e2e_value = reduce_max(e2.elapsed_time(e3)) / args.steps * 1e-3 / n_eig
+    e2e_value = None if args.no_e2e else reduce_max(e2.elapsed_time(e3)) / args.steps * 1e-3 / n_eig
     true_res = None
     if world == 1 and host_vecs:
         x = host_vecs[0]
@@ -555,7 +582,7 @@ def run_ours(args, w):
             line["result"].update(feast_iterations=iters, seconds_per_feast_iteration=ms_per_step * 1e-3 / iters,
                                   window=[w["eMin"], w["eMax"]], analytic_levels_in_window=[
                                       float(x) for x in w["analytic"] if w["eMin"] < x < w["eMax"]],
-                                  feast=getattr(drv, "last_profile", None))
+                                  feast=feast_profile, feast_tasks=feast_tasks)
         print(json.dumps(line), flush=True)
 
     # ---- informational extras, AFTER the headline is out (stderr): GCROT recycling (SciPy's CU=)
@@ -593,6 +620,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--extras", action="store_true", help="informational GCROT-recycling leg after the headline (stderr)")
     ap.add_argument("--no-extras", action="store_true", help="skip the informational matrix-free leg")
+    ap.add_argument("--no-e2e", action="store_true", help="development: skip the end-to-end leg (e2e.value = null)")
+    ap.add_argument("--no-profile", action="store_true", help="development: skip the profiled step (rooflines empty)")
+    ap.add_argument("--feast-tasks", action="store_true", help="c5, N > 1: also time distribute='tasks' (informational)")
     ap.add_argument("--cpu-budget", type=float, default=240.0, help="seconds of CPU sampling for --impl reference")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -17,9 +17,13 @@
 //   single-factor DIAGONAL terms are pre-summed on the host into one per-mode table
 //       dtab[dtab_off[d] + n_d],   diag(row) = sum_d dtab[..]
 //   every other factor is stored row-wise in ELL form with width w (<= its max non-zeros per row):
-//       tab_col[off + n*w + j], tab_val[off + n*w + j]   (padding: val 0, col n)
-// A term touches w_a (x w_b) entries of x per row; the loops run in 2 x 2 blocks so that four
-// independent gathers are in flight per term (q_i q_j has exactly 2 x 2 entries per row).
+//       tab_val[first + n*w + j],  tab_col[first + n*w + j] = (column - n) * stride(mode)   (the
+//       ELEMENT OFFSET the entry contributes to the gathered index; padding: value 0, offset 0)
+// A term touches w_a (x w_b) entries of x per row: index = row + off_a (+ off_b), value =
+// coef * val_a (* val_b); q_i q_j has exactly 2 x 2 entries per row = four independent gathers.
+// (First version: column digits in the tables, 64-bit index arithmetic and clamped gathers — ~40
+// instructions per gathered entry, instruction-bound at 1.03 ms for N = 2e7 against 0.68 ms of the
+// DIA kernel that streams 4 GB of values; profiles/bench_lines/r2_dev_c3_2.json.)
 //
 // Row-sharded mode: like the DIA kernel, x entries below / above the owned block live in two
 // contiguous band buffers (lo_len = hi_len = largest |column - row|) filled by the same halo
@@ -29,7 +33,7 @@
 
 constexpr int KR_MAX_DIM = 8;      // modes
 constexpr int KR_MAX_TERMS = 40;   // product terms (after the diagonal single-factor ones were merged)
-constexpr int KR_MAX_TAB = 2048;   // entries of all ELL tables together (shared memory: 12 B each)
+constexpr int KR_MAX_TAB = 1536;   // entries of all ELL tables together (shared memory: 16 B each)
 constexpr int KR_MAX_DTAB = 512;   // entries of the merged diagonal tables
 
 struct KronTerm {
@@ -50,7 +54,7 @@ struct KronArgs {
   int shift[KR_MAX_DIM];
   KronTerm term[KR_MAX_TERMS];
   const double *tab_val;
-  const int *tab_col;
+  const int *tab_col;  // element offsets, see above
   const double *dtab;
   int tab_len, dtab_len;
   long long row0;
@@ -58,8 +62,10 @@ struct KronArgs {
   int lo_len, hi_len;
 };
 
+// x entry at local index i.  Without a halo every index the tables can produce is inside [0, n)
+// (columns are valid digits; padding entries have offset 0), so the gather needs no clamp.
 template <typename T, bool HALO>
-__device__ __forceinline__ T kron_x(const KronArgs<T> &a, long long i, int n, double hs) {
+__device__ __forceinline__ T kron_x(const KronArgs<T> &a, int i, int n, double hs) {
   if (HALO) {
     if (i < 0) {
       i += a.lo_len;
@@ -69,20 +75,26 @@ __device__ __forceinline__ T kron_x(const KronArgs<T> &a, long long i, int n, do
       i -= n;
       return Num<T>::scale(ld_gather(a.halo_hi + (i >= a.hi_len ? a.hi_len - 1 : i)), hs);
     }
-    return ld_gather(a.s.x + i);
   }
-  i = i < 0 ? 0 : (i >= n ? n - 1 : i);  // only reachable through zero padding values
   return ld_gather(a.s.x + i);
 }
 
+struct __align__(16) KronEntry {  // one ELL slot in shared memory: a single 128-bit LDS
+  double val;
+  int off;  // (column digit - row digit) * stride of the factor's mode, in elements
+  int pad;
+};
+
 template <typename T, bool HALO, bool EPI, bool DOTS>
-__global__ void __launch_bounds__(CV_BLOCK, sizeof(T) == 8 ? 4 : 3) k_spmv_kron(const __grid_constant__ KronArgs<T> a) {
-  __shared__ double s_val[KR_MAX_TAB];
-  __shared__ int s_col[KR_MAX_TAB];
+__global__ void __launch_bounds__(CV_BLOCK, sizeof(T) == 8 ? 5 : 3) k_spmv_kron(const __grid_constant__ KronArgs<T> a) {
+  __shared__ KronEntry s_tab[KR_MAX_TAB];
   __shared__ double s_dtab[KR_MAX_DTAB];
   for (int i = threadIdx.x; i < a.tab_len; i += blockDim.x) {
-    s_val[i] = a.tab_val[i];
-    s_col[i] = a.tab_col[i];
+    KronEntry e;
+    e.val = a.tab_val[i];
+    e.off = a.tab_col[i];
+    e.pad = 0;
+    s_tab[i] = e;
   }
   for (int i = threadIdx.x; i < a.dtab_len; i += blockDim.x) s_dtab[i] = a.dtab[i];
   if (HALO) halo_wait_cta(a.s.wait);  // ends in __syncthreads()
@@ -113,40 +125,39 @@ __global__ void __launch_bounds__(CV_BLOCK, sizeof(T) == 8 ? 4 : 3) k_spmv_kron(
     for (int t = 0; t < a.nterm; ++t) {
       const KronTerm &k = a.term[t];
       const int na = (int)((digits >> (8 * k.mode_a)) & 0xFFull);
-      const long long sa = a.stride[k.mode_a];
       const int ra = k.tab_a + na * k.w_a;
       if (k.mode_b < 0) {
         for (int ja = 0; ja < k.w_a; ja += 2) {
           const bool two = ja + 1 < k.w_a;
-          const double v0 = k.coef * s_val[ra + ja], v1 = two ? k.coef * s_val[ra + ja + 1] : 0.0;
-          const long long o0 = (long long)(s_col[ra + ja] - na) * sa;
-          const long long o1 = two ? (long long)(s_col[ra + ja + 1] - na) * sa : 0ll;
-          const T x0 = kron_x<T, HALO>(a, row + o0, n, hs), x1 = kron_x<T, HALO>(a, row + o1, n, hs);
-          Num<T>::fmar(acc0, v0, x0);
-          Num<T>::fmar(acc1, v1, x1);
+          const KronEntry e0 = s_tab[ra + ja], e1 = s_tab[ra + (two ? ja + 1 : ja)];
+          const T x0 = kron_x<T, HALO>(a, row + e0.off, n, hs), x1 = kron_x<T, HALO>(a, row + e1.off, n, hs);
+          Num<T>::fmar(acc0, k.coef * e0.val, x0);
+          Num<T>::fmar(acc1, two ? k.coef * e1.val : 0.0, x1);
         }
-      } else {
-        const int nb = (int)((digits >> (8 * k.mode_b)) & 0xFFull);
-        const long long sb = a.stride[k.mode_b];
-        const int rb = k.tab_b + nb * k.w_b;
-        for (int ja = 0; ja < k.w_a; ja += 2) {
-          const bool a2 = ja + 1 < k.w_a;
-          const double va0 = k.coef * s_val[ra + ja], va1 = a2 ? k.coef * s_val[ra + ja + 1] : 0.0;
-          const long long oa0 = (long long)(s_col[ra + ja] - na) * sa;
-          const long long oa1 = a2 ? (long long)(s_col[ra + ja + 1] - na) * sa : 0ll;
-          for (int jb = 0; jb < k.w_b; jb += 2) {
-            const bool b2 = jb + 1 < k.w_b;
-            const double vb0 = s_val[rb + jb], vb1 = b2 ? s_val[rb + jb + 1] : 0.0;
-            const long long ob0 = (long long)(s_col[rb + jb] - nb) * sb;
-            const long long ob1 = b2 ? (long long)(s_col[rb + jb + 1] - nb) * sb : 0ll;
-            // four independent gathers
-            const T x00 = kron_x<T, HALO>(a, row + oa0 + ob0, n, hs), x01 = kron_x<T, HALO>(a, row + oa0 + ob1, n, hs);
-            const T x10 = kron_x<T, HALO>(a, row + oa1 + ob0, n, hs), x11 = kron_x<T, HALO>(a, row + oa1 + ob1, n, hs);
-            Num<T>::fmar(acc0, va0 * vb0, x00);
-            Num<T>::fmar(acc1, va0 * vb1, x01);
-            Num<T>::fmar(acc0, va1 * vb0, x10);
-            Num<T>::fmar(acc1, va1 * vb1, x11);
-          }
+        continue;
+      }
+      const int nb = (int)((digits >> (8 * k.mode_b)) & 0xFFull);
+      const int rb = k.tab_b + nb * k.w_b;
+      if (k.w_a == 2 && k.w_b == 2) {  // q_i q_j: exactly 2 x 2 entries per row, four independent gathers
+        const KronEntry a0 = s_tab[ra], a1 = s_tab[ra + 1], b0 = s_tab[rb], b1 = s_tab[rb + 1];
+        const double va0 = k.coef * a0.val, va1 = k.coef * a1.val;
+        const T x00 = kron_x<T, HALO>(a, row + a0.off + b0.off, n, hs), x01 = kron_x<T, HALO>(a, row + a0.off + b1.off, n, hs);
+        const T x10 = kron_x<T, HALO>(a, row + a1.off + b0.off, n, hs), x11 = kron_x<T, HALO>(a, row + a1.off + b1.off, n, hs);
+        Num<T>::fmar(acc0, va0 * b0.val, x00);
+        Num<T>::fmar(acc1, va0 * b1.val, x01);
+        Num<T>::fmar(acc0, va1 * b0.val, x10);
+        Num<T>::fmar(acc1, va1 * b1.val, x11);
+        continue;
+      }
+      for (int ja = 0; ja < k.w_a; ++ja) {
+        const KronEntry ea = s_tab[ra + ja];
+        const double va = k.coef * ea.val;
+        for (int jb = 0; jb < k.w_b; jb += 2) {
+          const bool two = jb + 1 < k.w_b;
+          const KronEntry b0 = s_tab[rb + jb], b1 = s_tab[rb + (two ? jb + 1 : jb)];
+          const T x0 = kron_x<T, HALO>(a, row + ea.off + b0.off, n, hs), x1 = kron_x<T, HALO>(a, row + ea.off + b1.off, n, hs);
+          Num<T>::fmar(acc0, va * b0.val, x0);
+          Num<T>::fmar(acc1, two ? va * b1.val : 0.0, x1);
         }
       }
     }

@@ -24,7 +24,7 @@ import scipy.sparse as sp
 from . import _lib
 from .operator import DeviceOperator
 
-_MAX_TAB, _MAX_DTAB, _MAX_TERMS, _MAX_DIM = 2048, 512, 40, 8
+_MAX_TAB, _MAX_DTAB, _MAX_TERMS, _MAX_DIM = 1536, 512, 40, 8
 
 
 def assemble_csr(dims, terms):
@@ -98,12 +98,12 @@ class KroneckerSumOperator(DeviceOperator):
             nzr = [np.nonzero(h[n])[0] for n in range(d)]
             w = max(1, max(len(c) for c in nzr))
             first = sum(len(v) for v in tab_val)
-            vals, cols = np.zeros((d, w)), np.tile(np.arange(d, dtype=np.int32)[:, None], (1, w))
+            vals, offs = np.zeros((d, w)), np.zeros((d, w), dtype=np.int64)
             for n in range(d):
                 vals[n, :len(nzr[n])] = h[n, nzr[n]]
-                cols[n, :len(nzr[n])] = nzr[n]
+                offs[n, :len(nzr[n])] = (nzr[n] - n) * strides[mode]   # element offset of the gathered entry
             tab_val.append(vals.reshape(-1))
-            tab_col.append(cols.reshape(-1).astype(np.int32))
+            tab_col.append(offs.reshape(-1).astype(np.int32))
             reach = max((int(np.max(np.abs(nzr[n] - n))) if len(nzr[n]) else 0) for n in range(d))
             cache[key] = (first, w, reach, int(sum(len(c) for c in nzr)))
             return cache[key]
@@ -150,8 +150,6 @@ class KroneckerSumOperator(DeviceOperator):
         self.format = "kron"
         self.padded_nnz = 0
         if rt.world > 1:
-            if self.max_offset > self.n_local:
-                raise NotImplementedError("the coupling band is wider than a rank's row block")
             self._setup_band_halo(self.max_offset, self.max_offset)
 
     # the N x N matrix is never stored: bytes a launch must move are x and y only

