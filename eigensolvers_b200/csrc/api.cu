@@ -766,7 +766,8 @@ int cv_orth_step_dev(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int m, const 
     it = occ_cache.emplace(kf, occ).first;
   }
   const int cap = it->second * ctx->sms;
-  const int ny = (m + 15) / 16;
+  const int mi_max = cplx_ ? ORTH_MI<cplx>::value : ORTH_MI<double>::value;
+  const int ny = (m + mi_max - 1) / mi_max;
   int64_t need = (n / W + CV_BLOCK - 1) / CV_BLOCK;
   if (need < ny) need = ny;
   const int grid = (int)(need < cap ? need : cap);

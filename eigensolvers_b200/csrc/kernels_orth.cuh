@@ -147,8 +147,8 @@ __device__ __forceinline__ bool push_pack(const PushArgs &a, int64_t ip, const P
 //           the grid has the same, balanced number of loads in flight.
 struct SlabMap {
   int ny;
-  int start[CV_MAX_PTRS / 16 + 2];  // first CTA of slab by; start[ny] = G
-  int i0[CV_MAX_PTRS / 16 + 2];     // first basis vector of slab by; i0[ny] = m
+  int start[CV_MAX_PTRS / 8 + 2];  // first CTA of slab by; start[ny] = G
+  int i0[CV_MAX_PTRS / 8 + 2];     // first basis vector of slab by; i0[ny] = m
 };
 __host__ __device__ inline void orth_slab_map(int m, int G, int MI, int mode, SlabMap &s) {
   s.ny = (m + MI - 1) / MI;
@@ -174,6 +174,11 @@ __host__ __device__ inline void orth_slab_map(int m, int G, int MI, int mode, Sl
   s.start[s.ny] = G;
 }
 
+template <typename T>
+struct ORTH_MI {
+  static constexpr int value = sizeof(T) == 16 ? 8 : 16;
+};
+
 #define ORTH_TRACE(slot)                                  \
   do {                                                    \
     if (a.trace && c == 0 && threadIdx.x == 0) {          \
@@ -186,7 +191,9 @@ __host__ __device__ inline void orth_slab_map(int m, int G, int MI, int mode, Sl
 template <typename T, int W>
 __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant__ OrthArgs a) {
   constexpr int NR = Num<T>::NRED;
-  constexpr int MI = 16, LB = 8, JB = 8;
+  // accumulators per thread / loads per batch: 16 / 8 for real data; complex128 accumulators take
+  // two registers pairs each, 16 of them spilled at the 80-register budget (3 CTAs/SM), so 8 / 8
+  constexpr int MI = ORTH_MI<T>::value, LB = 8, JB = 8;
   extern __shared__ double s_h[];  // m * NR doubles
   __shared__ double s_part[CV_WARPS][MI * NR + 1];
   __shared__ double s_vals[MI * NR + 1];

@@ -43,6 +43,8 @@ WORKLOADS = {
                tol=1e-2, nBlock=3),
     "c5mid": dict(kind="osc_feast", dims=(20, 10, 10, 10, 10, 10), m0=6, nc=16, levels=(7, 9), maxit=3, eConv=1e-6,
                   tol=1e-2, nBlock=3),
+    "c5midconv": dict(kind="osc_feast", dims=(20, 10, 10, 10, 10, 10), m0=6, nc=16, levels=(7, 9), maxit=16, eConv=1e-6,
+                      tol=1e-2, nBlock=3),
     "c5small": dict(kind="osc_feast", dims=(20, 10, 10, 10, 10), m0=6, nc=16, levels=(7, 9), maxit=3, eConv=1e-6,
                     tol=1e-2, nBlock=3),
 }
