@@ -366,7 +366,7 @@ def run_ours(args, w):
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             if feast:
-                kw = dict(distribute="nodes") if not (world == 1 and use_ref) else {}
+                kw = dict(distribute=args.distribute) if not (world == 1 and use_ref) else {}
                 out = drv(op, vecs, w["nc"], "legendre", w["eMin"], w["eMax"], w["eConv"], w["maxit"], writeOut=False, **kw)
             else:
                 v0 = vecs[0] if w["nBlock"] == 1 else vecs
@@ -416,6 +416,8 @@ def run_ours(args, w):
     n_eig = w["nBlock"]
     value = ms_per_step * 1e-3 / n_eig
     converged = bool(st["isConverged"])
+    if feast:   # feast.py leaves status["isConverged"] untouched; its stop rule is residual < eConv (feast.py:231)
+        converged = st.get("residual") is not None and float(st["residual"]) < w["eConv"]
     ev_arr = np.asarray(ev, dtype=float)
     if feast:
         ev_out = [float(x) for x in np.sort(ev_arr[(ev_arr > w["eMin"]) & (ev_arr < w["eMax"])])]
@@ -482,7 +484,7 @@ def run_ours(args, w):
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
                 evt, Yt, stt = drv(op, vecs_t, w["nc"], "legendre", w["eMin"], w["eMax"], w["eConv"], w["maxit"],
-                                   writeOut=False, distribute="tasks")
+                                   writeOut=False, distribute=args.feast_tasks)
             warnings.resetwarnings()
             q1.record()
             barrier()
@@ -622,7 +624,10 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the informational matrix-free leg")
     ap.add_argument("--no-e2e", action="store_true", help="development: skip the end-to-end leg (e2e.value = null)")
     ap.add_argument("--no-profile", action="store_true", help="development: skip the profiled step (rooflines empty)")
-    ap.add_argument("--feast-tasks", action="store_true", help="c5, N > 1: also time distribute='tasks' (informational)")
+    ap.add_argument("--feast-tasks", default=None, choices=["tasks", "dynamic"],
+                    help="c5, N > 1: also time this distribution of the (node, vector) solves (informational)")
+    ap.add_argument("--distribute", default="nodes", choices=["nodes", "tasks", "dynamic"],
+                    help="c5, N > 1: distribution of the timed run (BASELINE config 5: nodes = one node per GPU)")
     ap.add_argument("--cpu-budget", type=float, default=240.0, help="seconds of CPU sampling for --impl reference")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -13,6 +13,10 @@ right quadrant of the contour — kept as is, it is the parity t
 All (node, vector) solves of one iteration are independent (H replicated on every rank, the
 partial contour sums are added over ranks once per iteration):
   distribute="nodes"   node k is owned by rank k % world (BASELINE config 5: one node per GPU);
+  distribute="dynamic" the (node, vector) solves are PULLED by the ranks from one shared counter
+                       (torch.distributed's store), most expensive first (cost = measured time of the
+                       same solve in the previous iteration, 1/Im(z) in the first): no rank idles while
+                       work is left, whatever the cost estimate is worth.
   distribute="tasks"   the nc/2 * m0 (node, vector) solves are spread over the ranks by longest-
                        processing-time-first with MEASURED costs: nodes close to the real axis need
                        ~2x the matvecs of the far ones, so whole nodes per GPU leave
@@ -74,6 +78,17 @@ def updateQ(Q, im0, Qquad_k, k):
     return Q
 
 
+_CALLS = [0]
+
+
+def _task_order(nodes, m0, cost):
+    """All (node, vector) solves, most expensive first; identical on every rank."""
+    tasks = [(k, i) for k in range(len(nodes)) for i in range(m0)]
+    if cost is None or any(t not in cost for t in tasks):   # first iteration / subspace size changed
+        cost = {(k, i): 1.0 / max(abs(nodes[k][1].imag), 1e-3 * abs(nodes[0][1].imag) + 1e-300) for (k, i) in tasks}
+    return sorted(tasks, key=lambda t: (-cost[t], t))
+
+
 def _assign_tasks(distribute, rank, world, nodes, m0, cost):
     """The (node, vector) solves this rank performs.  Deterministic: every rank computes the same map."""
     tasks = [(k, i) for k in range(len(nodes)) for i in range(m0)]
@@ -109,9 +124,10 @@ def feastDiagonalization(A, Y, nc, quad, eMin, eMax, eConv, maxit, contourEllips
                            status, outFileName, summaryFileName)
     printObj.fileHeader()
     rank, world = 0, 1
-    if distribute not in (None, "nodes", "tasks"):
-        raise ValueError(f"distribute={distribute!r}: expected None, 'nodes' or 'tasks'")
-    if distribute in ("nodes", "tasks"):
+    if distribute not in (None, "nodes", "tasks", "dynamic"):
+        raise ValueError(f"distribute={distribute!r}: expected None, 'nodes', 'tasks' or 'dynamic'")
+    _CALLS[0] += 1        # every rank makes the same sequence of calls: a common name for this call's counters
+    if distribute in ("nodes", "tasks", "dynamic"):
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
             rank, world = dist.get_rank(), dist.get_world_size()
@@ -129,20 +145,36 @@ def feastDiagonalization(A, Y, nc, quad, eMin, eMax, eConv, maxit, contourEllips
             theta = -(np.pi * 0.5) * (gk[k] - 1)  # Polizzi (13)
             z = (eMin + eMax) * 0.5 + eRadius * (math.cos(theta) + contourEllipseFactor * 1.0j * math.sin(theta))
             nodes.append((theta, z))
-        mine = _assign_tasks(distribute, rank, world, nodes, N_SUBSPACE, task_cost)
         spent, work = {}, {}
         counter = getattr(typeClass, "matvecCount", None)
-        for k, (theta, z) in enumerate(nodes):
+
+        def do_task(k, im0, Q):
+            theta, z = nodes[k]
             status["quadrature"] = k
-            for im0 in range(N_SUBSPACE):
-                if (k, im0) not in mine:
-                    continue
-                t_task = time.perf_counter()
-                c0 = counter() if counter else 0
-                Qk = calculateQuadrature(A, Y[im0], z, eRadius, theta, wk[k], contourEllipseFactor)
-                Q = updateQ(Q, im0, Qk, 0 if Q[im0] is None else 1)
-                spent[(k, im0)] = time.perf_counter() - t_task
-                work[(k, im0)] = (counter() - c0) if counter else 0
+            t_task = time.perf_counter()
+            c0 = counter() if counter else 0
+            Qk = calculateQuadrature(A, Y[im0], z, eRadius, theta, wk[k], contourEllipseFactor)
+            Q = updateQ(Q, im0, Qk, 0 if Q[im0] is None else 1)
+            spent[(k, im0)] = time.perf_counter() - t_task
+            work[(k, im0)] = (counter() - c0) if counter else 0
+            return Q
+
+        if distribute == "dynamic" and world > 1:
+            import torch.distributed as dist
+            order = _task_order(nodes, N_SUBSPACE, task_cost)
+            store = dist.distributed_c10d._get_default_store()
+            key = f"eigb200_feast_{_CALLS[0]}_{it}"
+            while True:
+                idx = store.add(key, 1) - 1          # atomic fetch-and-add shared by all ranks
+                if idx >= len(order):
+                    break
+                Q = do_task(order[idx][0], order[idx][1], Q)
+        else:
+            mine = _assign_tasks(distribute if distribute != "dynamic" else None, rank, world, nodes, N_SUBSPACE, task_cost)
+            for k in range(len(nodes)):
+                for im0 in range(N_SUBSPACE):
+                    if (k, im0) in mine:
+                        Q = do_task(k, im0, Q)
         it_prof = {"solve_seconds_this_rank": sum(spent.values()), "matvecs_this_rank": sum(work.values())}
         if world > 1:
             import torch.distributed as dist
@@ -151,7 +183,7 @@ def feastDiagonalization(A, Y, nc, quad, eMin, eMax, eConv, maxit, contourEllips
             it_prof["reduction_seconds"] = time.perf_counter() - t_red
             box = [None] * world
             dist.all_gather_object(box, (spent, work))
-            if distribute == "tasks":
+            if distribute in ("tasks", "dynamic"):
                 task_cost = {}
                 for b in box:
                     task_cost.update(b[0])

@@ -63,7 +63,7 @@ def main():
         g = np.load(os.path.join(ROOT, "tests", "golden", "feast_osc.npz"))
         H, _ = hm.coupled_oscillators((6, 5, 5, 4), coupling=0.1, seed=1)
         o = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 2000, "linear_tol": 1e-2}}
-        for mode in ("nodes", "tasks"):
+        for mode in ("nodes", "tasks", "dynamic"):
             Y = [CudaVector(np.ascontiguousarray(g["Q"][:, i]), dict(o)) for i in range(4)]
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")

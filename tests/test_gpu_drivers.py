@@ -213,8 +213,9 @@ def test_feast(rt):
 
 
 def test_fortran_golden_through_gpu(rt):
-    """Polizzi's Fortran FEAST numbers (unittests/data_fortranCode.out) through the GPU path: the
-    exact solve is replaced by the device GCROT at rtol 1e-13 (no dense direct solver on device)."""
+    """Polizzi's Fortran FEAST numbers (unittests/data_fortranCode.out) through the GPU path with the
+    reference test's own option linearSolver="pardiso" (test_feast_fortran.py:41): CudaVector serves
+    that exact-solve branch with the device GCROT run to rtol 1e-14 (no dense direct solver on device)."""
     import math
     from eigensolvers_b200 import CudaVector
     from eigensolvers_b200.contour import calculateQuadrature, updateQ
@@ -224,7 +225,7 @@ def test_fortran_golden_through_gpu(rt):
     gk, wk = quadraturePointsWeights(8, "legendre", positiveHalf=False)
     theta = np.array([-(np.pi * 0.5) * (x - 1) for x in gk])[order]
     wko = wk[order]
-    tight = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 100, "linear_tol": 1e-13, "linear_atol": 0.0}}
+    tight = {"linearSystemArgs": {"linearSolver": "pardiso"}}
     Y = [CudaVector(g["guess"][i].copy(), tight) for i in range(3)]
     Q = [None] * 3
     for k in range(8):

@@ -161,7 +161,7 @@ def _feast_worker(rank, world, port, q, distribute="nodes"):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("distribute", ["nodes", "tasks"])
+@pytest.mark.parametrize("distribute", ["nodes", "tasks", "dynamic"])
 def test_feast_nodes_distributed_over_two_gloo_ranks(distribute):
     """FEAST with the quadrature nodes (or the individual (node, vector) solves, balanced by measured
     cost) split over 2 ranks (H replicated, one all-reduce of the m0 accumulated vectors per
