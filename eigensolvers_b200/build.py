@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcudavec.so")
 SOURCES = ["cudavec.cu"]
 DEPS = ["api.cu", "comm.cu", "peer.cu", "solvers.cu", "common.cuh", "internal.h", "kernels_vec.cuh",
-        "kernels_spmv.cuh", "kernels_dia.cuh", "kernels_kron.cuh", "kernels_orth.cuh", os.path.join("..", "..", "include", "cudavec.h")]
+        "kernels_spmv.cuh", "kernels_dia.cuh", "kernels_kron.cuh", "kernels_orth.cuh", "kernels_batch.cuh", os.path.join("..", "..", "include", "cudavec.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -55,7 +55,7 @@ constexpr int CV_MAX_RED = 1024;                       // reduction values per l
 
 // scratch layout handed over by the host language (torch tensor), see cv_ctx_create
 constexpr size_t CV_N_COUNTERS = 64;                     // unsigned tickets
-constexpr size_t CV_N_SCALARS = 4096;                    // doubles: reduction results / coefficients
+constexpr size_t CV_N_SCALARS = 8192;                    // doubles: reduction results / coefficients (lock-step solves: one block each)
 constexpr size_t CV_N_PARTIALS = (size_t)1 << 21;        // doubles: per-CTA partial sums (16 MiB)
 
 struct cv_comm_state;  // NCCL state, comm.cu

@@ -7,6 +7,7 @@
 #include "kernels_dia.cuh"
 #include "kernels_kron.cuh"
 #include "kernels_orth.cuh"
+#include "kernels_batch.cuh"
 
 struct cv_op {
   uint64_t id = 0;  // unique per created operator (recycling state is keyed on it)

@@ -19,6 +19,8 @@
 #include <complex>
 #include <vector>
 #include <limits>
+#include <unordered_map>
+#include <algorithm>
 #include "internal.h"
 
 typedef std::complex<double> zc;
@@ -672,6 +674,455 @@ int minres(cv_ctx *ctx, cv_op *op, int mode, double sigma, const double *b, cons
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------
+// LOCK-STEP GCROT(m,k): nrhs independent solves with the same operator advance one Arnoldi step at a
+// time TOGETHER (kernels_batch.cuh): one SpMV reading the matrix once for all of them, one fused
+// orthogonalisation kernel with one grid barrier, one mailbox message per step.  Every solve keeps
+// its own state (the same recurrences, stopping rules and return codes as gcrotmk() above); solves
+// that are between two inner cycles do their outer update with the one-problem kernels and rejoin.
+// Single GPU, fused step only; no recycling.
+// ------------------------------------------------------------------------------------------
+constexpr int S_BLOCK = ((S_END - CV_S_SOLVER + 7) / 8) * 8;  // scalar slots of one problem
+static_assert(CV_S_SOLVER + CV_MAX_BATCH * 2 * S_BLOCK <= CV_S_TRACE, "lock-step scalar blocks exceed the mailbox");
+
+struct LockstepSolve {
+  // problem
+  int cplx_ = 0, mode = 0, m = 20, k = 20, maxiter = 0;
+  double sre = 0, sim = 0, rtol = 0, atol_in = 0;
+  const void *b = nullptr;
+  void *x = nullptr;
+  Workspace ws{nullptr, 0};
+  cv_solve_stats *stats = nullptr;
+  int so = 0;  // offset of this problem's scalar block relative to the one-problem slots
+  // state
+  enum Phase { INNER, DONE } phase = DONE;
+  bool converged = false;
+  double b_norm = 0, beta = 0, atol = 0, atol_inner = 0, eta_now = 0.1, orth_tol = 1e-10, res = NAN;
+  int j_outer = 0, nc = 0, ml = 0, j = 0;
+  bool breakdown = false;
+  std::vector<int> cu_slots, free_slots;
+  std::vector<zc> Q, R, B, y, hy, by, hcur;
+  int ldq = 0, ldr = 0, ldb = 0;
+  std::vector<const void *> basis;
+
+  void *r() const { return ws.vec(0); }
+  void *V(int i) const { return ws.vec(1 + i); }
+  void *Cs(int i) const { return ws.vec(1 + (m + k + 1) + i); }
+  void *Us(int i) const { return ws.vec(1 + (m + k + 1) + (k + 1) + i); }
+
+  int start(cv_ctx *ctx, cv_op *op, const void *x0, cudaStream_t st) {
+    const int64_t n = op->n_rows;
+    const size_t ebytes = cplx_ ? 16 : 8;
+    double *mb = ctx->mailbox;
+    for (int i = k; i >= 0; --i) free_slots.push_back(i);
+    if (x0) {
+      if (x0 != x) CV_TRY(cv_copy(ctx, n, cplx_, x0, x, (void *)st));
+      CV_TRY(cv_spmv_dev(ctx, op, cplx_, mode, sre, sim, x, r(), -1.0, 1.0, b, true, -1, st));
+      stats->n_matvec++;
+    } else {
+      CV_CUDA(cudaMemsetAsync(x, 0, (size_t)n * ebytes, st));
+      CV_TRY(cv_copy(ctx, n, cplx_, b, r(), (void *)st));
+    }
+    CV_TRY(cv_nrm2sq_dev(ctx, n, cplx_, b, S_BETA + so + 1, st));
+    CV_TRY(cv_nrm2sq_dev(ctx, n, cplx_, r(), S_BETA + so, st));
+    CV_TRY(cv_fetch_scalars(ctx, S_BETA + so, 2, st));
+    stats->n_sync++;
+    b_norm = sqrt(mb[S_BETA + so + 1]);
+    beta = sqrt(mb[S_BETA + so]);
+    stats->b_norm = b_norm;
+    if (!std::isfinite(b_norm)) {
+      cv_set_error("gcrotmk: RHS must contain only finite numbers");
+      return CV_ERR_ARG;
+    }
+    atol = std::max(atol_in, rtol * b_norm);
+    if (b_norm == 0.0) {
+      CV_TRY(cv_copy(ctx, n, cplx_, b, x, (void *)st));
+      converged = true;
+      phase = DONE;
+      return CV_OK;
+    }
+    const int mlmax = m + k;
+    Q.assign((size_t)(mlmax + 2) * (mlmax + 2), zc(0));
+    R.assign((size_t)(mlmax + 2) * (mlmax + 1), zc(0));
+    B.assign((size_t)(k + 1) * (mlmax + 1), zc(0));
+    y.assign(mlmax + 2, zc(0));
+    hy.assign(mlmax + 2, zc(0));
+    by.assign(k + 1, zc(0));
+    hcur.assign(mlmax + 2, zc(0));
+    ldq = mlmax + 2, ldr = mlmax + 1, ldb = mlmax + 1;
+    basis.assign(CV_MAX_PTRS, nullptr);
+    eta_now = ctx->reorth_eta;
+    orth_tol = std::min(1e-7, std::max(1e-10, 1e-3 * std::max(rtol, b_norm > 0 ? atol_in / b_norm : 0.0)));
+    j_outer = 0;
+    return outer_begin(ctx, op, st);
+  }
+
+  // top of the outer loop (_gcrotmk.py:374-393): stopping test, then the start of an inner cycle
+  int outer_begin(cv_ctx *ctx, cv_op *op, cudaStream_t st) {
+    const int64_t n = op->n_rows;
+    double *mb = ctx->mailbox;
+    if (j_outer >= maxiter) {
+      phase = DONE;
+      return CV_OK;
+    }
+    const double beta_tol = std::max(atol, rtol * b_norm);
+    if (beta <= beta_tol && j_outer > 0) {
+      CV_TRY(cv_spmv_dev(ctx, op, cplx_, mode, sre, sim, x, r(), -1.0, 1.0, b, true, S_W + so, st));
+      stats->n_matvec++;
+      CV_TRY(cv_fetch_scalars(ctx, S_W + so, 3, st));
+      stats->n_sync++;
+      beta = sqrt(mb[S_W + so + 2]);
+    }
+    stats->resid = beta;
+    if (beta <= beta_tol) {
+      converged = true;
+      phase = DONE;
+      return CV_OK;
+    }
+    nc = (int)cu_slots.size();
+    ml = m + std::max(k - nc, 0);
+    atol_inner = std::max(atol, rtol * b_norm) / beta;
+    CV_TRY(scal_real(ctx, n, cplx_, 1.0 / beta, r(), V(0), st));
+    for (int c = 0; c < nc; ++c) basis[c] = Cs(cu_slots[c]);
+    std::fill(Q.begin(), Q.end(), zc(0));
+    std::fill(R.begin(), R.end(), zc(0));
+    std::fill(B.begin(), B.end(), zc(0));
+    Q[0] = 1.0;
+    j = 0;
+    breakdown = false;
+    res = NAN;
+    phase = INNER;
+    return CV_OK;
+  }
+
+  // after the batched step: Hessenberg column from the mailbox, Givens update, inner stopping test.
+  // Returns true when the inner cycle ended.
+  bool step_consume(cv_ctx *ctx) {
+    const double eps = std::numeric_limits<double>::epsilon();
+    const double *mb = ctx->mailbox;
+    const int nb = nc + j + 1;
+    stats->n_matvec++;
+    if (j > 0) {
+      const double dev = fabs(mb[S_LAG + so] - 1.0);
+      if (dev > stats->orth_loss) stats->orth_loss = dev;
+      if (dev > orth_tol && eta_now > 0.0 && eta_now < 0.70710678118654752) {
+        eta_now = 0.70710678118654752;
+        stats->n_safe++;
+      }
+    }
+    const bool two = mb[S_FLAG + so] != 0.0;
+    for (int i = 0; i < nb; ++i) {
+      zc h = cplx_ ? zc(mb[S_H1 + so + 2 * i], mb[S_H1 + so + 2 * i + 1]) : zc(mb[S_H1 + so + i], 0.0);
+      if (two) h += cplx_ ? zc(mb[S_H2 + so + 2 * i], mb[S_H2 + so + 2 * i + 1]) : zc(mb[S_H2 + so + i], 0.0);
+      if (i < nc)
+        B[(size_t)i * ldb + j] = h;
+      else
+        hcur[i - nc] = h;
+    }
+    if (two) stats->n_reorth++;
+    const double w_norm = sqrt(mb[S_W + so + 2]);
+    const double hlast = sqrt(mb[S_NRM + so]);
+    hcur[j + 1] = hlast;
+    if (!(hlast > eps * w_norm)) breakdown = true;
+    std::vector<zc> u(j + 2);
+    for (int c = 0; c <= j; ++c) {
+      zc sacc = 0;
+      for (int i = 0; i <= j; ++i) sacc += std::conj(Q[(size_t)i * ldq + c]) * hcur[i];
+      u[c] = sacc;
+    }
+    u[j + 1] = hcur[j + 1];
+    for (int i = 0; i <= j + 1; ++i) Q[(size_t)i * ldq + (j + 1)] = 0, Q[(size_t)(j + 1) * ldq + i] = 0;
+    Q[(size_t)(j + 1) * ldq + (j + 1)] = 1.0;
+    {
+      const zc a = u[j], bb = u[j + 1];
+      const double na = std::abs(a), nbb = std::abs(bb);
+      const double rho = std::hypot(na, nbb);
+      double c;
+      zc sg;
+      if (rho == 0.0 || !std::isfinite(rho)) {
+        c = 1.0;
+        sg = 0.0;
+      } else if (na == 0.0) {
+        c = 0.0;
+        sg = std::conj(bb) / nbb;
+      } else {
+        c = na / rho;
+        sg = (a / na) * std::conj(bb) / rho;
+      }
+      const zc rjj = c * a + sg * bb;
+      for (int i = 0; i < j; ++i) R[(size_t)i * ldr + j] = u[i];
+      R[(size_t)j * ldr + j] = rjj;
+      R[(size_t)(j + 1) * ldr + j] = 0.0;
+      for (int i = 0; i <= j + 1; ++i) {
+        zc qa = Q[(size_t)i * ldq + j], qb = Q[(size_t)i * ldq + j + 1];
+        Q[(size_t)i * ldq + j] = qa * c + qb * std::conj(sg);
+        Q[(size_t)i * ldq + j + 1] = -qa * sg + qb * c;
+      }
+    }
+    res = std::abs(Q[j + 1]);
+    if (res < atol_inner || breakdown) return true;
+    if (j + 1 >= ml) return true;  // python's loop variable stays at ml-1 after a full sweep
+    ++j;
+    return false;
+  }
+
+  // end of an inner cycle: least squares, new (c,u) pair, residual/solution update (_gcrotmk.py:179,430-499)
+  int outer_end(cv_ctx *ctx, cv_op *op, cudaStream_t st) {
+    const int64_t n = op->n_rows;
+    const int NR = cplx_ ? 2 : 1;
+    double *mb = ctx->mailbox;
+    if (!std::isfinite(R[(size_t)j * ldr + j].real()) || !std::isfinite(R[(size_t)j * ldr + j].imag())) {
+      phase = DONE;  // scipy: LinAlgError inside _fgmres, gcrotmk reports failure
+      ++j_outer;
+      return CV_OK;
+    }
+    const int ncol = j + 1;
+    for (int i = ncol - 1; i >= 0; --i) {
+      zc sacc = std::conj(Q[i]);
+      for (int c = i + 1; c < ncol; ++c) sacc -= R[(size_t)i * ldr + c] * y[c];
+      zc d = R[(size_t)i * ldr + i];
+      y[i] = (std::abs(d) > 0.0) ? sacc / d : zc(0);
+    }
+    for (int i = 0; i < ncol; ++i) y[i] *= beta;
+    for (int c = 0; c < nc; ++c) {
+      zc sacc = 0;
+      for (int i = 0; i < ncol; ++i) sacc += B[(size_t)c * ldb + i] * y[i];
+      by[c] = sacc;
+    }
+    std::vector<zc> ry(ncol + 1);
+    for (int i = 0; i <= ncol; ++i) {
+      zc sacc = 0;
+      for (int c = 0; c < ncol; ++c) sacc += R[(size_t)i * ldr + c] * y[c];
+      ry[i] = sacc;
+    }
+    for (int i = 0; i <= ncol; ++i) {
+      zc sacc = 0;
+      for (int c = 0; c <= ncol; ++c) sacc += Q[(size_t)i * ldq + c] * ry[c];
+      hy[i] = sacc;
+    }
+    CV_REQUIRE(!free_slots.empty(), "gcrotmk: CU ring exhausted");
+    const int slot_new = free_slots.back();
+    {
+      const int mt = ncol + 1 + nc;
+      std::vector<const void *> src(mt);
+      const int cs = cplx_ ? 2 : 1;
+      std::vector<double> coef((size_t)mt * 2 * cs, 0.0);
+      for (int i = 0; i <= ncol; ++i) {
+        src[i] = V(i);
+        zc cu = (i < ncol) ? y[i] : zc(0);
+        coef[(i * 2 + 0) * cs] = cu.real();
+        coef[(i * 2 + 1) * cs] = hy[i].real();
+        if (cplx_) {
+          coef[(i * 2 + 0) * cs + 1] = cu.imag();
+          coef[(i * 2 + 1) * cs + 1] = hy[i].imag();
+        }
+      }
+      for (int c = 0; c < nc; ++c) {
+        src[ncol + 1 + c] = Us(cu_slots[c]);
+        coef[((ncol + 1 + c) * 2 + 0) * cs] = -by[c].real();
+        if (cplx_) coef[((ncol + 1 + c) * 2 + 0) * cs + 1] = -by[c].imag();
+      }
+      void *outs[2] = {Us(slot_new), Cs(slot_new)};
+      CV_TRY(cv_lincomb_launch(ctx, n, cplx_, cplx_, mt, src.data(), 2, coef.data(), 2, 0, outs, S_CX + so, st));
+    }
+    CV_TRY(cv_fetch_scalars(ctx, S_CX + so, 2, st));
+    stats->n_sync++;
+    const double alpha = 1.0 / sqrt(mb[S_CX + so + 1]);
+    ++j_outer;
+    if (std::isfinite(alpha)) {
+      const int W = cplx_ ? 1 : 2;
+      int grid = cplx_ ? cv_occ_grid(ctx, (const void *)k_gcrot_update<cplx, 1>, n / W + 1, CV_BLOCK)
+                       : cv_occ_grid(ctx, (const void *)k_gcrot_update<double, 2>, n / W + 1, CV_BLOCK);
+      cv_prof_scope prof(ctx, 3, st, 11.0 * (double)n * (cplx_ ? 16.0 : 8.0));
+      double *sc = ctx->scalars;
+      if (cplx_) {
+        k_gcrot_scale_dot<cplx, 1><<<grid, CV_BLOCK, 0, st>>>(n, sc + S_CX + so + 1, (cplx *)Cs(slot_new), (cplx *)Us(slot_new),
+                                                             (const cplx *)r(), ctx->partials, ctx->counters, sc + S_GAMMA + so);
+        CV_TRY(cv_check_launch(ctx, "gcrot_scale_dot"));
+        k_gcrot_update<cplx, 1><<<grid, CV_BLOCK, 0, st>>>(n, sc + S_GAMMA + so, (const cplx *)Cs(slot_new), (const cplx *)Us(slot_new),
+                                                          (cplx *)r(), (cplx *)x, ctx->partials, ctx->counters, sc + S_BETA + so);
+      } else {
+        k_gcrot_scale_dot<double, 2><<<grid, CV_BLOCK, 0, st>>>(n, sc + S_CX + so + 1, (double *)Cs(slot_new), (double *)Us(slot_new),
+                                                               (const double *)r(), ctx->partials, ctx->counters, sc + S_GAMMA + so);
+        CV_TRY(cv_check_launch(ctx, "gcrot_scale_dot"));
+        k_gcrot_update<double, 2><<<grid, CV_BLOCK, 0, st>>>(n, sc + S_GAMMA + so, (const double *)Cs(slot_new),
+                                                            (const double *)Us(slot_new), (double *)r(), (double *)x, ctx->partials,
+                                                            ctx->counters, sc + S_BETA + so);
+      }
+      CV_TRY(cv_check_launch(ctx, "gcrot_update"));
+      free_slots.pop_back();
+      while ((int)cu_slots.size() >= k && !cu_slots.empty()) {
+        free_slots.push_back(cu_slots.front());
+        cu_slots.erase(cu_slots.begin());
+      }
+      cu_slots.push_back(slot_new);
+      CV_TRY(cv_fetch_scalars(ctx, S_BETA + so, 1, st));
+      stats->n_sync++;
+      beta = sqrt(mb[S_BETA + so]);
+    }
+    return outer_begin(ctx, op, st);
+  }
+};
+
+// batched SpMV of the active problems: one pass over a DIA matrix for all of them, else one launch each
+template <typename T>
+int lockstep_spmv(cv_ctx *ctx, cv_op *op, int mode, int np, LockstepSolve *const *P, cudaStream_t st) {
+  const bool one_pass = op->fmt == CV_FMT_DIA && np >= 2;
+  if (!one_pass) {
+    for (int q = 0; q < np; ++q)
+      CV_TRY(cv_spmv_dev(ctx, op, sizeof(T) == 16, mode, P[q]->sre, P[q]->sim, P[q]->V(P[q]->j), P[q]->V(P[q]->j + 1), 1.0, 0.0,
+                         nullptr, false, CV_S_TS + 3 * q, st));
+    return CV_OK;
+  }
+  const double vecb = (double)sizeof(T) * (double)op->n_rows * 2.0 * np;
+  cv_prof_add_bytes(ctx, 6, np * (12.0 * (double)op->nnz + (sizeof(T) == 16 ? 36.0 : 20.0) * (double)op->n_rows));
+  cv_prof_scope prof(ctx, 0, st, 8.0 * (double)op->n_diag * (double)op->dia_ld + vecb);
+#define GO_NB(NB)                                                                                   \
+  {                                                                                                 \
+    DiaBatchArgs<T, NB> a;                                                                          \
+    a.dia_val = op->dia_val;                                                                        \
+    a.ld = op->dia_ld;                                                                              \
+    a.n_diag = op->n_diag;                                                                          \
+    a.n_rows = (int)op->n_rows;                                                                     \
+    a.mode = mode;                                                                                  \
+    for (int d = 0; d < CV_MAX_DIAG; ++d) a.off[d] = d < op->n_diag ? op->dia_off[d] : 0;           \
+    for (int q = 0; q < NB; ++q) {                                                                  \
+      a.x[q] = static_cast<const T *>(P[q]->V(P[q]->j));                                            \
+      a.y[q] = static_cast<T *>(P[q]->V(P[q]->j + 1));                                              \
+      a.sigma[q] = Num<T>::make(P[q]->sre, P[q]->sim);                                              \
+    }                                                                                               \
+    a.partials = ctx->partials;                                                                     \
+    a.counter = ctx->counters;                                                                      \
+    a.out = ctx->scalars + CV_S_TS;                                                                 \
+    auto kf = k_spmv_dia_nb<T, NB>;                                                                 \
+    int wave = cv_occ_grid(ctx, (const void *)kf, (int64_t)1 << 40, CV_BLOCK);                      \
+    int64_t need = (op->n_rows + CV_BLOCK - 1) / CV_BLOCK;                                          \
+    kf<<<(int)(need < wave ? need : wave), CV_BLOCK, 0, st>>>(a);                                   \
+  }
+  switch (np) {
+    case 2: GO_NB(2); break;
+    case 3: GO_NB(3); break;
+    default: GO_NB(4); break;
+  }
+#undef GO_NB
+  return cv_check_launch(ctx, "spmv_dia_nb");
+}
+
+int lockstep_orth(cv_ctx *ctx, int64_t n, int cplx_, int np, LockstepSolve *const *P, cudaStream_t st) {
+  OrthBatchArgs a;
+  a.nprob = np;
+  a.n = n;
+  a.o_flag = S_FLAG;
+  a.o_nrm = S_NRM;
+  a.o_w = S_W;
+  a.o_h1 = S_H1;
+  a.o_h2 = S_H2;
+  a.o_lag = S_LAG;
+  int W = cplx_ ? 1 : 2, mmax = 1;
+  for (int q = 0; q < np; ++q) {
+    LockstepSolve &s = *P[q];
+    const int nb = s.nc + s.j + 1;
+    CV_REQUIRE(nb <= CV_BATCH_PTRS, "lock-step solve: %d basis vectors exceed %d", nb, CV_BATCH_PTRS);
+    s.basis[s.nc + s.j] = s.V(s.j);
+    for (int i = 0; i < nb; ++i) {
+      a.prob[q].v[i] = s.basis[i];
+      if ((uintptr_t)s.basis[i] & 15) W = 1;
+    }
+    a.prob[q].w = s.V(s.j + 1);
+    a.prob[q].m = nb;
+    a.prob[q].sbase = s.so;   // offsets o_* are the absolute one-problem slots: block base = so
+    a.prob[q].s_w_src = CV_S_TS + 3 * q;
+    a.prob[q].eta2 = s.eta_now * s.eta_now;
+    if (nb > mmax) mmax = nb;
+    cv_prof_add_bytes(ctx, 1, (double)(2 * nb + 3) * (double)n * (cplx_ ? 16.0 : 8.0));
+  }
+  const void *kf = cplx_ ? (const void *)k_orth_step_batch<cplx, 1>
+                         : (W == 2 ? (const void *)k_orth_step_batch<double, 2> : (const void *)k_orth_step_batch<double, 1>);
+  static std::unordered_map<const void *, int> occ_cache;
+  auto it = occ_cache.find(kf);
+  if (it == occ_cache.end()) {
+    int occ = 0;
+    CV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf, CV_BLOCK, sizeof(double) * 2 * CV_BATCH_PTRS));
+    CV_REQUIRE(occ >= 1, "lock-step orth: kernel does not fit on an SM");
+    it = occ_cache.emplace(kf, occ).first;
+  }
+  const int cap = it->second * ctx->sms;
+  const int mi_max = cplx_ ? ORTH_MI<cplx>::value : ORTH_MI<double>::value;
+  const int ny = (mmax + mi_max - 1) / mi_max;
+  int64_t need = (n / W + CV_BLOCK - 1) / CV_BLOCK;
+  if (need < ny) need = ny;
+  const int grid = (int)(need < cap ? need : cap);
+  a.pstride = (int64_t)mi_max * (cplx_ ? 2 : 1) * grid + 2048 + grid + 64;
+  CV_REQUIRE((size_t)a.pstride * np <= CV_N_PARTIALS, "lock-step orth: partial sums exceed the scratch area");
+  a.partials = ctx->partials;
+  a.bar = ctx->counters + CV_COUNTER_BAR;
+  a.ticket = ctx->counters + CV_COUNTER_PUSH;
+  a.scal = ctx->scalars;
+  a.slab_mode = ctx->slab_mode;
+  a.host_mb = ctx->mailbox;
+  a.host_flag = ctx->host_flag;
+  a.host_seq = ++ctx->host_seq;
+  const size_t sh = sizeof(double) * mmax * (cplx_ ? 2 : 1);
+  void *params[1] = {(void *)&a};
+  {
+    cv_prof_scope prof(ctx, 1, st);
+    CV_CUDA(cudaLaunchCooperativeKernel(kf, dim3(grid), dim3(CV_BLOCK), params, sh, st));
+  }
+  CV_TRY(cv_check_launch(ctx, "orth_step_batch"));
+  return cv_wait_mailbox(ctx, a.host_seq, st);
+}
+
+int gcrotmk_lockstep(cv_ctx *ctx, cv_op *op, int cplx_, int mode, int nrhs, const double *sre, const double *sim,
+                     const void *const *b, const void *const *x0, void *const *x, double rtol, double atol, int maxiter, int m,
+                     int k, char *work, size_t ws_one, cv_solve_stats *stats, cudaStream_t st) {
+  const int64_t n = op->n_rows;
+  std::vector<LockstepSolve> S(nrhs);
+  for (int q = 0; q < nrhs; ++q) {
+    LockstepSolve &s = S[q];
+    s.cplx_ = cplx_;
+    s.mode = mode;
+    s.m = m;
+    s.k = k;
+    s.maxiter = maxiter;
+    s.sre = sre[q];
+    s.sim = sim[q];
+    s.rtol = rtol;
+    s.atol_in = atol;
+    s.b = b[q];
+    s.x = x[q];
+    s.ws = Workspace{work + ws_one * (size_t)q, vec_stride_bytes(n, cplx_)};
+    s.stats = &stats[q];
+    s.so = S_BLOCK * (q % (2 * CV_MAX_BATCH));
+    CV_TRY(s.start(ctx, op, x0 ? x0[q] : nullptr, st));
+  }
+  std::vector<LockstepSolve *> act;
+  for (;;) {
+    act.clear();
+    for (auto &s : S)
+      if (s.phase == LockstepSolve::INNER) act.push_back(&s);
+    if (act.empty()) break;
+    for (size_t g0 = 0; g0 < act.size(); g0 += CV_MAX_BATCH) {
+      const int np = (int)std::min<size_t>(CV_MAX_BATCH, act.size() - g0);
+      LockstepSolve *const *P = act.data() + g0;
+      // problems of one group must use distinct scalar blocks: so = block of the problem's index mod 8 (nrhs <= 8)
+      if (cplx_)
+        CV_TRY(lockstep_spmv<cplx>(ctx, op, mode, np, P, st));
+      else
+        CV_TRY(lockstep_spmv<double>(ctx, op, mode, np, P, st));
+      CV_TRY(lockstep_orth(ctx, n, cplx_, np, P, st));
+      for (int q = 0; q < np; ++q) {
+        P[q]->stats->n_sync++;
+        if (P[q]->step_consume(ctx)) CV_TRY(P[q]->outer_end(ctx, op, st));
+      }
+    }
+  }
+  for (int q = 0; q < nrhs; ++q) {
+    stats[q].n_outer = S[q].converged ? S[q].j_outer : std::min(S[q].j_outer, maxiter);
+    stats[q].info = S[q].converged ? 0 : std::max(1, std::min(S[q].j_outer, maxiter));
+  }
+  return CV_OK;
+}
+
 // The fused Arnoldi step on caller-owned vectors (tests, micro-benchmarks): exactly the launch GCROT's
 // inner loop issues after every operator application.
 extern "C" int cv_arnoldi_step(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int m, const void *const *basis,
@@ -698,6 +1149,33 @@ extern "C" int cv_arnoldi_step(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int
   out_host[1] = mb[S_NRM];
   for (int i = 0; i < m * NR; ++i) out_host[2 + i] = mb[S_H1 + i] + (mb[S_FLAG] != 0.0 ? mb[S_H2 + i] : 0.0);
   return CV_OK;
+}
+
+extern "C" int cv_solve_batch(cv_ctx *ctx, cv_op *op, int cplx_, int nrhs, int reverse, const double *sigma_re,
+                              const double *sigma_im, const void *const *b, const void *const *x0, void *const *x_out,
+                              double rtol, double atol, int maxiter, int m, int k, void *work_dev, size_t work_bytes,
+                              cv_solve_stats *stats, void *stream) {
+  CV_REQUIRE(ctx && op && sigma_re && sigma_im && b && x_out && work_dev && stats, "cv_solve_batch: null argument");
+  CV_REQUIRE(nrhs >= 1 && nrhs <= 2 * CV_MAX_BATCH, "cv_solve_batch: nrhs=%d outside 1..%d", nrhs, 2 * CV_MAX_BATCH);
+  CV_REQUIRE(ctx->world == 1, "cv_solve_batch: lock-step solves run on a single GPU (row-sharded runs solve one at a time)");
+  CV_REQUIRE(op->n_rows == op->n_cols - op->n_halo, "cv_solve_batch: operator must be square");
+  CV_REQUIRE(maxiter >= 0 && rtol >= 0 && atol >= 0, "cv_solve_batch: bad tolerances");
+  if (m <= 0) m = 20;
+  if (k <= 0) k = m;
+  CV_REQUIRE(m + 2 * k + 2 <= CV_BATCH_PTRS, "cv_solve_batch: GCROT(m=%d,k=%d) exceeds %d basis vectors per problem", m, k,
+             CV_BATCH_PTRS);
+  const size_t ws_one = cv_solve_workspace_bytes(op->n_rows, cplx_, CV_SOLVER_GCROTMK, m, k);
+  CV_REQUIRE(((uintptr_t)work_dev & 255) == 0 && (ws_one & 255) == 0, "cv_solve_batch: workspace must be 256-byte aligned");
+  CV_REQUIRE(work_bytes >= ws_one * (size_t)nrhs, "cv_solve_batch: workspace too small");
+  for (int q = 0; q < nrhs; ++q) {
+    CV_REQUIRE(b[q] && x_out[q], "cv_solve_batch: null vector %d", q);
+    CV_REQUIRE(((uintptr_t)b[q] & 15) == 0 && ((uintptr_t)x_out[q] & 15) == 0 && (!x0 || !x0[q] || ((uintptr_t)x0[q] & 15) == 0),
+               "cv_solve_batch: vectors must be 16-byte aligned");
+    memset(&stats[q], 0, sizeof(stats[q]));
+  }
+  ctx->recycle.valid = false;
+  return gcrotmk_lockstep(ctx, op, cplx_, reverse ? CV_SPMV_RSHIFT : CV_SPMV_SHIFT, nrhs, sigma_re, sigma_im, b, x0, x_out, rtol,
+                          atol, maxiter, m, k, static_cast<char *>(work_dev), ws_one, stats, (cudaStream_t)stream);
 }
 
 extern "C" size_t cv_solve_workspace_bytes(int64_t n, int cplx_, int solver, int m, int k) {

@@ -375,6 +375,81 @@ class CudaVector(AbstractVector):
             warnings.warn("Warning:: Iterative solver is not converged ")
         return CudaVector._wrap(out, b.options, b._n_global)
 
+    @staticmethod
+    def solveBlock(H, bs, sigma, x0=None, opType="her", reverseGF=False):
+        """`[solve(H, b, s) for b, s in zip(bs, sigmas)]` with the solves advanced in LOCK STEP
+        (cv_solve_batch): the independent shifted solves of one block-Lanczos step
+        (inexact_Lanczos.py:319-320) or of one FEAST node (feast.py:190-201) share one pass over the
+        matrix and one fused orthogonalisation launch per Arnoldi step.  `sigma` is a scalar or one
+        shift per right-hand side.  Each solve follows exactly the recurrences of `solve`; anything
+        the batched path does not cover (MINRES, row-sharded runs, recycling, differing options) is
+        solved one at a time.  Raises like `solve` when a system does not converge."""
+        rt = Runtime.get()
+        bs = list(bs)
+        nrhs = len(bs)
+        sigmas = list(sigma) if isinstance(sigma, (list, tuple, np.ndarray)) else [sigma] * nrhs
+        x0s = list(x0) if x0 is not None else [None] * nrhs
+        assert len(sigmas) == nrhs and len(x0s) == nrhs
+        options = bs[0].options["linearSystemArgs"] if nrhs else None
+        m_in = int(options.get("gcrot_m", 20)) if nrhs else 20
+        k_in = int(options.get("gcrot_k", 0)) if nrhs else 0
+        batched = (nrhs >= 2 and rt.world == 1 and options["linearSolver"] == "gcrotmk" and not options.get("recycle", False)
+                   and all(b.options["linearSystemArgs"] is options or b.options["linearSystemArgs"] == options for b in bs)
+                   and m_in + 2 * (k_in if k_in else m_in) + 2 <= 64)
+        if not batched:
+            return [CudaVector.solve(H, b, s, x0=x, opType=opType, reverseGF=reverseGF) for b, s, x in zip(bs, sigmas, x0s)]
+        op = rt.operator_for(H)
+        n = op.shape[0]
+        if any(len(b) != n for b in bs):
+            raise ValueError("solveBlock: shape mismatch between operator and right-hand side")
+        cplx = any(bool(np.issubdtype(np.result_type(s, op.dtype, b.dtype), np.complexfloating)) for b, s in zip(bs, sigmas))
+        tol, atol, maxiter = options["linear_tol"], options["linear_atol"], options["linearIter"]
+        nloc = bs[0]._nloc
+        ws_one = rt.lib.cv_solve_workspace_bytes(nloc, int(cplx), _lib.CV_SOLVER_GCROTMK, m_in, k_in if k_in else m_in)
+        free_bytes = rt.torch.cuda.mem_get_info(rt.device)[0] + (rt._workspaces["solve"].numel() if "solve" in rt._workspaces else 0)
+        group = int(max(1, min(8, nrhs, (0.85 * free_bytes) // ws_one)))
+        if group < 2:
+            return [CudaVector.solve(H, b, s, x0=x, opType=opType, reverseGF=reverseGF) for b, s, x in zip(bs, sigmas, x0s)]
+        outs = []
+        for g0 in range(0, nrhs, group):
+            idx = list(range(g0, min(g0 + group, nrhs)))
+            if len(idx) == 1:
+                outs.append(CudaVector.solve(H, bs[idx[0]], sigmas[idx[0]], x0=x0s[idx[0]], opType=opType, reverseGF=reverseGF))
+                continue
+            work = rt.workspace(ws_one * len(idx))
+            bt = [bs[i]._as_complex_tensor() if cplx else bs[i]._t for i in idx]
+            xt = [None if x0s[i] is None else (x0s[i]._as_complex_tensor() if cplx else x0s[i]._t) for i in idx]
+            yt = [rt.empty(nloc, cplx) for _ in idx]
+            sre = (C.c_double * len(idx))(*[complex(sigmas[i]).real for i in idx])
+            sim = (C.c_double * len(idx))(*[complex(sigmas[i]).imag for i in idx])
+            bp, _k1 = _lib.ptr_array([t.data_ptr() for t in bt])
+            xp, _k2 = _lib.ptr_array([0 if t is None else t.data_ptr() for t in xt])
+            yp, _k3 = _lib.ptr_array([t.data_ptr() for t in yt])
+            stats = (_lib.SolveStats * len(idx))()
+            _lib.check(rt.lib.cv_ctx_set_recycle(rt.ctx, 0))
+            _lib.check(rt.lib.cv_solve_batch(rt.ctx, op.handle, int(cplx), len(idx), int(bool(reverseGF)), sre, sim, bp,
+                                             xp if any(t is not None for t in xt) else None, yp, float(tol), float(atol),
+                                             int(maxiter), m_in, k_in, work.data_ptr(), work.numel(), stats, rt.stream))
+            bad = False
+            for j, i in enumerate(idx):
+                st = stats[j]
+                rt.stats["solves"] += 1
+                rt.stats["matvecs"] += st.n_matvec
+                rt.stats["syncs"] += st.n_sync
+                rt.stats["outer"] += st.n_outer
+                rt.stats["reorth"] = rt.stats.get("reorth", 0) + st.n_reorth
+                rt.stats["safe_solves"] = rt.stats.get("safe_solves", 0) + st.n_safe
+                rt.stats["orth_loss"] = max(rt.stats.get("orth_loss", 0.0), st.orth_loss)
+                rt.stats["lockstep_solves"] = rt.stats.get("lockstep_solves", 0) + 1
+                bad = bad or st.info != 0
+                outs.append(CudaVector._wrap(yt[j], bs[i].options, bs[i]._n_global))
+            rt.last_solve = stats[len(idx) - 1]
+            rt.last_block_matvecs = getattr(rt, "last_block_matvecs", [])[:0] + [stats[j].n_matvec for j in range(len(idx))]
+            if bad:  # numpyVector.py:175-177
+                warnings.simplefilter('error', UserWarning)
+                warnings.warn("Warning:: Iterative solver is not converged ")
+        return outs
+
     # ------------------------------------------------------------------ small matrices
     @staticmethod
     def _tsdot(vs, ws, conj=True):
@@ -467,6 +542,11 @@ class CudaVector(AbstractVector):
         overlap = np.append(overlap, elems[:, :-1].conj(), axis=0)
         overlap = np.append(overlap, elems.T, axis=1)
         return overlap
+
+    @staticmethod
+    def lastBlockMatvecs():
+        """Operator applications of each solve of the most recent lock-step group (solveBlock)."""
+        return list(getattr(Runtime.get(), "last_block_matvecs", []))
 
     @staticmethod
     def matvecCount():

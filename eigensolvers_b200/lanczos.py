@@ -54,6 +54,16 @@ def generateSubspace(Hop, vec, sigma, eConv):
     return out, False
 
 
+def _solve_block(typeClass, Hop, vecs, sigma):
+    """The nBlock shifted solves of one Krylov step.  They are independent (inexact_Lanczos.py:319-320),
+    so a vector class that offers `solveBlock` may advance them together (CudaVector: lock-step GCROT,
+    one pass over H per Arnoldi step for the whole block); the results equal the one-by-one solves."""
+    fn = getattr(typeClass, "solveBlock", None)
+    if fn is None:
+        return None
+    return fn(Hop, vecs, sigma)
+
+
 def checkConvergence(ev, eConv, status, printObj=None):
     """Relative change of the sorted first nBlock picked eigenvalues against the previous
     step's, from the second cumulative step on (inexact_Lanczos.py:115-143)."""
@@ -111,7 +121,7 @@ def inexactLanczosDiagonalization(H, v0, sigma, L, maxit, eConv, checkFitTol=1e-
                                   Hsolve=None, pick=None, status=None,
                                   writeOut=True, eShift=0.0, convertUnit="au",
                                   outFileName=None, summaryFileName=None,
-                                  saveTNSsEachIteration=False, saveDir="saveTNSs"):
+                                  saveTNSsEachIteration=False, saveDir="saveTNSs", lockstep=True):
     """Eigenpairs of H closest to `sigma` (or selected by `pick`).
 
     H        operator for the Rayleigh-Ritz matrices; Hsolve (default H) is used for the solves
@@ -160,8 +170,16 @@ def inexactLanczosDiagonalization(H, v0, sigma, L, maxit, eConv, checkFitTol=1e-
             # -- new directions: the last nBlock vectors, visited back to front
             fresh = []
             nonzero = True
+            block = _solve_block(typeClass, Hsolve, [Ylist[-iBlock] for iBlock in range(1, nBlock + 1)], sigma) \
+                if (nBlock > 1 and lockstep) else None
             for iBlock in range(1, nBlock + 1):
-                out, nonzero = generateSubspace(Hsolve, Ylist[-iBlock], sigma, eConv)
+                if block is None:
+                    out, nonzero = generateSubspace(Hsolve, Ylist[-iBlock], sigma, eConv)
+                else:  # same test as generateSubspace, on the result of the lock-step solve
+                    out = block[iBlock - 1]
+                    nonzero = typeClass.norm(out) > 0.001 * eConv
+                    if nonzero:
+                        out = typeClass.normalize(out)
                 if not nonzero:
                     status["zeroVector"] = True
                     warnings.warn(f"Alert: zero vector: ||inv(H-sigma)vec||={typeClass.norm(out):5.3e}")

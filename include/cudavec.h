@@ -297,6 +297,18 @@ int cv_solve(cv_ctx *ctx, cv_op *op, int cplx, int solver, int reverse, double s
              double atol, int maxiter, int m, int k, void *work_dev, size_t work_bytes,
              cv_solve_stats *stats, void *stream);
 
+/* LOCK-STEP solves: nrhs (<= 8) independent systems (sigma_q I - H) x_q = b_q with the same operator
+ * (the nBlock solves of one block-Lanczos step, inexact_Lanczos.py:319-320; the m0 solves of a FEAST
+ * quadrature node, feast.py:190-201) advance one GCROT Arnoldi step at a time together: the matrix
+ * is read once per step for all of them (DIA storage) and one fused orthogonalisation kernel with one
+ * grid barrier and one host message serves all problems.  Per solve: same recurrences, stopping
+ * rules and return codes as cv_solve (stats[q]).  GCROT only, single GPU, m + 2k + 2 <= 64;
+ * work_dev holds nrhs workspaces of cv_solve_workspace_bytes() each.  x0 may be NULL (or hold NULLs). */
+int cv_solve_batch(cv_ctx *ctx, cv_op *op, int cplx, int nrhs, int reverse, const double *sigma_re,
+                   const double *sigma_im, const void *const *b, const void *const *x0,
+                   void *const *x_out, double rtol, double atol, int maxiter, int m, int k,
+                   void *work_dev, size_t work_bytes, cv_solve_stats *stats, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -212,6 +212,30 @@ def test_feast(rt):
         np.testing.assert_allclose(_overlap(uvE[:, iE], vecs[iT].array), 1, rtol=1e-2)
 
 
+def test_feast_lockstep_equals_sequential(rt):
+    """The FEAST wrapper advancing the (node, vector) solves in lock step (complex shifts, one per
+    problem) against the same wrapper solving one by one, and against the reference golden."""
+    from eigensolvers_b200 import CudaVector, hamiltonians as hm
+    from eigensolvers_b200.contour import feastDiagonalization
+    g = gold("feast_osc")
+    H, _ = hm.coupled_oscillators((6, 5, 5, 4), coupling=0.1, seed=1)
+    o = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 2000, "linear_tol": 1e-2}}
+    res = []
+    for lock in (True, False):
+        ls0 = rt.stats.get("lockstep_solves", 0)
+        Y = [CudaVector(np.ascontiguousarray(g["Q"][:, i]), dict(o)) for i in range(4)]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ev, vecs, st = feastDiagonalization(H, Y, 16, "legendre", float(g["eMin"]), float(g["eMax"]), 1e-8, 12,
+                                                writeOut=False, lockstep=lock)
+        assert (rt.stats.get("lockstep_solves", 0) > ls0) == lock
+        res.append(np.sort([e for e in ev if g["eMin"] < e < g["eMax"]]))
+    inside_ref = np.sort([e for e in g["ev"] if g["eMin"] < e < g["eMax"]])
+    assert len(res[0]) == len(res[1]) == len(inside_ref)
+    np.testing.assert_allclose(res[0], res[1], rtol=0, atol=5e-6)
+    np.testing.assert_allclose(res[0], inside_ref, rtol=0, atol=5e-6)
+
+
 def test_fortran_golden_through_gpu(rt):
     """Polizzi's Fortran FEAST numbers (unittests/data_fortranCode.out) through the GPU path with the
     reference test's own option linearSolver="pardiso" (test_feast_fortran.py:41): CudaVector serves

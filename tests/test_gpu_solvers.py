@@ -247,3 +247,118 @@ def test_gcrotmk_recycling_across_solves(rt):
     x = CudaVector.solve(op, CudaVector(b0, o), sigma + 0.01).array
     assert rt.last_solve.n_recycled == 0
     assert np.linalg.norm(b0 - ((sigma + 0.01) * x - H @ x)) <= 1e-6 * (1 + 1e-6)
+
+
+# --------------------------------------------------------------------------------------------
+# lock-step solves (cv_solve_batch / CudaVector.solveBlock): the independent solves of a block-Lanczos
+# step (inexact_Lanczos.py:319-320) or of FEAST nodes (feast.py:190-201) advanced together
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nrhs", [2, 3, 4, 6])
+@pytest.mark.parametrize("kind", ["dia", "general"])
+@pytest.mark.parametrize("cplx", [False, True])
+def test_lockstep_solves_match_single_solves(rt, nrhs, kind, cplx):
+    """Every solve of a lock-step group is the same algorithm as a single solve: same verdict, the same
+    number of operator applications (+-2 %: reduction orders differ), solutions equal to solver accuracy,
+    residuals within tolerance — with ONE shift for the block and with one shift per right-hand side."""
+    from eigensolvers_b200 import CudaVector, DeviceOperator, hamiltonians as hm
+    if kind == "dia":
+        H = hm.laplacian3d(16, seed=2, W=1.0)
+        op = DeviceOperator.from_host(H)
+        assert op.format == "dia"
+        base = 0.9
+    else:
+        rng = np.random.default_rng(3)
+        A = sp.random(3000, 3000, density=0.003, random_state=3, format="csr")
+        H = (A + A.T + sp.diags(np.linspace(1.0, 9.0, 3000))).tocsr()
+        op = DeviceOperator.from_host(H)
+        assert op.format in ("sell", "csr")
+        base = 4.3
+    n = H.shape[0]
+    rng = np.random.default_rng(nrhs)
+    o = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 3000, "linear_tol": 1e-9, "linear_atol": 0.0}}
+    bs = [rng.standard_normal(n) for _ in range(nrhs)]
+    for sigmas in ([base + (0.02j if cplx else 0.0)] * nrhs,
+                   [base + 0.013 * q + (0.03j * (q + 1) if cplx else 0.0) for q in range(nrhs)]):
+        B = [CudaVector(b, dict(o)) for b in bs]
+        mv0 = rt.stats["matvecs"]
+        singles = [CudaVector.solve(op, B[q], sigmas[q]).array for q in range(nrhs)]
+        mv_single = rt.stats["matvecs"] - mv0
+        mv0, ls0 = rt.stats["matvecs"], rt.stats.get("lockstep_solves", 0)
+        block = CudaVector.solveBlock(op, B, sigmas if len(set(sigmas)) > 1 else sigmas[0])
+        mv_block = rt.stats["matvecs"] - mv0
+        assert rt.stats.get("lockstep_solves", 0) - ls0 == nrhs          # the batched path really ran
+        assert abs(mv_block - mv_single) <= 0.02 * mv_single + 2, (mv_block, mv_single)
+        for q in range(nrhs):
+            xb = block[q].array
+            res = np.linalg.norm(bs[q] - (sigmas[q] * xb - H @ xb)) / np.linalg.norm(bs[q])
+            assert res < 5e-9, (q, res)
+            assert np.linalg.norm(xb - singles[q]) <= 1e-7 * np.linalg.norm(singles[q])
+
+
+def test_lockstep_hard_shift_with_second_passes(rt):
+    """sigma inside a dense spectrum (BASELINE config 2's regime at 24^3): thousands of operator
+    applications per solve, most Arnoldi steps cancel and take the second Gram-Schmidt pass, solves of
+    the group finish at different times and do their outer updates out of phase."""
+    from eigensolvers_b200 import CudaVector, DeviceOperator
+    from eigensolvers_b200.workloads import build_workload, solver_options
+    w = build_workload("c2small")
+    op = DeviceOperator.from_host(w["H"])
+    o = solver_options(w)
+    B = [CudaVector(g.copy(), dict(o)) for g in w["guesses"]]
+    r0 = rt.stats.get("reorth", 0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        block = CudaVector.solveBlock(op, B, w["sigma"])
+    warnings.resetwarnings()
+    assert rt.stats.get("reorth", 0) > r0
+    la = o["linearSystemArgs"]
+    for q, g in enumerate(w["guesses"]):
+        x = block[q].array
+        res = np.linalg.norm(g - (w["sigma"] * x - w["H"] @ x))
+        assert res <= 1.05 * max(la["linear_atol"], la["linear_tol"] * np.linalg.norm(g)), (q, res)
+
+
+def test_lockstep_fallbacks_and_errors(rt):
+    """solveBlock covers what the batched path does not by solving one at a time, and raises like solve."""
+    from eigensolvers_b200 import CudaVector, hamiltonians as hm
+    H = hm.laplacian3d(10)
+    n = H.shape[0]
+    rng = np.random.default_rng(0)
+    bs = [rng.standard_normal(n) for _ in range(3)]
+    ls0 = rt.stats.get("lockstep_solves", 0)
+    out = CudaVector.solveBlock(H, [CudaVector(b, _opts("minres", 1e-8)) for b in bs], 0.5)      # MINRES: one at a time
+    assert rt.stats.get("lockstep_solves", 0) == ls0 and len(out) == 3
+    for b, x in zip(bs, out):
+        xa = x.array
+        assert np.linalg.norm(b - (0.5 * xa - H @ xa)) <= 1e-5 * np.linalg.norm(b)
+    one = CudaVector.solveBlock(H, [CudaVector(bs[0], _opts("gcrotmk", 1e-8))], 0.5)             # a block of one
+    assert len(one) == 1
+    tight = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 1, "linear_tol": 1e-14, "linear_atol": 0.0}}
+    with pytest.raises(UserWarning):                                                             # numpyVector.py:175-177
+        CudaVector.solveBlock(H, [CudaVector(b, dict(tight)) for b in bs], 3.1)
+    warnings.resetwarnings()
+
+
+def test_block_lanczos_lockstep_equals_sequential(rt):
+    """The mirror driver with lock-step block solves against the same driver solving one by one:
+    same number of Krylov steps, same eigenvalues (C2's generator at 12^3, four guesses)."""
+    from eigensolvers_b200 import CudaVector, hamiltonians as hm
+    from eigensolvers_b200.hostmath import calculateTarget
+    from eigensolvers_b200.lanczos import inexactLanczosDiagonalization
+    H = hm.laplacian3d(12, seed=2, W=1.0)
+    evs = np.linalg.eigvalsh(H.toarray())
+    sigma = calculateTarget(evs, 10)
+    guess = hm.orthonormal_block(H.shape[0], 4, seed=3)
+    o = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 1000, "linear_tol": 1e-4, "linear_atol": 1e-4}}
+    out = []
+    for lock in (True, False):
+        ls0 = rt.stats.get("lockstep_solves", 0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out.append(inexactLanczosDiagonalization(H, [CudaVector(v.copy(), dict(o)) for v in guess], sigma, 10, 20, 1e-8,
+                                                     writeOut=False, lockstep=lock))
+        warnings.resetwarnings()
+        assert (rt.stats.get("lockstep_solves", 0) > ls0) == lock
+    (ev_a, Y_a, st_a), (ev_b, Y_b, st_b) = out
+    assert st_a["isConverged"] and st_b["isConverged"] and abs(st_a["cumIter"] - st_b["cumIter"]) <= 1
+    np.testing.assert_allclose(np.sort(ev_a[:4]), np.sort(ev_b[:4]), rtol=1e-8)
