@@ -120,6 +120,64 @@ struct OrthBatchArgs {
   unsigned long long host_seq;
 };
 
+// Work split of one pass over all problems that take part in it.  Phase A: every (problem, slab of
+// <= MI vectors) pair gets a contiguous range of CTAs proportional to its loads per row (mi + 1);
+// phase B: every problem gets a range proportional to (m + 2).  All problems stream CONCURRENTLY —
+// one ramp-up and one tail per phase for the whole batch, and at small N (1e6 rows, 4 problems) a
+// CTA's stream is 4x longer than when the whole grid works on one problem after the other.
+constexpr int CV_BATCH_SLABS = CV_MAX_BATCH * (CV_BATCH_PTRS / 8);
+struct BatchMap {
+  int nslab;
+  int q[CV_BATCH_SLABS], i0[CV_BATCH_SLABS], mi[CV_BATCH_SLABS];
+  int start[CV_BATCH_SLABS + 1];   // phase A: first CTA of each slab
+  int bstart[CV_MAX_BATCH + 1];    // phase B: first CTA of each problem (inactive problems: empty range)
+};
+__device__ inline void batch_map_build(const OrthBatchArgs &a, unsigned active_mask, int G, int MI, BatchMap &M) {
+  int ns = 0, wsum = 0, bsum = 0;
+  for (int q = 0; q < a.nprob; ++q) {
+    if (!((active_mask >> q) & 1u)) continue;
+    const int m = a.prob[q].m;
+    const int ny = (m + MI - 1) / MI;
+    const int base = m / ny, rem = m % ny;
+    int at = 0;
+    for (int by = 0; by < ny; ++by) {
+      M.q[ns] = q;
+      M.i0[ns] = at;
+      M.mi[ns] = base + (by < rem ? 1 : 0);
+      at += M.mi[ns];
+      wsum += M.mi[ns] + 1;
+      ++ns;
+    }
+    bsum += m + 2;
+  }
+  M.nslab = ns;
+  int acc = 0;
+  for (int s = 0; s < ns; ++s) {
+    M.start[s] = acc;
+    int g = (int)(((long long)G * (M.mi[s] + 1)) / wsum);
+    if (g < 1) g = 1;
+    const int remaining = ns - 1 - s;
+    if (acc + g > G - remaining) g = G - remaining - acc;
+    if (s == ns - 1) g = G - acc;
+    acc += g;
+  }
+  M.start[ns] = G;
+  acc = 0;
+  int left = 0;
+  for (int q = 0; q < a.nprob; ++q) left += (active_mask >> q) & 1u;
+  for (int q = 0; q < a.nprob; ++q) {
+    M.bstart[q] = acc;
+    if (!((active_mask >> q) & 1u)) continue;
+    --left;
+    int g = (int)(((long long)G * (a.prob[q].m + 2)) / bsum);
+    if (g < 1) g = 1;
+    if (acc + g > G - left) g = G - left - acc;
+    if (left == 0) g = G - acc;
+    acc += g;
+  }
+  M.bstart[a.nprob] = G;
+}
+
 template <typename T, int W>
 __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step_batch(const __grid_constant__ OrthBatchArgs a) {
   constexpr int NR = Num<T>::NRED;
@@ -127,33 +185,43 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step_batch(const __grid_co
   extern __shared__ double s_h[];  // max_q m_q * NR doubles
   __shared__ double s_part[CV_WARPS][MI * NR + 1];
   __shared__ double s_vals[MI * NR + 1];
-  __shared__ SlabMap s_map;
+  __shared__ BatchMap s_map;
   __shared__ int s_state[CV_MAX_BATCH];  // after the barrier of a pass: 1 = this problem needs pass 2
+  __shared__ unsigned s_mask;
   const int G = gridDim.x, c = blockIdx.x;
   const int64_t n = a.n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t npf = n / W;
   const bool tail_mine = (W == 2) && (n & 1);
+  double *p_ww = a.partials + (size_t)MI * NR * G;  // pass 2: [q][512] partial |w'|^2 of the problem's first slab
+  double *p_nx = p_ww + CV_MAX_BATCH * 512;         // [q][512] explicit |v_new|^2 partials of the problem's phase-B CTAs
+  unsigned final_mask1 = 0;                         // problems that were final in pass 1 (for the tail)
 
   for (int pass = 1; pass <= 2; ++pass) {
-    // ---------------- phase A: dots of every problem that takes part in this pass ----------------
-    for (int q = 0; q < a.nprob; ++q) {
+    // problems taking part in this pass, and the work split over them
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned mask = 0;
+      for (int q = 0; q < a.nprob; ++q)
+        if (pass == 1 || __ldcg(a.scal + a.prob[q].sbase + a.o_flag) != 0.0) mask |= 1u << q;
+      s_mask = mask;
+      batch_map_build(a, mask, G, MI, s_map);
+    }
+    __syncthreads();
+    const unsigned mask = s_mask;
+    // ---------------- phase A: this CTA's (problem, slab) ----------------------------------------
+    {
+      int sl_i = 0;
+      while (sl_i + 1 < s_map.nslab && c >= s_map.start[sl_i + 1]) ++sl_i;
+      const int q = s_map.q[sl_i];
       const OrthProb &P = a.prob[q];
-      if (pass == 2 && __ldcg(a.scal + P.sbase + a.o_flag) == 0.0) continue;
-      const int m = P.m;
-      __syncthreads();  // s_map / s_vals of the previous problem are no longer read
-      if (threadIdx.x == 0) orth_slab_map(m, G, MI, a.slab_mode, s_map);
-      __syncthreads();
-      int by = 0;
-      while (by + 1 < s_map.ny && c >= s_map.start[by + 1]) ++by;
-      const int bx = c - s_map.start[by];
-      const int gx = s_map.start[by + 1] - s_map.start[by];
-      const int i0 = s_map.i0[by];
-      const int mi = s_map.i0[by + 1] - i0;
-      const int half = (a.slab_mode && mi > LB) ? (mi + 1) / 2 : (mi < LB ? mi : LB);
-      const bool want_ww = pass == 2 && by == 0;
+      const int bx = c - s_map.start[sl_i];
+      const int gx = s_map.start[sl_i + 1] - s_map.start[sl_i];
+      const int i0 = s_map.i0[sl_i];
+      const int mi = s_map.mi[sl_i];
+      const int half = (mi > LB) ? (mi + 1) / 2 : mi;
+      const bool want_ww = pass == 2 && i0 == 0;
       const T *wvec = static_cast<const T *>(P.w);
-      double *preg = a.partials + (size_t)q * a.pstride;
       T acc[MI];
       double ww = 0.0;
 #pragma unroll
@@ -211,40 +279,37 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step_batch(const __grid_co
         s_vals[v] = s;
       }
       __syncthreads();
-      double *pslab = preg + (size_t)MI * NR * s_map.start[by];
+      double *pslab = a.partials + (size_t)MI * NR * s_map.start[sl_i];
       for (int v = threadIdx.x; v < mi * NR; v += blockDim.x) {
         const int i = v / NR, k = v - i * NR;
         const int sl = i < half ? i : LB + (i - half);
         pslab[(size_t)v * gx + bx] = s_vals[sl * NR + k];
       }
-      if (want_ww && threadIdx.x == 0) preg[(size_t)MI * NR * G + bx] = s_vals[MI * NR];
+      if (want_ww && threadIdx.x == 0) p_ww[q * 512 + bx] = s_vals[MI * NR];
     }
     // ---------------- ONE barrier: the last CTA finishes every problem's reduction ----------------
     grid_barrier_with(a.bar, [&]() {
       bool any_again = false;
       for (int q = 0; q < a.nprob; ++q) {
-        const OrthProb &P = a.prob[q];
-        const bool active = pass == 1 || __ldcg(a.scal + P.sbase + a.o_flag) != 0.0;
         if (threadIdx.x == 0) s_state[q] = 0;
-        if (!active) continue;  // uniform over the CTA
+        if (!((mask >> q) & 1u)) continue;  // uniform over the CTA
+        const OrthProb &P = a.prob[q];
         const int m = P.m;
         const int s_h_out = P.sbase + (pass == 1 ? a.o_h1 : a.o_h2);
-        double *preg = a.partials + (size_t)q * a.pstride;
-        __syncthreads();
-        if (threadIdx.x == 0) orth_slab_map(m, G, MI, a.slab_mode, s_map);
-        __syncthreads();
+        int first = 0;  // first slab of this problem
+        while (s_map.q[first] != q) ++first;
         for (int v = warp; v < m * NR; v += CV_WARPS) {
-          int by = 0;
-          while (v / NR >= s_map.i0[by + 1]) ++by;
-          const int local = v - s_map.i0[by] * NR;
-          const int gx = s_map.start[by + 1] - s_map.start[by];
-          const double *pp = preg + (size_t)MI * NR * s_map.start[by] + (size_t)local * gx;
+          int sl_i = first;
+          while (sl_i + 1 < s_map.nslab && s_map.q[sl_i + 1] == q && v / NR >= s_map.i0[sl_i + 1]) ++sl_i;
+          const int local = v - s_map.i0[sl_i] * NR;
+          const int gx = s_map.start[sl_i + 1] - s_map.start[sl_i];
+          const double *pp = a.partials + (size_t)MI * NR * s_map.start[sl_i] + (size_t)local * gx;
           double r = ordered_lane_sum(pp, gx, lane);
           r = warp_sum(r);
           if (lane == 0) a.scal[s_h_out + v] = r;
         }
         if (pass == 2 && warp == 0) {
-          double r = ordered_lane_sum(preg + (size_t)MI * NR * G, s_map.start[1], lane);
+          double r = ordered_lane_sum(p_ww + q * 512, s_map.start[first + 1] - s_map.start[first], lane);
           r = warp_sum(r);
           if (lane == 0) a.scal[s_h_out + m * NR] = r;
         }
@@ -293,15 +358,21 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step_batch(const __grid_co
         if (threadIdx.x == 0) st_release_sys(a.host_flag, a.host_seq);
       }
     });
-    // ---------------- phase B: w <- (w - [C,V] h) [/ |w'| when final] ------------------------------
+    // ---------------- phase B: this CTA's problem: w <- (w - [C,V] h) [/ |w'| when final] ----------
     bool any_again = false;
-    for (int q = 0; q < a.nprob; ++q) {
+    for (int q = 0; q < a.nprob; ++q)
+      if (((mask >> q) & 1u) && pass == 1 && __ldcg(a.scal + a.prob[q].sbase + a.o_flag) != 0.0) any_again = true;
+    {
+      int q = 0;
+      while (q + 1 < a.nprob && c >= s_map.bstart[q + 1]) ++q;
+      while (!((mask >> q) & 1u)) ++q;  // empty ranges of inactive problems share their start with the next one
       const OrthProb &P = a.prob[q];
-      const double flag = __ldcg(a.scal + P.sbase + a.o_flag);
-      // pass 1: everybody updates (final unless flagged); pass 2: only the flagged problems, final
-      if (pass == 2 && flag == 0.0) continue;
-      const bool final_pass = pass == 2 || flag == 0.0;
-      any_again = any_again || !final_pass;
+      const int bc = c - s_map.bstart[q];
+      int qn = q + 1;
+      while (qn < a.nprob && !((mask >> qn) & 1u)) ++qn;
+      const int bg = (qn < a.nprob ? s_map.bstart[qn] : G) - s_map.bstart[q];
+      const bool final_pass = pass == 2 || __ldcg(a.scal + P.sbase + a.o_flag) == 0.0;
+      if (pass == 1 && final_pass) final_mask1 |= 1u << q;
       const int m = P.m;
       const int s_h_out = P.sbase + (pass == 1 ? a.o_h1 : a.o_h2);
       T *wvec = static_cast<T *>(P.w);
@@ -310,11 +381,10 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step_batch(const __grid_co
         f = 1.0 / sqrt(__ldcg(a.scal + P.sbase + a.o_nrm));
         if (!isfinite(f)) f = 1.0;
       }
-      __syncthreads();
       for (int j = threadIdx.x; j < m * NR; j += blockDim.x) s_h[j] = -__ldcg(a.scal + s_h_out + j);
       __syncthreads();
       double nx = 0.0;
-      for (int64_t ip = (int64_t)c * blockDim.x + threadIdx.x; ip < npf; ip += (int64_t)G * blockDim.x) {
+      for (int64_t ip = (int64_t)bc * blockDim.x + threadIdx.x; ip < npf; ip += (int64_t)bg * blockDim.x) {
         Pack<T, W> acc = pk_ld_cg<T, W>(wvec, ip);
         for (int j0 = 0; j0 < m; j0 += JB) {
           Pack<T, W> v[JB];
@@ -337,7 +407,7 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step_batch(const __grid_co
         }
         pk_st<T, W>(wvec, ip, acc);
       }
-      if (tail_mine && c == 0 && threadIdx.x == 0) {
+      if (tail_mine && bc == 0 && threadIdx.x == 0) {
         T acc = ld_cg(wvec + (n - 1));
         for (int j = 0; j < m; ++j)
           Num<T>::fma(acc, Num<T>::from_red(s_h + j * NR), static_cast<const T *>(P.v[j])[n - 1]);
@@ -354,13 +424,15 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step_batch(const __grid_co
           double r = 0.0;
 #pragma unroll
           for (int w = 0; w < CV_WARPS; ++w) r += s_part[w][0];
-          a.partials[(size_t)q * a.pstride + (size_t)MI * NR * G + 2048 + c] = r;
+          p_nx[q * 512 + bc] = r;
+          if (bc == 0) p_nx[CV_MAX_BATCH * 512 + q] = (double)bg;  // how many partials this problem has
         }
       }
     }
     if (pass == 2 || !any_again) break;
     grid_barrier_with(a.bar, [&]() {});  // pass 2 reads rows other CTAs have just rewritten
   }
+  (void)final_mask1;
   // ---------------- kernel tail: the last CTA to finish sums the explicit |v_new|^2 partials ---------
   __syncthreads();
   __shared__ bool s_last_b;
@@ -372,7 +444,8 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step_batch(const __grid_co
   if (s_last_b) {
     __threadfence();
     for (int q = warp; q < a.nprob; q += CV_WARPS) {
-      double r = ordered_lane_sum(a.partials + (size_t)q * a.pstride + (size_t)MI * NR * G + 2048, G, lane);
+      const int cnt = (int)__ldcg(p_nx + CV_MAX_BATCH * 512 + q);
+      double r = ordered_lane_sum(p_nx + q * 512, cnt, lane);
       r = warp_sum(r);
       if (lane == 0) a.scal[a.prob[q].sbase + a.o_nrm] = r;  // read as the lagged norm by the next step
     }

@@ -1048,12 +1048,15 @@ int lockstep_orth(cv_ctx *ctx, int64_t n, int cplx_, int np, LockstepSolve *cons
   }
   const int cap = it->second * ctx->sms;
   const int mi_max = cplx_ ? ORTH_MI<cplx>::value : ORTH_MI<double>::value;
-  const int ny = (mmax + mi_max - 1) / mi_max;
   int64_t need = (n / W + CV_BLOCK - 1) / CV_BLOCK;
-  if (need < ny) need = ny;
+  if (need < CV_BATCH_SLABS) need = CV_BATCH_SLABS;
   const int grid = (int)(need < cap ? need : cap);
-  a.pstride = (int64_t)mi_max * (cplx_ ? 2 : 1) * grid + 2048 + grid + 64;
-  CV_REQUIRE((size_t)a.pstride * np <= CV_N_PARTIALS, "lock-step orth: partial sums exceed the scratch area");
+  a.pstride = 0;  // one shared region: [MI*NR*G slab partials | CV_MAX_BATCH*512 ww | CV_MAX_BATCH*512 nx | counts]
+  CV_REQUIRE(grid <= 512, "lock-step orth: grid of %d CTAs exceeds the per-problem partial capacity", grid);
+  CV_REQUIRE((size_t)mi_max * 2 * grid + 2 * CV_MAX_BATCH * 512 + 64 <= CV_N_PARTIALS, "lock-step orth: partial sums exceed the scratch area");
+  int total_slabs = 0;
+  for (int q = 0; q < np; ++q) total_slabs += (P[q]->nc + P[q]->j + 1 + mi_max - 1) / mi_max;
+  CV_REQUIRE(grid >= total_slabs && grid >= np, "lock-step orth: grid of %d CTAs smaller than %d slabs", grid, total_slabs);
   a.partials = ctx->partials;
   a.bar = ctx->counters + CV_COUNTER_BAR;
   a.ticket = ctx->counters + CV_COUNTER_PUSH;
