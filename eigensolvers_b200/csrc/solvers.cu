@@ -310,7 +310,6 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
       stats->n_matvec++;
       basis[nc + j] = V(j);
       const int nb = nc + j + 1;
-      const void *wp[1] = {w};
       // Classical Gram-Schmidt against [C, V], repeated only if the projection cancelled the
       // vector down to less than eta of its norm (Daniel-Gragg-Kaufman-Stewart), normalisation
       // and the halo push of the new basis vector: ONE fused persistent kernel whose scalars land
@@ -343,13 +342,6 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
         if (mb[S_FLAG] != 0.0) {
           stats->n_reorth++;
           cv_prof_add_bytes(ctx, 1, (double)(2 * nb + 2) * (double)n * (cplx_ ? 16.0 : 8.0));  // second pass
-        }
-        static const int dbg = getenv("EIGB200_DEBUG") ? atoi(getenv("EIGB200_DEBUG")) : 0;
-        if (dbg && (mb[S_FLAG] != 0.0 || !(mb[S_NRM] > 0) || (dbg > 1 && j_outer >= dbg))) {
-          double q1 = 0, q2 = 0;
-          for (int i = 0; i < nb * NR; ++i) q1 += mb[S_H1 + i] * mb[S_H1 + i], q2 += mb[S_H2 + i] * mb[S_H2 + i];
-          fprintf(stderr, "[orth] outer %d j %d nc %d nb %d ww %.17g sum_h1^2 %.17g flag %g sum_h2^2 %.17g nrm2 %.17g beta %.6g\n",
-                  j_outer, j, nc, nb, mb[S_W + 2], q1, mb[S_FLAG], q2, mb[S_NRM], beta);
         }
       } else {
         CV_TRY(arnoldi_orth_unfused(ctx, n, cplx_, nc, nb, basis, w, B, ldb, j, hcur, stats, st));

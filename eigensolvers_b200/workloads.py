@@ -41,6 +41,8 @@ WORKLOADS = {
     "c4small": dict(kind="osc_lindep", dims=(10, 8, 6, 5), nBlock=2, level=8, L=100, maxit=2, eConv=1e-15, tol=1e-1),
     "c5": dict(kind="osc_feast", dims=(20, 10, 10, 10, 10, 10, 10), m0=6, nc=16, levels=(7, 9), maxit=3, eConv=1e-6,
                tol=1e-2, nBlock=3),
+    "c5conv": dict(kind="osc_feast", dims=(20, 10, 10, 10, 10, 10, 10), m0=6, nc=16, levels=(7, 9), maxit=14, eConv=1e-6,
+                   tol=1e-2, nBlock=3),
     "c5mid": dict(kind="osc_feast", dims=(20, 10, 10, 10, 10, 10), m0=6, nc=16, levels=(7, 9), maxit=3, eConv=1e-6,
                   tol=1e-2, nBlock=3),
     "c5midconv": dict(kind="osc_feast", dims=(20, 10, 10, 10, 10, 10), m0=6, nc=16, levels=(7, 9), maxit=16, eConv=1e-6,
