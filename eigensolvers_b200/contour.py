@@ -159,42 +159,50 @@ def feastDiagonalization(A, Y, nc, quad, eMin, eMax, eConv, maxit, contourEllips
             work[(k, im0)] = (counter() - c0) if counter else 0
             return Q
 
+        block_solve = getattr(typeClass, "solveBlock", None) if (lockstep and Y[0].hasExactAddition) else None
+
+        def do_group(grp, Q):
+            """Several (node, vector) solves advanced in lock step (each carries its own complex shift z_k)."""
+            zs = [nodes[k][1].real if abs(nodes[k][1].imag) < 1e-15 else nodes[k][1] for k, _ in grp]
+            t_task = time.perf_counter()
+            c0 = counter() if counter else 0
+            Qe = block_solve(A, [Y[im0] for _, im0 in grp], zs)
+            dt, dc = time.perf_counter() - t_task, (counter() - c0) if counter else 0
+            per = getattr(typeClass, "lastBlockMatvecs", lambda: [])()
+            tot = float(sum(per)) if len(per) == len(grp) and sum(per) > 0 else 0.0
+            for j, (k, im0) in enumerate(grp):
+                theta = nodes[k][0]
+                mult = -0.50 * wk[k] * eRadius * (contourEllipseFactor * math.cos(theta) + math.sin(theta) * 1j)
+                Q = updateQ(Q, im0, typeClass.real(mult * Qe[j]), 0 if Q[im0] is None else 1)   # feast.py:90-92
+                share = per[j] / tot if tot else 1.0 / len(grp)
+                spent[(k, im0)] = dt * share
+                work[(k, im0)] = per[j] if tot else dc // len(grp)
+            return Q
+
         if distribute == "dynamic" and world > 1:
             import torch.distributed as dist
             order = _task_order(nodes, N_SUBSPACE, task_cost)
             store = dist.distributed_c10d._get_default_store()
             key = f"eigb200_feast_{_CALLS[0]}_{it}"
+            chunk = 2 if block_solve is not None else 1   # neighbours in cost order: similar length, good lock-step pairs
             while True:
-                idx = store.add(key, 1) - 1          # atomic fetch-and-add shared by all ranks
+                idx = store.add(key, chunk) - chunk      # atomic fetch-and-add shared by all ranks
                 if idx >= len(order):
                     break
-                Q = do_task(order[idx][0], order[idx][1], Q)
+                grp = order[idx:idx + chunk]
+                if len(grp) > 1:
+                    Q = do_group(grp, Q)
+                else:
+                    Q = do_task(grp[0][0], grp[0][1], Q)
         else:
             mine = _assign_tasks(distribute if distribute != "dynamic" else None, rank, world, nodes, N_SUBSPACE, task_cost)
             todo = [(k, im0) for k in range(len(nodes)) for im0 in range(N_SUBSPACE) if (k, im0) in mine]
-            block_solve = getattr(typeClass, "solveBlock", None) if lockstep else None
-            if block_solve is None or not Y[0].hasExactAddition or len(todo) < 2:
+            if block_solve is None or len(todo) < 2:
                 for k, im0 in todo:
                     Q = do_task(k, im0, Q)
             else:
-                # the (node, vector) solves of this rank are independent: advance them in lock step, up to
-                # 8 at a time (each problem carries its own complex shift z_k)
-                for g0 in range(0, len(todo), 8):
-                    grp = todo[g0:g0 + 8]
-                    zs = [nodes[k][1].real if abs(nodes[k][1].imag) < 1e-15 else nodes[k][1] for k, _ in grp]
-                    t_task = time.perf_counter()
-                    c0 = counter() if counter else 0
-                    Qe = block_solve(A, [Y[im0] for _, im0 in grp], zs)
-                    dt, dc = time.perf_counter() - t_task, (counter() - c0) if counter else 0
-                    per = getattr(typeClass, "lastBlockMatvecs", lambda: [])()
-                    tot = float(sum(per)) if len(per) == len(grp) and sum(per) > 0 else 0.0
-                    for j, (k, im0) in enumerate(grp):
-                        theta = nodes[k][0]
-                        mult = -0.50 * wk[k] * eRadius * (contourEllipseFactor * math.cos(theta) + math.sin(theta) * 1j)
-                        Q = updateQ(Q, im0, typeClass.real(mult * Qe[j]), 0 if Q[im0] is None else 1)   # feast.py:90-92
-                        share = per[j] / tot if tot else 1.0 / len(grp)
-                        spent[(k, im0)] = dt * share
-                        work[(k, im0)] = per[j] if tot else dc // len(grp)
+                for g0 in range(0, len(todo), 8):   # up to 8 at a time
+                    Q = do_group(todo[g0:g0 + 8], Q)
         it_prof = {"solve_seconds_this_rank": sum(spent.values()), "matvecs_this_rank": sum(work.values())}
         if world > 1:
             import torch.distributed as dist

@@ -25,3 +25,22 @@ for same in (False, True):
     out = CudaVector.solveBlock(op, B, 0.9)
     print("lockstep same=%s" % same, rt.last_block_matvecs, [float(np.linalg.norm(bs[0 if same else q] - (0.9 * out[q].array - H @ out[q].array)) / np.linalg.norm(bs[q])) for q in range(2)],
           "reorth", rt.stats.get("reorth"), "safe", rt.stats.get("safe_solves"))
+
+# the general-sparsity case of tests/test_gpu_solvers.py::test_lockstep_solves_match_single_solves
+import scipy.sparse as sp
+A = sp.random(3000, 3000, density=0.003, random_state=3, format="csr")
+H2 = (A + A.T + sp.diags(np.linspace(1.0, 9.0, 3000))).tocsr()
+op2 = DeviceOperator.from_host(H2)
+ev = np.linalg.eigvalsh(H2.toarray())
+print("format", op2.format, "nearest eigenvalue distance to 4.3:", np.min(np.abs(ev - 4.3)))
+rng = np.random.default_rng(2)
+for q in range(3):
+    b = rng.standard_normal(3000)
+    try:
+        x = CudaVector.solve(op2, CudaVector(b, dict(o)), 4.3)
+        s = rt.last_solve
+        print("general single", q, "info", s.info, "matvec", s.n_matvec, "outer", s.n_outer, "resid", s.resid)
+    except Exception as e:
+        s = rt.last_solve
+        print("general single", q, "EXC", type(e).__name__, "info", s.info, "matvec", s.n_matvec, "outer", s.n_outer, "resid", s.resid, "bnorm", s.b_norm)
+    import warnings; warnings.resetwarnings()
