@@ -271,12 +271,14 @@ def test_lockstep_solves_match_single_solves(rt, nrhs, kind, cplx):
     else:
         rng = np.random.default_rng(3)
         A = sp.random(3000, 3000, density=0.003, random_state=3, format="csr")
-        H = (A + A.T + sp.diags(np.linspace(1.0, 9.0, 3000))).tocsr()
+        H = (0.1 * (A + A.T) + sp.diags(np.linspace(1.0, 9.0, 3000))).tocsr()
         op = DeviceOperator.from_host(H)
         assert op.format in ("sell", "csr")
-        ev = np.linalg.eigvalsh(H.toarray())            # shift in the middle of the widest gap near 4.3
-        near = np.where((ev[:-1] > 4.0) & (ev[1:] < 4.6))[0]
-        k = near[np.argmax(ev[near + 1] - ev[near])]
+        # shift in the middle of a gap with ~1 % of the spectrum below it: interior, but a system the
+        # one-problem GCROT(20,20) itself solves to 1e-9 (at sigma = 4.3 on the unscaled matrix it
+        # stagnates at 1e-6 after 60 000 applications — as SciPy's does: not a lock-step question)
+        ev = np.linalg.eigvalsh(H.toarray())
+        k = 30 + int(np.argmax(np.diff(ev[30:45])))
         base = 0.5 * (ev[k] + ev[k + 1])
     n = H.shape[0]
     rng = np.random.default_rng(nrhs)
