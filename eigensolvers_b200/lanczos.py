@@ -1,19 +1,23 @@
-"""Restarted (block) inexact shift-and-invert Lanczos — the host control flow that drives the
-vector plug-in.  Same call signature, status dictionary, return values and failure behaviour as
-the reference's ``inexactLanczosDiagonalization`` (inexact_Lanczos.py:229-443); written against
-the ``AbstractVector`` interface only, so it runs with ``CudaVector`` on the GPU and with the
-CPU oracle in the parity tests.  On a machine that has the reference checked out, the
-reference's own unchanged driver can be used with ``CudaVector`` instead.
+"""Stand-alone restarted (block) inexact shift-and-invert Lanczos driver for the vector plug-in.
 
-Algorithm (per outer iteration): grow a Krylov list Y by solving (sigma - H) w = y for the last
-nBlock vectors, Gram-Schmidt the results against Y, extend the small overlap/Hamiltonian
-matrices S, Hm by one column each, Rayleigh-Ritz in the Loewdin-orthogonalised basis, order the
-Ritz pairs with `pick`, test the change of the nBlock picked eigenvalues, restart from the
-picked Ritz vectors after L-1 steps.
+The product path runs the REFERENCE'S OWN `inexactLanczosDiagonalization` unchanged on
+`CudaVector` (eigensolvers_b200/refdrivers.py, tests/test_gpu_dropin.py, bench.py).  This module
+exists for two things the reference's file cannot give:
+
+  * a driver on machines without a reference checkout — same call signature, status dictionary,
+    return values and failure behaviour as inexact_Lanczos.py:229-443 (tests/test_oracle.py: driven
+    with a NumPy vector class it reproduces the reference's runs bit for bit, same Krylov steps);
+  * LOCK-STEP block solves: the reference normalises each solve's result before it requests the
+    next (inexact_Lanczos.py:319-327), which serialises the nBlock independent solves of a Krylov
+    step; here they are requested together (`solveBlock`) when the vector class offers it.
+
+Structure: a `_KrylovSpace` object owns the list of vectors with its overlap / Hamiltonian matrices
+and knows how to grow, diagonalise (Rayleigh-Ritz in the Loewdin basis) and collapse itself; the
+driver function is the schedule of outer (restart) and inner (growth) steps around it.
 
 Deviations from the reference, both of which only remove crashes:
-  * `saveTNSsEachIteration` defaults to False (the reference's default True raises
-    AttributeError for non-TTNS vectors); when True, vectors exposing `.ttns.saveToHDF5` are saved.
+  * `saveTNSsEachIteration` defaults to False (the reference's default True raises AttributeError
+    for non-TTNS vectors); when True, vectors exposing `.ttns.saveToHDF5` are saved.
   * a linear dependency or zero vector on the very first Krylov step returns NaN eigenvalues
     instead of raising UnboundLocalError.
 """
@@ -29,92 +33,128 @@ from .hostmath import (basisTransformation, diagonalizeHamiltonian, eigenvalueRe
 from .runlog import LanczosRunLog
 from .vector_api import AbstractVector
 
-
-def _getStatus(status, guessVector, nBlock):
-    """Defaults of the status dictionary, overridden key by key by the user's dict
-    (inexact_Lanczos.py:23-82; no whitelist)."""
-    out = {"ref": [], "residual": np.inf, "nBlock": nBlock,
-           "flagAddition": guessVector.hasExactAddition,
-           "outerIter": 0, "innerIter": 0, "cumIter": 0, "iBlock": 0,
-           "zeroVector": False, "isConverged": False, "lindep": False,
-           "futileRestarts": 0, "startTime": time.time(), "runTime": 0.0,
-           "KSmaxD": [], "fitmaxD": None, "phase": 1}
-    if status is not None:
-        out.update(status)
-    return out
+_STATUS_DEFAULTS = dict(ref=None, residual=np.inf, nBlock=None, flagAddition=None, outerIter=0, innerIter=0,
+                        cumIter=0, iBlock=0, zeroVector=False, isConverged=False, lindep=False,
+                        futileRestarts=0, startTime=None, runTime=0.0, KSmaxD=None, fitmaxD=None, phase=1)
 
 
-def generateSubspace(Hop, vec, sigma, eConv):
-    """One shift-invert step: solve, then normalise unless the result is (numerically) zero,
-    i.e. norm <= 0.001*eConv (inexact_Lanczos.py:84-105)."""
-    typeClass = type(vec)
-    out = typeClass.solve(Hop, vec, sigma)
-    if typeClass.norm(out) > 0.001 * eConv:
-        return typeClass.normalize(out), True
-    return out, False
+def _initial_status(user, first_vector, nBlock):
+    """Status dictionary: defaults, then every key of the user's dict on top (no whitelist — the
+    reference's tests pass unrelated keys through it; inexact_Lanczos.py:23-82)."""
+    st = dict(_STATUS_DEFAULTS)
+    st.update(ref=[], KSmaxD=[], nBlock=nBlock, flagAddition=first_vector.hasExactAddition, startTime=time.time())
+    st.update(user or {})
+    return st
 
 
-def _solve_block(typeClass, Hop, vecs, sigma):
-    """The nBlock shifted solves of one Krylov step.  They are independent (inexact_Lanczos.py:319-320),
-    so a vector class that offers `solveBlock` may advance them together (CudaVector: lock-step GCROT,
-    one pass over H per Arnoldi step for the whole block); the results equal the one-by-one solves."""
-    fn = getattr(typeClass, "solveBlock", None)
-    if fn is None:
-        return None
-    return fn(Hop, vecs, sigma)
+class _KrylovSpace:
+    """The Krylov list Y with S = <Y|Y> and Hm = <Y|H|Y>, kept current column by column."""
+
+    def __init__(self, vecClass, H, vectors):
+        self.vc, self.H = vecClass, H
+        self.Y = list(vectors)
+        self.S = vecClass.overlapMatrix(self.Y)
+        self.Hm = None          # filled by measure(); the initial-guess check comes first
+        self.ritz = None        # (values, coefficients) of the last Rayleigh-Ritz, ordered by `pick`
+
+    def measure(self):
+        self.Hm = self.vc.matrixRepresentation(self.H, self.Y)
+
+    def is_orthonormal(self, tol):
+        return np.allclose(self.S, np.eye(len(self.Y)), rtol=tol, atol=tol)
+
+    def absorb(self, candidate):
+        """Gram-Schmidt `candidate` against Y (reference semantics, numpyVector.py:121-145); append it
+        and one column to S and Hm.  False when it is linearly dependent (GS returned None)."""
+        q = self.vc.orthogonalize_against_set(candidate, self.Y)
+        if q is None:
+            return False
+        self.Y.append(q.compress())
+        both = getattr(self.vc, "extendBoth", None)
+        if both is not None:      # one SpMV + one pass over the list for the two columns
+            self.S, self.Hm = both(self.H, self.Y, self.S, self.Hm)
+        else:
+            self.S = self.vc.extendOverlapMatrix(self.Y, self.S)
+            self.Hm = self.vc.extendMatrixRepresentation(self.H, self.Y, self.Hm)
+        return True
+
+    def rayleigh_ritz(self, pick, status, log):
+        """Ritz pairs in the Loewdin-orthogonalised basis (util_funcs.py:346-385), ordered by `pick`."""
+        status, lowdin = lowdinOrthoMatrix(self.S, status)
+        assert not status["lindep"]          # absorb() has already refused dependent vectors
+        values, rot = diagonalizeHamiltonian(lowdin, self.Hm, log)
+        coeff = lowdin @ rot
+        order = pick(coeff, self.Y, values)
+        assert len(order) == len(values), f"{len(values)=} {len(order)=}"
+        self.ritz = (values[order], coeff[:, order])
+        return status
+
+    def collapse_to_ritz_vectors(self, count=None):
+        """Replace Y by Ritz vectors: all of them (final answer) or the first `count`, each normalised
+        on its own and NOT re-orthogonalised (restart, inexact_Lanczos.py:414-425)."""
+        coeff = self.ritz[1]
+        if count is None:
+            self.Y = basisTransformation(self.Y, coeff)
+        else:
+            self.Y = [self.vc.normalize(basisTransformation(self.Y, coeff[:, b])[0]) for b in range(count)]
+        self.S = self.vc.overlapMatrix(self.Y)
 
 
-def checkConvergence(ev, eConv, status, printObj=None):
-    """Relative change of the sorted first nBlock picked eigenvalues against the previous
-    step's, from the second cumulative step on (inexact_Lanczos.py:115-143)."""
-    nBlock = status["nBlock"]
-    current = np.sort(ev[0:nBlock])
-    converged = False
+def _shifted_solves(vc, Hsolve, sources, sigma, eConv, lockstep):
+    """Normalised results of (sigma - H) w = y for the given sources, in order; the list stops in front of
+    the first (numerically) zero result, whose norm is returned as second value
+    (inexact_Lanczos.py:84-105, 319-327: norm <= 0.001*eConv counts as zero)."""
+    together = getattr(vc, "solveBlock", None) if (lockstep and len(sources) > 1) else None
+    raw = together(Hsolve, sources, sigma) if together is not None else None
+    done = []
+    for i, y in enumerate(sources):
+        w = raw[i] if raw is not None else vc.solve(Hsolve, y, sigma)
+        size = vc.norm(w)
+        if not size > 0.001 * eConv:
+            return done, size
+        done.append(vc.normalize(w))
+    return done, None
+
+
+def _update_convergence(values, eConv, status, log):
+    """Relative change of the sorted first nBlock picked values against the previous step's, from the
+    second cumulative step on (inexact_Lanczos.py:115-143)."""
+    now = np.sort(values[:status["nBlock"]])
+    hit = False
     if status["cumIter"] > 1:
-        residual = eigenvalueResidual(current, status["ref"][-1])
-        status["residual"] = residual
-        converged = residual <= eConv
-    status["isConverged"] = bool(converged)
+        status["residual"] = eigenvalueResidual(now, status["ref"][-1])
+        hit = status["residual"] <= eConv
+    status["isConverged"] = bool(hit)
     status["runTime"] = time.time() - status["startTime"]
-    if printObj is not None:
-        printObj.writeFile("summary", current, status)
-    status["ref"].append(current)
-    if len(status["ref"]) > 2:
-        status["ref"].pop(0)
+    if log is not None:
+        log.writeFile("summary", now, status)
+    status["ref"] = (status["ref"] + [now])[-2:]
     return status
 
 
-def terminateRestart(blockEnergies, eConv, status, num=3):
-    """Count restarts that did not improve the block energies while lindep is flagged; give up
-    after more than `num` (inexact_Lanczos.py:167-194)."""
-    previous = status["ref"][0]
-    if status["lindep"]:
-        if eigenvalueResidual(blockEnergies, previous) > max(1e-9, eConv):
-            status["futileRestarts"] += 1
-    if status["futileRestarts"] > num:
+def _out_of_budget(status, maxit, L):
+    last = status["outerIter"] == maxit - 1 and status["innerIter"] == L - 1
+    if last and not status["isConverged"]:
+        print("Alert: Lanczos iterations is not converged!")
+    return last
+
+
+def _futile(block_values, eConv, status, limit=3):
+    """Restarts that do not move the block energies while lindep is flagged are counted; more than
+    `limit` of them end the run (inexact_Lanczos.py:167-194)."""
+    if status["lindep"] and eigenvalueResidual(block_values, status["ref"][0]) > max(1e-9, eConv):
+        status["futileRestarts"] += 1
+    if status["futileRestarts"] > limit:
         warnings.warn("Lindep and did not have fruitful restarts")
         return True
     return False
 
 
-def analyzeStatus(status, maxit, L):
-    """Continue unless converged or the last inner step of the last outer iteration was reached
-    (inexact_Lanczos.py:197-222)."""
-    if status["isConverged"]:
-        return False
-    if status["outerIter"] == maxit - 1 and status["innerIter"] == L - 1:
-        print("Alert: Lanczos iterations is not converged!")
-        return False
-    return True
-
-
-def _extend_small_matrices(typeClass, H, Ylist, Smat, Hmat):
-    fused = getattr(typeClass, "extendBoth", None)
-    if fused is not None:  # one SpMV + one pass over the Krylov list for both columns
-        return fused(H, Ylist, Smat, Hmat)
-    Smat = typeClass.extendOverlapMatrix(Ylist, Smat)
-    Hmat = typeClass.extendMatrixRepresentation(H, Ylist, Hmat)
-    return Smat, Hmat
+def _checkpoint(space, status, saveDir):
+    os.makedirs(saveDir, exist_ok=True)
+    extra = {"status": status, "eigencoefficients": space.ritz[1], "eigenvalues": space.ritz[0]}
+    for i, vec in enumerate(space.Y):
+        vec.ttns.saveToHDF5(f"{saveDir}/tns_{status['cumIter']}_{i}.h5", additionalInformation=extra)
 
 
 def inexactLanczosDiagonalization(H, v0, sigma, L, maxit, eConv, checkFitTol=1e-7,
@@ -128,139 +168,95 @@ def inexactLanczosDiagonalization(H, v0, sigma, L, maxit, eConv, checkFitTol=1e-
     v0       guess vector or list of mutually orthogonal guess vectors (block Lanczos)
     L        Krylov vectors per block between restarts;  maxit  outer iterations
     eConv    relative eigenvalue-change tolerance
+    lockstep request the nBlock solves of a step together when the vector class has `solveBlock`
     Returns (ev, Ylist, status): ALL Ritz values ordered by `pick`, the Ritz vectors, the status.
     """
     if issubclass(type(v0), AbstractVector):
         v0 = [v0]
     else:
         assert isinstance(v0, (list, tuple, np.ndarray)), f"{v0=} {type(v0)=}"
-    if Hsolve is None:
-        Hsolve = H
-    typeClass = type(v0[0])
-    nBlock = len(v0)
+    Hsolve = H if Hsolve is None else Hsolve
+    vc, nBlock = type(v0[0]), len(v0)
 
-    Ylist = list(v0)
-    Smat = typeClass.overlapMatrix(Ylist)
-    if not np.allclose(Smat, np.eye(nBlock), rtol=1e-3, atol=1e-3):
+    space = _KrylovSpace(vc, H, v0)
+    if not space.is_orthonormal(1e-3):
         if nBlock > 1:
-            raise RuntimeError(f"Input vectors not orthogonalized: {Smat=}")
-        Ylist[0].normalize()  # single guess: normalise quietly (inexact_Lanczos.py:292-295)
-        Smat[0, 0] = 1
-    Hmat = typeClass.matrixRepresentation(H, Ylist)
+            raise RuntimeError(f"Input vectors not orthogonalized: Smat={space.S}")
+        space.Y[0].normalize()   # a single guess is normalised quietly (inexact_Lanczos.py:292-295)
+        space.S[0, 0] = 1
+    space.measure()
 
-    status = _getStatus(status, Ylist[0], nBlock)
-    if pick is None:
-        pick = get_pick_function_close_to_sigma(sigma)
+    status = _initial_status(status, space.Y[0], nBlock)
+    pick = pick if pick is not None else get_pick_function_close_to_sigma(sigma)
     assert callable(pick)
-    printObj = LanczosRunLog(Ylist[0], sigma, L, maxit, eConv, checkFitTol, writeOut, eShift,
-                             convertUnit, pick, status, outFileName, summaryFileName)
-    printObj.fileHeader()
+    log = LanczosRunLog(space.Y[0], sigma, L, maxit, eConv, checkFitTol, writeOut, eShift,
+                        convertUnit, pick, status, outFileName, summaryFileName)
+    log.fileHeader()
 
-    ev = np.array([np.nan] * len(Ylist))
-    aborted = False          # linear dependency (or an unusable zero vector): leave both loops
-    keepGoing = True
-    for outerIter in range(maxit):
-        uSH = None           # Ritz coefficients of the current Krylov list, none yet
-        status["outerIter"] = outerIter
-        status["KSmaxD"] = [Ylist[0].maxD]
-        status["fitmaxD"] = None
-        for innerIter in range(1, L):
-            status["innerIter"] = innerIter
+    ev = np.full(len(space.Y), np.nan)
+    for outer in range(maxit):
+        status.update(outerIter=outer, KSmaxD=[space.Y[0].maxD], fitmaxD=None)
+        space.ritz = None
+        verdict = "restart"                      # how this outer iteration ends
+        for inner in range(1, L):
+            status["innerIter"] = inner
             status["cumIter"] += 1
-            # -- new directions: the last nBlock vectors, visited back to front (SURVEY §9.1)
-            fresh = []
-            nonzero = True
-            block = _solve_block(typeClass, Hsolve, [Ylist[-iBlock] for iBlock in range(1, nBlock + 1)], sigma) \
-                if (nBlock > 1 and lockstep) else None
-            for iBlock in range(1, nBlock + 1):
-                if block is None:
-                    out, nonzero = generateSubspace(Hsolve, Ylist[-iBlock], sigma, eConv)
-                else:  # same test as generateSubspace, on the result of the lock-step solve
-                    out = block[iBlock - 1]
-                    nonzero = typeClass.norm(out) > 0.001 * eConv
-                    if nonzero:
-                        out = typeClass.normalize(out)
-                if not nonzero:
-                    status["zeroVector"] = True
-                    warnings.warn(f"Alert: zero vector: ||inv(H-sigma)vec||={typeClass.norm(out):5.3e}")
-                    break
-                fresh.append(out)
-            if not nonzero:
-                # inexact_Lanczos.py:321-329: leave the Krylov loop; the code after it restarts
-                # from the last Ritz vectors.  Without any (first step) there is nothing to
-                # restart from (the reference fails on stale/unbound data there): stop.
-                aborted = uSH is None
+            # new directions from the last nBlock vectors, visited back to front (SURVEY §9.1)
+            fresh, zero_norm = _shifted_solves(vc, Hsolve, [space.Y[-b] for b in range(1, nBlock + 1)], sigma, eConv,
+                                               lockstep)
+            if zero_norm is not None:
+                status["zeroVector"] = True
+                warnings.warn(f"Alert: zero vector: ||inv(H-sigma)vec||={zero_norm:5.3e}")
+                # the reference leaves the Krylov loop and restarts from the last Ritz vectors; with none
+                # yet (first step) there is nothing to restart from: stop
+                verdict = "restart" if space.ritz is not None else "abort"
                 break
-            # -- orthogonalise in list order, append, grow S and H by one column each
-            lindepProblem = False
-            for iBlock in range(nBlock):
-                status["iBlock"] = iBlock
-                q = typeClass.orthogonalize_against_set(fresh[iBlock], Ylist)
-                if q is None:
-                    lindepProblem = True
-                    if printObj.writeOut:
-                        warnings.warn(f"Linear dependency problem in iteration {outerIter} "
-                                      f"and microiteration {innerIter} for block state {iBlock},"
-                                      f" abort current Lanczos iteration and restart.")
+            # orthogonalise in list order, append, grow S and Hm
+            dependent = False
+            for b, w in enumerate(fresh):
+                status["iBlock"] = b
+                if not space.absorb(w):
+                    dependent = True
+                    if log.writeOut:
+                        warnings.warn(f"Linear dependency problem in iteration {outer} and microiteration {inner} "
+                                      f"for block state {b}, abort current Lanczos iteration and restart.")
                     break
-                Ylist.append(q.compress())
-                status["KSmaxD"].append(Ylist[-1].maxD)
-                Smat, Hmat = _extend_small_matrices(typeClass, H, Ylist, Smat, Hmat)
-            printObj.writeFile("iteration", status)
-            printObj.writeFile("overlap", Smat)
-            printObj.writeFile("KSmaxD", status)
-            if lindepProblem:
-                # inexact_Lanczos.py:356-359: results are NaN, the solver returns
-                ev = np.array([np.nan] * len(Ylist))
-                aborted = True
+                status["KSmaxD"].append(space.Y[-1].maxD)
+            log.writeFile("iteration", status)
+            log.writeFile("overlap", space.S)
+            log.writeFile("KSmaxD", status)
+            if dependent:                        # inexact_Lanczos.py:356-359: NaN results, the solver returns
+                ev = np.full(len(space.Y), np.nan)
+                verdict = "abort"
                 break
-            # -- Rayleigh-Ritz in the Loewdin basis
-            status, uS = lowdinOrthoMatrix(Smat, status)
-            assert not status["lindep"]  # Gram-Schmidt above should have caught it
-            ev, uv = diagonalizeHamiltonian(uS, Hmat, printObj)
-            uSH = uS @ uv
-            idx = pick(uSH, Ylist, ev)
-            assert len(idx) == len(ev), f"{len(ev)=} {len(idx)=}"
-            ev = ev[idx]
-            uSH = uSH[:, idx]
-            status = checkConvergence(ev, eConv, status, printObj)
-            keepGoing = analyzeStatus(status, maxit, L)
+            status = space.rayleigh_ritz(pick, status, log)
+            ev = space.ritz[0]
+            status = _update_convergence(ev, eConv, status, log)
             if saveTNSsEachIteration:
-                os.makedirs(saveDir, exist_ok=True)
-                extra = {"status": status, "eigencoefficients": uSH, "eigenvalues": ev}
-                for iv, vec in enumerate(Ylist):
-                    vec.ttns.saveToHDF5(f"{saveDir}/tns_{status['cumIter']}_{iv}.h5",
-                                        additionalInformation=extra)
-            if not keepGoing:
+                _checkpoint(space, status, saveDir)
+            if status["isConverged"] or _out_of_budget(status, maxit, L):
+                verdict = "finish"
                 break
-        if aborted:
+        if verdict == "abort":
             break
-        if not keepGoing:
-            # final back-transformation of ALL Ritz vectors and orthonormality check
-            Ylist = basisTransformation(Ylist, uSH)
-            Smat = typeClass.overlapMatrix(Ylist)
-            if not np.allclose(Smat, np.eye(len(Ylist)), rtol=checkFitTol, atol=checkFitTol):
-                warnings.warn(f"Alert:Final eigenvectors are not properly fitted. S=\n{Smat}")
-            status["fitmaxD"] = [item.maxD for item in Ylist]
-            printObj.writeFile("fitmaxD", status)
+        if verdict == "finish":                  # back-transform ALL Ritz vectors, check orthonormality
+            space.collapse_to_ritz_vectors()
+            if not space.is_orthonormal(checkFitTol):
+                warnings.warn(f"Alert:Final eigenvectors are not properly fitted. S=\n{space.S}")
+            status["fitmaxD"] = [v.maxD for v in space.Y]
+            log.writeFile("fitmaxD", status)
             break
-        # -- plain restart from the nBlock picked Ritz vectors (normalised, not re-orthogonalised)
-        guesses = []
-        for iBlock in range(nBlock):
-            g = basisTransformation(Ylist, uSH[:, iBlock])
-            guesses.append(typeClass.normalize(g[0]))
-        Ylist = guesses
-        Smat = typeClass.overlapMatrix(Ylist)
-        Hmat = typeClass.matrixRepresentation(H, Ylist)
-        if not np.allclose(Smat, np.eye(len(Ylist)), rtol=checkFitTol, atol=checkFitTol):
-            warnings.warn(f"Alert:Final eigenvectors are not properly fitted. S=\n{Smat}")
+        # plain restart from the nBlock picked Ritz vectors
+        space.collapse_to_ritz_vectors(nBlock)
+        space.measure()
+        if not space.is_orthonormal(checkFitTol):
+            warnings.warn(f"Alert:Final eigenvectors are not properly fitted. S=\n{space.S}")
             break
-        evNew = sla.eigvalsh(Hmat, Smat)
-        if terminateRestart(evNew, eConv, status):
+        if _futile(sla.eigvalsh(space.Hm, space.S), eConv, status):
             break
-        status["fitmaxD"] = [item.maxD for item in Ylist]
-        printObj.writeFile("fitmaxD", status)
+        status["fitmaxD"] = [v.maxD for v in space.Y]
+        log.writeFile("fitmaxD", status)
 
-    printObj.writeFile("results", ev)
-    printObj.fileFooter()
-    return ev, Ylist, status
+    log.writeFile("results", ev)
+    log.fileFooter()
+    return ev, space.Y, status
