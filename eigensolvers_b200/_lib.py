@@ -43,6 +43,7 @@ SIGNATURES = {
     "cv_ctx_set_reorth_eta": (_i, [_vp, _d]),
     "cv_ctx_set_recycle": (_i, [_vp, _i]),
     "cv_ctx_set_option": (_i, [_vp, C.c_char_p, _d]),
+    "cv_solve_precond": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _vp, _vp, _vp, _d, _d, _i, _i, _i, _vp, _vp, _sz, _vp, _vp]),
     "cv_solve_batch": (_i, [_vp, _vp, _i, _i, _i, _pd, _pd, _pvp, _pvp, _pvp, _d, _d, _i, _i, _i, _vp, _sz, _vp, _vp]),
     "cv_arnoldi_step": (_i, [_vp, _vp, _i64, _i, _i, _pvp, _vp, _d, _d, _pd, _vp]),
     "cv_ctx_trace_read": (_i, [_vp, _pd, _i]),

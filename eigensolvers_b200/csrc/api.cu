@@ -51,6 +51,8 @@ extern "C" int cv_ctx_create(int device, void *scratch_dev, size_t scratch_bytes
   c->prepushed_op = nullptr;
   c->push_early = getenv("EIGB200_PUSH_EARLY") ? atoi(getenv("EIGB200_PUSH_EARLY")) != 0 : true;
   c->slab_mode = getenv("EIGB200_SLAB") ? atoi(getenv("EIGB200_SLAB")) : 1;
+  c->precond_dinv = nullptr;
+  c->precond_z = c->precond_t = nullptr;
   c->launches = 0;
   c->prof = nullptr;
   c->reorth_eta = getenv("EIGB200_REORTH_ETA") ? atof(getenv("EIGB200_REORTH_ETA")) : 0.1;

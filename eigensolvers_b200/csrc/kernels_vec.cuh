@@ -256,6 +256,32 @@ __global__ void __launch_bounds__(CV_BLOCK, 8) k_scale_dev(int64_t n, T *__restr
 }
 
 // ------------------------------------------------------------------------------------------
+// y = d (.) x   element-wise (complex product for complex data; y may alias x).  Diagonal right
+// preconditioner of the shifted solves: z_j = M v_j with M = diag(1 / (sigma - H_ii)) (SciPy's
+// `M=` argument of gcrotmk, _gcrotmk.py:100 `z = rpsolve(v)`).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(CV_BLOCK, 8) k_diag_mul(int64_t n, const T *__restrict__ d, const T *x, T *y) {
+  constexpr int U = 4;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = tid; i0 < n; i0 += U * stride) {
+    T dv[U], xv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      dv[u] = (i < n) ? ld_plain(d + i) : Num<T>::zero();
+      xv[u] = (i < n) ? ld_plain(x + i) : Num<T>::zero();
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n) st_plain(y + i, Num<T>::mul(dv[u], xv[u]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Linear combinations  Y_k = sum_j c[j,k] V_j   (k < NC outputs, one pass over the m inputs)
 // numpyVector.py:105-119 through util_funcs.py:208-231; GCROT's ux / cx (_gcrotmk.py:430-447).
 // Pointers and coefficients travel in kernel parameter space (constant bank, broadcast reads).

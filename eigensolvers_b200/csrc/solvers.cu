@@ -58,6 +58,19 @@ int scal_real(cv_ctx *ctx, int64_t n, int cplx_, double a, const void *x, void *
   return cv_scal(ctx, n, cplx_, cplx_, a, 0.0, x, y, (void *)st);
 }
 
+// y = d (.) x (diagonal preconditioner application)
+int diag_mul(cv_ctx *ctx, int64_t n, int cplx_, const void *d, const void *x, void *y, cudaStream_t st) {
+  cv_prof_scope prof(ctx, 3, st, 3.0 * (double)n * (cplx_ ? 16.0 : 8.0));
+  if (cplx_) {
+    auto kf = k_diag_mul<cplx>;
+    kf<<<cv_occ_grid(ctx, (const void *)kf, n, CV_BLOCK), CV_BLOCK, 0, st>>>(n, (const cplx *)d, (const cplx *)x, (cplx *)y);
+  } else {
+    auto kf = k_diag_mul<double>;
+    kf<<<cv_occ_grid(ctx, (const void *)kf, n, CV_BLOCK), CV_BLOCK, 0, st>>>(n, (const double *)d, (const double *)x, (double *)y);
+  }
+  return cv_check_launch(ctx, "diag_mul");
+}
+
 // Separate-kernel form of one Arnoldi orthogonalisation step (NCCL transport): two tall-skinny
 // passes, the SpMV's dots and the projection coefficients in ONE all-reduce, one copy to the host.
 int arnoldi_orth_unfused(cv_ctx *ctx, int64_t n, int cplx_, int nc, int nb, std::vector<const void *> &basis,
@@ -113,6 +126,8 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
   const size_t ebytes = cplx_ ? 16 : 8;
   const double eps = std::numeric_limits<double>::epsilon();
   double *mb = ctx->mailbox;
+  // right preconditioner M = diag(dinv) (SciPy's `M=`): z_j = M v_j, w = A z_j, ux = M (V y) - U by
+  const void *dinv = ctx->precond_dinv;
 
   // workspace map: r | V[0..m+k] | C ring (k+1) | U ring (k+1)
   const int nV = m + k + 1;
@@ -304,7 +319,12 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
     for (j = 0; j < ml; ++j) {
       void *w = V(j + 1);
       ctx->defer_reduce = true;  // reduced together with the projection coefficients below
-      int rc_mv = cv_spmv_dev(ctx, op, cplx_, mode, sre, sim, V(j), w, 1.0, 0.0, nullptr, false, S_W, st);
+      const void *zj = V(j);
+      if (dinv) {
+        CV_TRY(diag_mul(ctx, n, cplx_, dinv, V(j), ctx->precond_z, st));
+        zj = ctx->precond_z;
+      }
+      int rc_mv = cv_spmv_dev(ctx, op, cplx_, mode, sre, sim, zj, w, 1.0, 0.0, nullptr, false, S_W, st);
       ctx->defer_reduce = false;
       CV_TRY(rc_mv);
       stats->n_matvec++;
@@ -446,7 +466,25 @@ int gcrotmk(cv_ctx *ctx, cv_op *op, int cplx_, int mode, double sre, double sim,
         if (cplx_) coef[((ncol + 1 + c) * 2 + 0) * cs + 1] = -by[c].imag();
       }
       void *outs[2] = {Us(slot_new), Cs(slot_new)};
-      CV_TRY(cv_lincomb_launch(ctx, n, cplx_, cplx_, mt, src.data(), 2, coef.data(), 2, 0, outs, S_CX, st));
+      if (!dinv) {
+        CV_TRY(cv_lincomb_launch(ctx, n, cplx_, cplx_, mt, src.data(), 2, coef.data(), 2, 0, outs, S_CX, st));
+      } else {
+        // t = V y and cx = V hy in one pass over V; ux = M t - U by
+        void *outs1[2] = {ctx->precond_t, Cs(slot_new)};
+        CV_TRY(cv_lincomb_launch(ctx, n, cplx_, cplx_, ncol + 1, src.data(), 2, coef.data(), 2, 0, outs1, S_CX, st));
+        CV_TRY(diag_mul(ctx, n, cplx_, dinv, ctx->precond_t, ctx->precond_t, st));
+        std::vector<const void *> src2(nc + 1);
+        std::vector<double> coef2((size_t)(nc + 1) * cs, 0.0);
+        src2[0] = ctx->precond_t;
+        coef2[0] = 1.0;
+        for (int c = 0; c < nc; ++c) {
+          src2[1 + c] = Us(cu_slots[c]);
+          coef2[(1 + c) * cs] = -by[c].real();
+          if (cplx_) coef2[(1 + c) * cs + 1] = -by[c].imag();
+        }
+        void *outs2[1] = {Us(slot_new)};
+        CV_TRY(cv_lincomb_launch(ctx, n, cplx_, cplx_, nc + 1, src2.data(), 1, coef2.data(), 1, 0, outs2, -1, st));
+      }
     }
     CV_TRY(cv_fetch_scalars(ctx, S_CX, 2, st));
     stats->n_sync++;
@@ -1144,6 +1182,27 @@ extern "C" int cv_arnoldi_step(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int
   out_host[1] = mb[S_NRM];
   for (int i = 0; i < m * NR; ++i) out_host[2 + i] = mb[S_H1 + i] + (mb[S_FLAG] != 0.0 ? mb[S_H2 + i] : 0.0);
   return CV_OK;
+}
+
+extern "C" int cv_solve_precond(cv_ctx *ctx, cv_op *op, int cplx_, int solver, int reverse, double sigma_re,
+                                double sigma_im, const void *b, const void *x0, void *x_out, double rtol, double atol,
+                                int maxiter, int m, int k, const void *dinv_dev, void *work_dev, size_t work_bytes,
+                                cv_solve_stats *stats, void *stream) {
+  CV_REQUIRE(ctx && op && dinv_dev && work_dev, "cv_solve_precond: null argument");
+  CV_REQUIRE(solver == CV_SOLVER_GCROTMK, "cv_solve_precond: a right preconditioner applies to GCROT only (MINRES needs an SPD one)");
+  CV_REQUIRE(((uintptr_t)dinv_dev & 15) == 0, "cv_solve_precond: the diagonal must be 16-byte aligned");
+  const int mm = m <= 0 ? 20 : m, kk = k <= 0 ? mm : k;
+  const size_t base = cv_solve_workspace_bytes(op->n_rows, cplx_, solver, mm, kk);
+  const size_t stride = vec_stride_bytes(op->n_rows, cplx_);
+  CV_REQUIRE(work_bytes >= base + 2 * stride, "cv_solve_precond: workspace needs two more vectors than cv_solve_workspace_bytes()");
+  ctx->precond_dinv = dinv_dev;
+  ctx->precond_z = static_cast<char *>(work_dev) + base;
+  ctx->precond_t = static_cast<char *>(work_dev) + base + stride;
+  ctx->recycle.valid = false;
+  const int rc = cv_solve(ctx, op, cplx_, solver, reverse, sigma_re, sigma_im, b, x0, x_out, rtol, atol, maxiter, m, k, work_dev,
+                          base, stats, stream);
+  ctx->precond_dinv = nullptr;
+  return rc;
 }
 
 extern "C" int cv_solve_batch(cv_ctx *ctx, cv_op *op, int cplx_, int nrhs, int reverse, const double *sigma_re,

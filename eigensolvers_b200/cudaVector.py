@@ -351,17 +351,38 @@ class CudaVector(AbstractVector):
         m_in, k_in = int(options.get("gcrot_m", 20)), int(options.get("gcrot_k", 0))
         nloc = b._nloc
         wbytes = rt.lib.cv_solve_workspace_bytes(nloc, int(cplx), solver, m_in, k_in if k_in else m_in)
+        # opt-in: diagonal right preconditioner (SciPy's M= argument, which the reference never passes):
+        # "jacobi" = 1/(sigma - H_ii), or a CudaVector / array holding the diagonal of M
+        pre = options.get("preconditioner", None)
+        dinv = None
+        if pre is not None and name == "gcrotmk":
+            if isinstance(pre, str):
+                if pre != "jacobi":
+                    raise ValueError(f"unknown preconditioner {pre!r} (expected 'jacobi' or the diagonal of M)")
+                dinv = op.inverse_shifted_diagonal(sigma, bool(reverseGF), cplx)
+            else:
+                pv = pre if isinstance(pre, CudaVector) else CudaVector(np.asarray(pre), b.options)
+                dinv = pv._as_complex_tensor() if cplx else pv._t
+                if dinv.is_complex() != cplx or dinv.numel() != nloc:
+                    raise ValueError("preconditioner diagonal does not match the system's type/length")
+            wbytes += 2 * ((nloc * (16 if cplx else 8) + 255) // 256 * 256)
         work = rt.workspace(wbytes)
         out = rt.empty(nloc, cplx)
         stats = _lib.SolveStats()
         # opt-in: keep GCROT's recycled subspace between successive solves with the same H and sigma
         # (SciPy's CU= argument; the reference does not use it, so the default is off)
-        _lib.check(rt.lib.cv_ctx_set_recycle(rt.ctx, int(bool(options.get("recycle", False)))))
+        _lib.check(rt.lib.cv_ctx_set_recycle(rt.ctx, int(bool(options.get("recycle", False)) and dinv is None)))
         s = complex(sigma)
-        _lib.check(rt.lib.cv_solve(rt.ctx, op.handle, int(cplx), solver, int(bool(reverseGF)), s.real, s.imag,
-                                   bt.data_ptr(), None if x0t is None else x0t.data_ptr(), out.data_ptr(),
-                                   float(tol), float(atol), int(maxiter), m_in, k_in, work.data_ptr(),
-                                   work.numel(), C.byref(stats), rt.stream))
+        if dinv is None:
+            _lib.check(rt.lib.cv_solve(rt.ctx, op.handle, int(cplx), solver, int(bool(reverseGF)), s.real, s.imag,
+                                       bt.data_ptr(), None if x0t is None else x0t.data_ptr(), out.data_ptr(),
+                                       float(tol), float(atol), int(maxiter), m_in, k_in, work.data_ptr(),
+                                       work.numel(), C.byref(stats), rt.stream))
+        else:
+            _lib.check(rt.lib.cv_solve_precond(rt.ctx, op.handle, int(cplx), solver, int(bool(reverseGF)), s.real, s.imag,
+                                               bt.data_ptr(), None if x0t is None else x0t.data_ptr(), out.data_ptr(),
+                                               float(tol), float(atol), int(maxiter), m_in, k_in, dinv.data_ptr(),
+                                               work.data_ptr(), work.numel(), C.byref(stats), rt.stream))
         rt.stats["solves"] += 1
         rt.stats["matvecs"] += stats.n_matvec
         rt.stats["syncs"] += stats.n_sync
@@ -394,6 +415,7 @@ class CudaVector(AbstractVector):
         m_in = int(options.get("gcrot_m", 20)) if nrhs else 20
         k_in = int(options.get("gcrot_k", 0)) if nrhs else 0
         batched = (nrhs >= 2 and rt.world == 1 and options["linearSolver"] == "gcrotmk" and not options.get("recycle", False)
+                   and options.get("preconditioner", None) is None
                    and all(b.options["linearSystemArgs"] is options or b.options["linearSystemArgs"] == options for b in bs)
                    and m_in + 2 * (k_in if k_in else m_in) + 2 <= 64)
         if not batched:

@@ -149,6 +149,17 @@ class KroneckerSumOperator(DeviceOperator):
                                             self.max_offset, self.nnz, C.byref(self.handle)))
         self.format = "kron"
         self.padded_nnz = 0
+        # diagonal of H over this rank's rows (Jacobi preconditioner): sum over the terms of the products of
+        # the factors' diagonal entries at the row's digits
+        rows = np.arange(r0, r1, dtype=np.int64)
+        digit = [((rows // strides[i]) % dims[i]) for i in range(D)]
+        diag = np.zeros(r1 - r0)
+        for coef, factors in self.terms:
+            prod = np.full(r1 - r0, float(coef))
+            for mode, h in factors.items():
+                prod = prod * np.diag(h)[digit[mode]]
+            diag += prod
+        self._diag_host = diag
         if rt.world > 1:
             self._setup_band_halo(self.max_offset, self.max_offset)
 

@@ -36,6 +36,8 @@ class DeviceOperator:
         self.format = "csr"
         self.halo_cols = None
         self.send_idx = None
+        self._diag_host = None    # this rank's diagonal entries H_ii (host float64), for the Jacobi preconditioner
+        self._dinv = {}           # (sigma, reverse, cplx) -> device tensor 1/(sigma - H_ii)
 
     def __del__(self):
         try:
@@ -82,8 +84,10 @@ class DeviceOperator:
         indices = np.ascontiguousarray(A.indices, dtype=np.int32)
         data = np.ascontiguousarray(A.data, dtype=np.float64)
         if rt.world == 1:
+            op._diag_host = np.asarray(A.diagonal(), dtype=np.float64)
             return op._finish(indptr, indices, data, fmt, indices, 0)
         r0, r1 = rt.local_range(A.shape[0])
+        op._diag_host = np.asarray(A.diagonal()[r0:r1], dtype=np.float64)
         lo, hi = int(indptr[r0]), int(indptr[r1])
         return op._finish_sharded(np.ascontiguousarray(indptr[r0:r1 + 1] - lo), indices[lo:hi], data[lo:hi], r0, r1, fmt)
 
@@ -320,6 +324,7 @@ class DeviceOperator:
         indptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
         indices = np.ascontiguousarray(A.indices, dtype=np.int32)
         data = np.ascontiguousarray(A.data, dtype=np.float64)
+        op._diag_host = np.asarray(A.diagonal(k=r0), dtype=np.float64)   # rows are local, columns global
         if rt.world == 1:
             return op._finish(indptr, indices, data, fmt, indices, r0)
         return op._finish_sharded(indptr, indices, data, r0, r1, fmt)
@@ -352,6 +357,28 @@ class DeviceOperator:
                 dst_off = np.ascontiguousarray([i[1][rt.rank] for i in infos], dtype=np.int64)
                 _lib.check(rt.lib.cv_op_set_halo_peers(rt.ctx, self.handle, C.cast(arr, C.POINTER(C.c_void_p)),
                                                        strides.ctypes.data, dst_off.ctypes.data))
+
+    # -- Jacobi preconditioner ---------------------------------------------------------------
+    def inverse_shifted_diagonal(self, sigma, reverse=False, cplx=False):
+        """Device vector 1/(sigma - H_ii) (reverse: 1/(H_ii - sigma)) over this rank's rows, cached per
+        shift: the diagonal right preconditioner of the shifted solves.  Entries whose denominator
+        vanishes (|.| < 1e-300) are left unpreconditioned (1)."""
+        key = (complex(sigma), bool(reverse), bool(cplx))
+        hit = self._dinv.get(key)
+        if hit is not None:
+            return hit
+        if self._diag_host is None:
+            raise NotImplementedError("this operator does not know its diagonal")
+        den = (complex(sigma) - self._diag_host) if not reverse else (self._diag_host - complex(sigma))
+        if not cplx:
+            den = den.real
+        safe = np.abs(den) > 1e-300
+        dinv = np.where(safe, 1.0 / np.where(safe, den, 1.0), 1.0)
+        t = self.rt.upload(np.ascontiguousarray(dinv, dtype=np.complex128 if cplx else np.float64))
+        if len(self._dinv) > 8:
+            self._dinv.clear()
+        self._dinv[key] = t
+        return t
 
     # -- roofline bookkeeping (SURVEY §8d) ----------------------------------------------------
     def algorithmic_bytes(self, cplx=False):

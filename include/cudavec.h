@@ -297,6 +297,16 @@ int cv_solve(cv_ctx *ctx, cv_op *op, int cplx, int solver, int reverse, double s
              double atol, int maxiter, int m, int k, void *work_dev, size_t work_bytes,
              cv_solve_stats *stats, void *stream);
 
+/* cv_solve with a DIAGONAL RIGHT PRECONDITIONER M = diag(dinv) — SciPy's `M=` argument of gcrotmk
+ * (_gcrotmk.py:100 z = M v), which the reference leaves unused: z_j = M v_j, w = A z_j, the solution
+ * update uses the z_j; the residual test is on the true residual b - A x, as in cv_solve.  dinv_dev has
+ * n elements of the vectors' type (e.g. 1/(sigma - H_ii): Jacobi).  GCROT only; work_dev must hold
+ * cv_solve_workspace_bytes() + two more vectors (each n elements rounded up to 256 bytes).          */
+int cv_solve_precond(cv_ctx *ctx, cv_op *op, int cplx, int solver, int reverse, double sigma_re,
+                     double sigma_im, const void *b, const void *x0, void *x_out, double rtol,
+                     double atol, int maxiter, int m, int k, const void *dinv_dev, void *work_dev,
+                     size_t work_bytes, cv_solve_stats *stats, void *stream);
+
 /* LOCK-STEP solves: nrhs (<= 8) independent systems (sigma_q I - H) x_q = b_q with the same operator
  * (the nBlock solves of one block-Lanczos step, inexact_Lanczos.py:319-320; the m0 solves of a FEAST
  * quadrature node, feast.py:190-201) advance one GCROT Arnoldi step at a time together: the matrix

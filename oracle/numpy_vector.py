@@ -110,7 +110,11 @@ class NumpyVectorOracle(AbstractVector):
         opt = b.options["linearSystemArgs"]
         tol, atol, maxiter = opt["linear_tol"], opt["linear_atol"], opt["linearIter"]
         if opt["linearSolver"] == "gcrotmk":
-            wk, conv = spla.gcrotmk(linOp, b.array, x0, rtol=tol, atol=atol, maxiter=maxiter)
+            M = None
+            if opt.get("preconditioner") == "jacobi":   # test counterpart of CudaVector's opt-in option: SciPy's M=
+                den = (sigma - H.diagonal()) if not reverseGF else (H.diagonal() - sigma)
+                M = spla.LinearOperator((n, n), matvec=lambda x: x / den, dtype=dtype)
+            wk, conv = spla.gcrotmk(linOp, b.array, x0, M=M, rtol=tol, atol=atol, maxiter=maxiter)
         elif opt["linearSolver"] == "minres":
             wk, conv = spla.minres(linOp, b.array, x0, rtol=tol, maxiter=maxiter)
         elif opt["linearSolver"] == "pardiso":  # dense -> CSC spsolve, only for the Fortran comparison

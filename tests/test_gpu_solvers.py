@@ -372,3 +372,80 @@ def test_block_lanczos_lockstep_equals_sequential(rt):
     (ev_a, Y_a, st_a), (ev_b, Y_b, st_b) = out
     assert st_a["isConverged"] and st_b["isConverged"] and abs(st_a["cumIter"] - st_b["cumIter"]) <= 1
     np.testing.assert_allclose(np.sort(ev_a[:4]), np.sort(ev_b[:4]), rtol=1e-8)
+
+
+# --------------------------------------------------------------------------------------------
+# opt-in diagonal right preconditioner (SciPy's M= argument)
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("kind", ["csr", "kron"])
+def test_jacobi_preconditioned_solve_matches_scipy(rt, cplx, kind):
+    """options["linearSystemArgs"]["preconditioner"] = "jacobi": GCROT with M = diag(1/(sigma - H_ii)) as the
+    right preconditioner, against scipy.sparse.linalg.gcrotmk(..., M=M) on the same inputs — the same
+    stopping rule on the TRUE residual, a comparable number of operator applications, and far fewer than
+    without (the oscillator Hamiltonian is diagonally dominant)."""
+    from eigensolvers_b200 import CudaVector, KroneckerSumOperator, hamiltonians as hm
+    from eigensolvers_b200.hostmath import calculateTarget
+    dims = (12, 10, 8, 6)
+    H, om = hm.coupled_oscillators(dims, coupling=0.1, seed=1)
+    op = H if kind == "csr" else KroneckerSumOperator.coupled_oscillators(dims, coupling=0.1, seed=1)
+    lev = hm.oscillator_levels(om, 0.1, 20, max_quanta=6)
+    sigma = float(calculateTarget(lev, 8)) + (0.01j if cplx else 0.0)
+    n = H.shape[0]
+    b = np.random.default_rng(5).standard_normal(n)
+    count = [0]
+
+    def shifted(x):
+        count[0] += 1
+        return sigma * x - H @ x
+    dtype = np.complex128 if cplx else np.float64
+    lin = spla.LinearOperator((n, n), matvec=shifted, dtype=dtype)
+    den = sigma - H.diagonal()
+    M = spla.LinearOperator((n, n), matvec=lambda x: x / den, dtype=dtype)
+    x_ref, info = spla.gcrotmk(lin, b.astype(dtype), M=M, rtol=1e-8, atol=0.0, maxiter=1000)
+    assert info == 0
+    mv_ref = count[0]
+    o = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 1000, "linear_tol": 1e-8, "linear_atol": 0.0,
+                              "preconditioner": "jacobi"}}
+    mv0 = rt.stats["matvecs"]
+    x = CudaVector.solve(op, CudaVector(b, dict(o)), sigma).array
+    mv_pre = rt.stats["matvecs"] - mv0
+    res = np.linalg.norm(b - (sigma * x - H @ x)) / np.linalg.norm(b)
+    assert res <= 1.05e-8, res
+    assert np.linalg.norm(x - x_ref) <= 1e-6 * np.linalg.norm(x_ref)
+    assert abs(mv_pre - mv_ref) <= 0.15 * mv_ref + 3, (mv_pre, mv_ref)
+    o2 = {"linearSystemArgs": dict(o["linearSystemArgs"], preconditioner=None)}
+    mv0 = rt.stats["matvecs"]
+    CudaVector.solve(op, CudaVector(b, dict(o2)), sigma)
+    mv_plain = rt.stats["matvecs"] - mv0
+    assert mv_pre * 3 < mv_plain, (mv_pre, mv_plain)
+    # a user-supplied diagonal (the diagonal of M itself) gives the same solve
+    o3 = {"linearSystemArgs": dict(o["linearSystemArgs"], preconditioner=(1.0 / den).astype(dtype))}
+    x3 = CudaVector.solve(op, CudaVector(b, dict(o3)), sigma).array
+    assert np.linalg.norm(x3 - x) <= 1e-10 * np.linalg.norm(x)
+
+
+def test_preconditioned_lanczos_reaches_the_same_eigenpair(rt):
+    """The inexact Lanczos run with Jacobi-preconditioned solves converges to the eigenpair of the plain run
+    (same eConv, same solver tolerance) with a fraction of the operator applications."""
+    from eigensolvers_b200 import CudaVector, DeviceOperator
+    from eigensolvers_b200.lanczos import inexactLanczosDiagonalization
+    from eigensolvers_b200.workloads import build_workload, solver_options
+    w = build_workload("c3small")
+    op = DeviceOperator.from_host(w["H"])
+    runs = []
+    for pre in (None, "jacobi"):
+        o = solver_options(w)
+        o["linearSystemArgs"]["preconditioner"] = pre
+        mv0 = rt.stats["matvecs"]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ev, vecs, st = inexactLanczosDiagonalization(op, CudaVector(w["guesses"][0].copy(), o), w["sigma"], w["L"], w["maxit"],
+                                                         w["eConv"], writeOut=False)
+        warnings.resetwarnings()
+        assert st["isConverged"]
+        runs.append((ev[0], vecs[0].array, rt.stats["matvecs"] - mv0))
+    (e0, v0, mv0), (e1, v1, mv1) = runs
+    assert abs(e0 - e1) <= max(w["eConv"], 1e-10) * abs(e0)
+    assert abs(np.vdot(v0, v1)) >= 1 - 1e-8
+    assert mv1 * 5 < mv0, (mv1, mv0)
