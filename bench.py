@@ -319,6 +319,8 @@ def run_ours(args, w):
     if world > 1 and not feast:
         rt.init_distributed()          # row-sharded mode; FEAST replicates H and distributes nodes instead
     opts = solver_options(w)
+    if args.preconditioner:   # development: the whole run (headline included) with the opt-in preconditioner
+        opts["linearSystemArgs"]["preconditioner"] = args.preconditioner
     H = w["H"]
     use_ref = args.driver == "reference" or (args.driver == "auto" and refdrivers.available())
     if feast:
@@ -548,7 +550,7 @@ def run_ours(args, w):
     # ---- informational: the same run with JACOBI-PRECONDITIONED inner solves (opt-in linearSystemArgs["preconditioner"],
     # SciPy's M= argument).  The reference never passes M, so the headline stays unpreconditioned.
     preconditioned = None
-    if w["kind"] in ("osc", "osc_lindep") and not args.no_extras:
+    if w["kind"] in ("osc", "osc_lindep") and not args.no_extras and not args.preconditioner:
         try:
             popts = {"linearSystemArgs": dict(opts["linearSystemArgs"], preconditioner="jacobi")}
             opp = make_operator()
@@ -630,7 +632,7 @@ def run_ours(args, w):
             "e2e": {"value": e2e_value, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "roofline": dominant, "roofline_spmv": roof_spmv, "roofline_arnoldi_step": roof_orth,
             "roofline_gram_schmidt": roof_gs, "cpu_baseline": cpu, "matrix_free": matrix_free, "lockstep": lockstep, "preconditioned": preconditioned,
-            "result": {"driver": drv_name, "transport": rt.transport, "format": fmt, "converged": converged, "eigenvalues": ev_out,
+            "result": {"driver": drv_name, "options": {k: v for k, v in opts["linearSystemArgs"].items()}, "transport": rt.transport, "format": fmt, "converged": converged, "eigenvalues": ev_out,
                        "cumIter": int(st.get("cumIter", st.get("outerIter", 0))),
                        "n_vectors_returned": len(Y), "lindep_abort": bool(np.any(np.isnan(ev_arr))),
                        "status_at_exit": {k: int(st[k]) for k in ("outerIter", "innerIter", "iBlock") if k in st},
@@ -689,6 +691,8 @@ def main():
                     help="c5, N > 1: also time this distribution of the (node, vector) solves (informational)")
     ap.add_argument("--distribute", default="nodes", choices=["nodes", "tasks", "dynamic"],
                     help="c5, N > 1: distribution of the timed run (BASELINE config 5: nodes = one node per GPU)")
+    ap.add_argument("--preconditioner", default=None, choices=["jacobi"],
+                    help="development: run the workload with linearSystemArgs['preconditioner'] set (stated in result.options)")
     ap.add_argument("--cpu-budget", type=float, default=240.0, help="seconds of CPU sampling for --impl reference")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
