@@ -550,7 +550,7 @@ def run_ours(args, w):
     # ---- informational: the same run with JACOBI-PRECONDITIONED inner solves (opt-in linearSystemArgs["preconditioner"],
     # SciPy's M= argument).  The reference never passes M, so the headline stays unpreconditioned.
     preconditioned = None
-    if w["kind"] in ("osc", "osc_lindep") and not args.no_extras and not args.preconditioner:
+    if w["kind"] == "osc" and not args.no_extras and not args.preconditioner:
         try:
             popts = {"linearSystemArgs": dict(opts["linearSystemArgs"], preconditioner="jacobi")}
             opp = make_operator()
