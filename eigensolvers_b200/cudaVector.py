@@ -466,7 +466,7 @@ class CudaVector(AbstractVector):
                 bad = bad or st.info != 0
                 outs.append(CudaVector._wrap(yt[j], bs[i].options, bs[i]._n_global))
             rt.last_solve = stats[len(idx) - 1]
-            rt.last_block_matvecs = getattr(rt, "last_block_matvecs", [])[:0] + [stats[j].n_matvec for j in range(len(idx))]
+            rt.last_block_matvecs = [stats[j].n_matvec for j in range(len(idx))]
             if bad:  # numpyVector.py:175-177
                 warnings.simplefilter('error', UserWarning)
                 warnings.warn("Warning:: Iterative solver is not converged ")

@@ -131,3 +131,26 @@ def test_gcrotmk_recycling_tracks_scipy():
     ref = sum(sequence(scipy_solver([])))
     assert ours < plain, (ours, plain)
     assert abs(ours - ref) <= 0.15 * ref, (ours, ref, plain)
+
+
+def test_oracle_jacobi_option_is_scipys_M():
+    """The oracle's counterpart of CudaVector's opt-in preconditioner option passes M = diag(1/(sigma - H_ii))
+    to SciPy (gcrotmk's `M=`): same stopping rule on the true residual, far fewer operator applications on the
+    diagonally dominant oscillator Hamiltonian."""
+    import numpy as np
+    from eigensolvers_b200 import hamiltonians as hm
+    from eigensolvers_b200.hostmath import calculateTarget
+    from oracle.numpy_vector import NumpyVectorOracle as NV
+    H, om = hm.coupled_oscillators((8, 6, 5, 4), coupling=0.1, seed=1)
+    lev = hm.oscillator_levels(om, 0.1, 20, max_quanta=6)
+    sigma = float(calculateTarget(lev, 8))
+    b = np.random.default_rng(1).standard_normal(H.shape[0])
+    counts = []
+    for pre in (None, "jacobi"):
+        o = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 1000, "linear_tol": 1e-8, "linear_atol": 0.0,
+                                  "preconditioner": pre}}
+        NV.matvec_count = 0
+        x = NV.solve(H, NV(b.copy(), o), sigma).array
+        counts.append(NV.matvec_count)
+        assert np.linalg.norm(b - (sigma * x - H @ x)) <= 1.01e-8 * np.linalg.norm(b)
+    assert counts[1] * 3 < counts[0], counts
