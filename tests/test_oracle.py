@@ -274,3 +274,33 @@ def test_driver_error_paths():
     # non-converged inner solve raises (numpyVector.py:175-177)
     with pytest.raises(UserWarning):
         _run(A, NV(Y0.copy(), opts("gcrotmk", 1e-14, it=1)), 30.3, 4, 2, 1e-6)
+
+
+def test_mirror_drivers_write_their_run_logs(tmp_path, monkeypatch):
+    """writeOut=True (the drivers' default): the mirror drivers write the two files per run the
+    reference's printUtils.py writes (iteration log + summary table, same default names), one summary
+    line per cumulative Krylov step / FEAST iteration; the results do not depend on logging."""
+    from eigensolvers_b200.contour import feastDiagonalization
+    from eigensolvers_b200.lanczos import inexactLanczosDiagonalization
+    from oracle.numpy_vector import NumpyVectorOracle as NV
+    monkeypatch.chdir(tmp_path)
+    g = gold("lanczos_c1")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ev, vecs, st = inexactLanczosDiagonalization(g["A"], NV(g["Y0"].copy(), opts()), 30, 6, 4, 1e-8)   # writeOut default
+    warnings.resetwarnings()
+    np.testing.assert_array_equal(ev, g["ev"])
+    it_log, summ = (tmp_path / "iterations_lanczos.out").read_text(), (tmp_path / "summary_lanczos.out").read_text()
+    assert "inexact Lanczos" in it_log and "overlap matrix (condition number" in it_log and "final eigenvalues" in it_log
+    rows = [ln for ln in summ.splitlines() if ln and not ln.startswith("#")]
+    assert len(rows) == st["cumIter"] and rows[-1].split()[2] == str(st["cumIter"])
+    assert abs(float(rows[-1].split()[4]) - np.sort(ev[:1])[0]) < 1e-10
+    gf = gold("feast_t1")
+    Y = [NV(gf["Y1"][:, i].copy(), opts("gcrotmk", 1e-2)) for i in range(6)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        evf, vf, stf = feastDiagonalization(gf["A"], Y, 8, "legendre", 160.0, 166.0, 1e-10, 3, outFileName="f_it.out",
+                                            summaryFileName="f_sum.out")
+    warnings.resetwarnings()
+    assert "FEAST" in (tmp_path / "f_it.out").read_text()
+    assert len([ln for ln in (tmp_path / "f_sum.out").read_text().splitlines() if ln and not ln.startswith("#")]) == 2
