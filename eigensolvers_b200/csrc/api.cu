@@ -51,6 +51,7 @@ extern "C" int cv_ctx_create(int device, void *scratch_dev, size_t scratch_bytes
   c->prepushed_op = nullptr;
   c->push_early = getenv("EIGB200_PUSH_EARLY") ? atoi(getenv("EIGB200_PUSH_EARLY")) != 0 : true;
   c->slab_mode = getenv("EIGB200_SLAB") ? atoi(getenv("EIGB200_SLAB")) : 1;
+  c->snake = getenv("EIGB200_SNAKE") ? atoi(getenv("EIGB200_SNAKE")) : 1;
   c->precond_dinv = nullptr;
   c->precond_z = c->precond_t = nullptr;
   c->launches = 0;
@@ -107,6 +108,8 @@ extern "C" int cv_ctx_set_option(cv_ctx *ctx, const char *name, double value) {
     ctx->reorth_eta = value;
   } else if (!strcmp(name, "slab_mode")) {
     ctx->slab_mode = value != 0.0;
+  } else if (!strcmp(name, "snake")) {
+    ctx->snake = value != 0.0;
   } else if (!strcmp(name, "push_early")) {
     ctx->push_early = value != 0.0;
   } else {
@@ -737,6 +740,7 @@ int cv_orth_step_dev(cv_ctx *ctx, cv_op *op, int64_t n, int cplx_, int m, const 
   a.push.ticket = ctx->counters + CV_COUNTER_PUSH;
   a.push_early = 0;
   a.slab_mode = ctx->slab_mode;
+  a.snake = ctx->snake;
   if (ctx->world > 1) {
     a.pp = *cv_peer_ptrs(ctx);
     const bool dia = cv_op_banded(op);

@@ -126,6 +126,7 @@ struct cv_ctx {
   cv_recycle_state recycle;
   bool push_early;  // fused step pushes unnormalised halo rows from phase B (EIGB200_PUSH_EARLY=0: off)
   int slab_mode;    // dot-phase work split of the fused Arnoldi step (kernels_orth.cuh SlabMap; EIGB200_SLAB)
+  int snake;        // update phase walks the rows downwards (EIGB200_SNAKE)
   // diagonal right preconditioner of the current cv_solve_precond call (null: none) and its two scratch vectors
   const void *precond_dinv;
   void *precond_z, *precond_t;

@@ -114,7 +114,7 @@ struct OrthBatchArgs {
   unsigned *bar;     // [0] arrivals, [1] generation
   unsigned *ticket;
   double *scal;
-  int slab_mode;
+  int slab_mode, snake;
   double *host_mb;
   unsigned long long *host_flag;
   unsigned long long host_seq;
@@ -384,7 +384,11 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step_batch(const __grid_co
       for (int j = threadIdx.x; j < m * NR; j += blockDim.x) s_h[j] = -__ldcg(a.scal + s_h_out + j);
       __syncthreads();
       double nx = 0.0;
-      for (int64_t ip = (int64_t)bc * blockDim.x + threadIdx.x; ip < npf; ip += (int64_t)bg * blockDim.x) {
+      // rows downwards: phase A's tail is still in L2 (see k_orth_step)
+      const int64_t b_first = (int64_t)bc * blockDim.x + threadIdx.x, b_stride = (int64_t)bg * blockDim.x;
+      const int64_t b_count = b_first < npf ? (npf - b_first + b_stride - 1) / b_stride : 0;
+      for (int64_t kk = 0; kk < b_count; ++kk) {
+        const int64_t ip = a.snake ? b_first + (b_count - 1 - kk) * b_stride : b_first + kk * b_stride;
         Pack<T, W> acc = pk_ld_cg<T, W>(wvec, ip);
         for (int j0 = 0; j0 < m; j0 += JB) {
           Pack<T, W> v[JB];

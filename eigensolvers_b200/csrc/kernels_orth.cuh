@@ -43,6 +43,7 @@ struct OrthArgs {
   int push_early;  // all segments are contiguous ranges: phase B stores the new rows into the peers'
                    // halo buffers as it produces them; otherwise (gather lists) a late push follows
   int slab_mode;     // phase A work split, see SlabMap
+  int snake;         // phase B walks the rows downwards (L2 reuse of phase A's tail)
   int publish_late;  // debug: hand the scalars to the host at the END of the kernel
   double *trace;   // [16] accumulated phase times of CTA 0 in ns (tools/orth_trace.py)
   // host mailbox
@@ -378,7 +379,14 @@ __global__ void __launch_bounds__(CV_BLOCK, 3) k_orth_step(const __grid_constant
     for (int j = threadIdx.x; j < m * NR; j += blockDim.x) s_h[j] = -__ldcg(a.scal + s_h_out + j);
     __syncthreads();
     double nx = 0.0;
-    for (int64_t ip = (int64_t)c * blockDim.x + threadIdx.x; ip < npf; ip += (int64_t)G * blockDim.x) {
+    // Phase B walks the rows in the OPPOSITE direction of phase A ("snake"): phase A has just streamed
+    // [C,V] and w in ascending order, so the last ~126 MB of it — the high rows of every vector — are
+    // still in L2 when phase B starts there.  Nothing at 160 MB per vector; at 8-20 MB per vector
+    // (BASELINE config 2, or config 3 on 8 GPUs) it serves a good part of phase B from L2.
+    const int64_t b_first = (int64_t)c * blockDim.x + threadIdx.x, b_stride = (int64_t)G * blockDim.x;
+    const int64_t b_count = b_first < npf ? (npf - b_first + b_stride - 1) / b_stride : 0;
+    for (int64_t kk = 0; kk < b_count; ++kk) {
+      const int64_t ip = a.snake ? b_first + (b_count - 1 - kk) * b_stride : b_first + kk * b_stride;
       Pack<T, W> acc = pk_ld_cg<T, W>(wvec, ip);
       for (int j0 = 0; j0 < m; j0 += JB) {
         Pack<T, W> v[JB];

@@ -1092,6 +1092,7 @@ int lockstep_orth(cv_ctx *ctx, int64_t n, int cplx_, int np, LockstepSolve *cons
   a.ticket = ctx->counters + CV_COUNTER_PUSH;
   a.scal = ctx->scalars;
   a.slab_mode = ctx->slab_mode;
+  a.snake = ctx->snake;
   a.host_mb = ctx->mailbox;
   a.host_flag = ctx->host_flag;
   a.host_seq = ++ctx->host_seq;

@@ -28,10 +28,16 @@ def main():
     eb = 16 if cplx else 8
     tr = (C.c_double * 16)()
     out = (C.c_double * (2 + 2 * mmax))()
-    for m in (1, 5, 12, 16, 17, 21, 24, 28, 32, 33, 36, 40, 48, 49, 60):
+    snake_sweep = len(sys.argv) > 3 and sys.argv[3] == "snake"
+    flush = t.zeros(40 * 1024 * 1024, dtype=t.float64, device=rt.device)   # 320 MB: what the SpMV between two steps does to L2
+    for m in ((21, 28, 36, 48) if snake_sweep else (1, 5, 12, 16, 17, 21, 24, 28, 32, 33, 36, 40, 48, 49, 60)):
         ptrs, _keep = _lib.ptr_array([b.data_ptr() for b in basis[:m]])
         for mode in (0, 1):
-            _lib.check(rt.lib.cv_ctx_set_option(rt.ctx, b"slab_mode", float(mode)))
+            if snake_sweep:   # mode = snake off / on, new slab split
+                _lib.check(rt.lib.cv_ctx_set_option(rt.ctx, b"slab_mode", 1.0))
+                _lib.check(rt.lib.cv_ctx_set_option(rt.ctx, b"snake", float(mode)))
+            else:
+                _lib.check(rt.lib.cv_ctx_set_option(rt.ctx, b"slab_mode", float(mode)))
             w = w0.clone()
             # correctness of h against torch on the first launch
             _lib.check(rt.lib.cv_arnoldi_step(rt.ctx, None, n, cplx, m, ptrs, w.data_ptr(), ww, 0.1, out, rt.stream))
@@ -45,6 +51,8 @@ def main():
             evs = []
             for _ in range(reps):
                 w.copy_(w0)
+                if snake_sweep:
+                    flush.add_(1.0)
                 e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
                 e0.record()
                 _lib.check(rt.lib.cv_arnoldi_step(rt.ctx, None, n, cplx, m, ptrs, w.data_ptr(), ww, 0.1, out, rt.stream))
@@ -54,7 +62,7 @@ def main():
             _lib.check(rt.lib.cv_ctx_trace_read(rt.ctx, tr, 1))
             k = max(tr[5], 1.0)
             ms = float(np.median(evs))
-            print(json.dumps({"m": m, "slab_mode": mode, "n": n, "cplx": cplx, "ms": round(ms, 4),
+            print(json.dumps({"m": m, ("snake" if snake_sweep else "slab_mode"): mode, "n": n, "cplx": cplx, "ms": round(ms, 4),
                               "GBs": round((2 * m + 3) * eb * n / ms / 1e6, 1),
                               "dots_us": round(tr[0] / k * 1e-3, 1), "barrier_us": round(tr[1] / k * 1e-3, 1),
                               "update_us": round(tr[2] / k * 1e-3, 1), "second_pass": out[0], "h_rel_err": err}), flush=True)
