@@ -2,7 +2,7 @@
 split (slab_mode 0 / 1), through the C-ABI entry cv_arnoldi_step: per-launch CUDA-event time, the
 kernel's own phase stamps (dots / barrier+all-reduce / update) and GB/s on (2m+3)*8N.
 
-    python tools/orth_sweep.py [N=20000000] [cplx=0]
+    python tools/orth_sweep.py [N=20000000] [cplx=0] [snake]     # "snake": A/B the update-phase row order, L2 flushed between launches
 """
 import ctypes as C
 import json
