@@ -269,13 +269,15 @@ class CudaVector(AbstractVector):
                 raise ValueError("vectors of different length")
         return n
 
-    def linearCombination(vectors, coeffs):  # numpyVector.py:105-119
-        """c1*v1 + ... + cn*vn; result dtype is that of vectors[0] (complex terms on a real
-        accumulator raise, as numpy's in-place add does in the reference)."""
-        assert len(vectors) == len(coeffs)
-        out = CudaVector.linearCombinationBlock(vectors, np.asarray(coeffs).reshape(len(coeffs), 1))
+    @staticmethod
+    def linearCombination(other, coeff):  # numpyVector.py:105-119
+        """c1*v1 + ... + cn*vn over the list ``other``; result dtype is that of other[0] (complex
+        terms on a real accumulator raise, as numpy's in-place add does in the reference)."""
+        assert len(other) == len(coeff)
+        out = CudaVector.linearCombinationBlock(other, np.asarray(coeff).reshape(len(coeff), 1))
         return out[0]
 
+    @staticmethod
     def linearCombinationBlock(vectors, coeffMatrix):
         """All columns of ``coeffMatrix`` (m x k) at once: Y_k = sum_j C[j,k] v_j, one pass over the
         inputs per four outputs.  Batched form of the per-column calls of basisTransformation
@@ -301,13 +303,14 @@ class CudaVector(AbstractVector):
         opts, ng = vectors[0].options, vectors[0]._n_global
         return [CudaVector._wrap(t, opts, ng) for t in outs]
 
-    def orthogonalize_against_set(x, qs, lindep=LINDEP_DEFAULT_VALUE):  # numpyVector.py:121-145
+    @staticmethod
+    def orthogonalize_against_set(x, xs, lindep=LINDEP_DEFAULT_VALUE):  # numpyVector.py:121-145
         """Sequential Gram-Schmidt with unconjugated products and division by q.q; returns the
         normalised vector or None when x.x <= lindep after projection."""
         rt = Runtime.get()
-        cplx = x._cplx or any(q._cplx for q in qs)
+        cplx = x._cplx or any(q._cplx for q in xs)
         xin = x._as_complex_tensor() if cplx else x._t
-        qts = [q._as_complex_tensor() if cplx else q._t for q in qs]
+        qts = [q._as_complex_tensor() if cplx else q._t for q in xs]
         out = rt.empty(x._nloc, cplx)
         status = C.c_int()
         inner = _lib.dbl_array(2)
@@ -495,6 +498,7 @@ class CudaVector(AbstractVector):
             res[i0:i0 + len(chunk), :] = flat.reshape(len(chunk), b)
         return res
 
+    @staticmethod
     def matrixRepresentation(operator, vectors):  # numpyVector.py:180-190
         """M[i,j] = <v_i | H v_j>, lower triangle computed and mirrored by conjugation."""
         rt = Runtime.get()
@@ -511,6 +515,7 @@ class CudaVector(AbstractVector):
                     qtAq[j, i] = qtAq[i, j].conj()
         return qtAq
 
+    @staticmethod
     def overlapMatrix(vectors):  # numpyVector.py:192-203
         """S[i,j] = <v_i|v_j>, upper triangle computed and mirrored by conjugation."""
         m = len(vectors)
@@ -545,6 +550,7 @@ class CudaVector(AbstractVector):
             return a.view(np.complex128) if cplx else a
         return (to_np(s_col) if want_s else None), (to_np(h_col) if want_h else None)
 
+    @staticmethod
     def extendMatrixRepresentation(operator, vectors, opMat):  # numpyVector.py:205-221
         m = len(vectors)
         dtype = vectors[0].dtype
@@ -555,6 +561,7 @@ class CudaVector(AbstractVector):
         opMat = np.append(opMat, elems.T, axis=1)
         return opMat
 
+    @staticmethod
     def extendOverlapMatrix(vectors, overlap):  # numpyVector.py:223-238
         m = len(vectors)
         dtype = vectors[0].dtype
@@ -609,6 +616,7 @@ class CudaVector(AbstractVector):
             out.append(CudaVector._wrap(bucket[i * n:(i + 1) * n], proto.options, proto._n_global))
         return out
 
+    @staticmethod
     def extendBoth(operator, vectors, overlap, opMat):
         """Fused form of the two extend* calls the Lanczos driver makes back to back
         (inexact_Lanczos.py:349-350): one SpMV and ONE pass over the Krylov list."""

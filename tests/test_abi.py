@@ -53,3 +53,52 @@ def test_product_has_no_cpu_fallback():
         from eigensolvers_b200 import CudaVector
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             CudaVector(np.ones(3))
+
+
+def test_vector_classes_conform_to_the_plugin_interface():
+    """CudaVector and the oracle's NumpyVector expose every member of the reference's ABC
+    (abstractVector.py:15-169) with the reference's argument names and defaults."""
+    from eigensolvers_b200 import CudaVector
+    from eigensolvers_b200.vector_api import INTERFACE, conformance, _VectorInterface
+    from oracle.numpy_vector import NumpyVectorOracle as NumpyVector
+    assert conformance(CudaVector) == []
+    assert conformance(NumpyVector, strict_static=False) == []
+    assert conformance(NumpyVector) != []     # declared as in numpyVector.py: plain functions, class-level use only
+    assert conformance(_VectorInterface) == []
+    assert len(INTERFACE) == 25
+
+    class Broken(CudaVector):
+        @staticmethod
+        def solve(H, rhs, sigma):   # renamed argument, missing optionals
+            return None
+        norm = property(lambda self: 0.0)
+    bad = conformance(Broken)
+    assert any(p.startswith("solve") for p in bad) and any(p.startswith("norm") for p in bad)
+
+
+def test_interface_table_matches_the_reference_abc():
+    """The table is checked against the reference's own abstractVector.py when it is installed
+    (baseline/_ref, git-ignored): same members, same kinds, same signatures."""
+    import inspect
+    import os
+    import sys
+    import pytest
+    from eigensolvers_b200.vector_api import INTERFACE, conformance
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref, "abstractVector.py")):
+        pytest.skip("reference not installed under baseline/_ref")
+    sys.path.insert(0, ref)
+    try:
+        import abstractVector as ref_mod
+    finally:
+        sys.path.remove(ref)
+    assert conformance(ref_mod.AbstractVector) == []
+    public = {n for n, v in vars(ref_mod.AbstractVector).items()
+              if not n.startswith("_") or n in ("__mul__", "__rmul__", "__truediv__", "__imul__", "__itruediv__", "__len__")}
+    public -= {"_abc_impl"}
+    assert public == {row[0] for row in INTERFACE}
+    assert ref_mod.LINDEP_DEFAULT_VALUE == 1e-14
+    for name, kind, *_ in INTERFACE:
+        raw = inspect.getattr_static(ref_mod.AbstractVector, name)
+        abstract = getattr(raw.fget if isinstance(raw, property) else raw, "__isabstractmethod__", False)
+        assert abstract == (kind != "static"), name
