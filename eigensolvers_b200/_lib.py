@@ -76,6 +76,7 @@ SIGNATURES = {
     "cv_op_attach_dia": (_i, [_vp, _vp, _i, _vp, _vp, _i64, _vp, _i64, _pi, _vp]),
     "cv_op_set_dia_halo": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "cv_dia_halo_plan": (_i, [_vp, _i, _i, _i64, _i64, _i, _pi, _vp, _pi, _vp]),
+    "cv_op_set_imag": (_i, [_vp, _vp, _vp]),
     "cv_op_set_format": (_i, [_vp, _i]),
     "cv_op_info": (_i, [_vp, _pi64, _pi64, _pi64, _pi]),
     "cv_spmv": (_i, [_vp, _vp, _i, _i, _d, _d, _vp, _vp, _vp]),

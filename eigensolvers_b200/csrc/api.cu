@@ -973,6 +973,7 @@ extern "C" int cv_op_attach_sell(cv_ctx *ctx, cv_op *op, const int64_t *slice_pt
                                  int64_t padded_nnz, int32_t *sell_col_dev, double *sell_val_dev,
                                  void *stream) {
   CV_REQUIRE(ctx && op && slice_ptr_dev, "cv_op_attach_sell: null argument");
+  CV_REQUIRE(!op->data_im, "cv_op_attach_sell: a complex-valued operator stays in CSR storage");
   CV_REQUIRE(padded_nnz == 0 || (sell_col_dev && sell_val_dev), "cv_op_attach_sell: null storage");
   CV_REQUIRE(padded_nnz % 64 == 0, "cv_op_attach_sell: slice widths must be even (padded_nnz %% 64 == 0)");
   CV_REQUIRE(((uintptr_t)sell_val_dev & 15) == 0 && ((uintptr_t)sell_col_dev & 7) == 0,
@@ -997,6 +998,7 @@ extern "C" int cv_op_attach_dia(cv_ctx *ctx, cv_op *op, int n_diag, const int32_
                                 const int32_t *col_global_dev, int64_t row0, double *dia_val_dev,
                                 int64_t ld, int *ok_host, void *stream) {
   CV_REQUIRE(ctx && op && offsets_host && dia_val_dev && ok_host, "cv_op_attach_dia: null argument");
+  CV_REQUIRE(!op->data_im, "cv_op_attach_dia: a complex-valued operator stays in CSR storage");
   CV_REQUIRE(n_diag >= 1 && n_diag <= CV_MAX_DIAG, "cv_op_attach_dia: n_diag=%d outside 1..%d", n_diag, CV_MAX_DIAG);
   CV_REQUIRE(ld >= op->n_rows, "cv_op_attach_dia: leading dimension smaller than the row count");
   for (int d = 1; d < n_diag; ++d)
@@ -1037,8 +1039,18 @@ extern "C" int cv_op_attach_dia(cv_ctx *ctx, cv_op *op, int n_diag, const int32_
   return CV_OK;
 }
 
+extern "C" int cv_op_set_imag(cv_ctx *ctx, cv_op *op, const double *data_im_dev) {
+  CV_REQUIRE(ctx && op, "cv_op_set_imag: null argument");
+  CV_REQUIRE(op->fmt == CV_FMT_CSR && !op->slice_ptr && !op->dia_val,
+             "cv_op_set_imag: complex values are carried by plain CSR storage only");
+  CV_REQUIRE(op->nnz == 0 || data_im_dev, "cv_op_set_imag: null array");
+  op->data_im = op->nnz ? data_im_dev : nullptr;
+  return CV_OK;
+}
+
 extern "C" int cv_op_set_format(cv_op *op, int fmt) {
   CV_REQUIRE(op, "cv_op_set_format: null operator");
+  CV_REQUIRE(!op->data_im || fmt == CV_FMT_CSR, "cv_op_set_format: a complex-valued operator stays in CSR storage");
   CV_REQUIRE(op->fmt != CV_FMT_KRON || fmt == CV_FMT_KRON, "cv_op_set_format: a matrix-free operator has no stored format");
   CV_REQUIRE(fmt == CV_FMT_CSR || (fmt == CV_FMT_SELL && op->slice_ptr) || (fmt == CV_FMT_DIA && op->dia_val) ||
                  (fmt == CV_FMT_KRON && op->fmt == CV_FMT_KRON),
@@ -1177,6 +1189,9 @@ static int launch_spmv_t(cv_ctx *ctx, cv_op *op, int mode, T sigma, const T *x, 
   a.indptr = op->indptr;
   a.indices = op->indices;
   a.data = op->data;
+  a.data_im = op->data_im;
+  CV_REQUIRE(!op->data_im || (sizeof(T) == 16 && op->fmt == CV_FMT_CSR),
+             "spmv: a complex-valued operator acts on complex vectors, in CSR storage");
   a.x = x;
   a.halo = static_cast<const T *>(op->halobuf);
   a.n_local_cols = op->n_halo > 0 ? op->n_cols - op->n_halo : op->n_cols;

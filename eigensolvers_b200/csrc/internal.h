@@ -16,6 +16,7 @@ struct cv_op {
   const int64_t *indptr = nullptr;
   const int32_t *indices = nullptr;
   const double *data = nullptr;
+  const double *data_im = nullptr;  // imaginary parts of a complex-valued H (CSR only, cv_op_set_imag)
   int csr_group = 8;
   // SELL-32 (borrowed device arrays)
   int64_t n_slices = 0, padded_nnz = 0;

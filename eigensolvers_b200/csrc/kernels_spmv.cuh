@@ -32,6 +32,7 @@ struct SpmvArgs {
   const int64_t *indptr;
   const int32_t *indices;
   const double *data;
+  const double *data_im;  // non-null: complex-valued matrix, entry k = data[k] + i data_im[k] (complex vectors only)
   // vectors
   const T *x;
   const T *halo;        // columns >= n_local_cols read halo[c - n_local_cols]
@@ -175,7 +176,18 @@ __global__ void __launch_bounds__(CV_BLOCK) k_spmv_csr(const __grid_constant__ S
     const bool valid = row < a.n_rows;
     T acc = Num<T>::zero();
     if (valid) {
-      const int64_t rs = __ldg(a.indptr + row), re = __ldg(a.indptr + row + 1);
+      int64_t rs = __ldg(a.indptr + row);
+      const int64_t re = __ldg(a.indptr + row + 1);
+      if constexpr (sizeof(T) == 16) {
+        if (a.data_im != nullptr) {  // complex Hermitian H: split real / imaginary value streams
+          for (int64_t k = rs + gl; k < re; k += G) {
+            int c = ld_stream(a.indices + k);
+            cplx v = make_cplx(ld_stream(a.data + k), ld_stream(a.data_im + k));
+            Num<T>::fma(acc, v, spmv_gather<T, HALO>(a, c));
+          }
+          rs = re;
+        }
+      }
       for (int64_t k = rs + gl; k < re; k += G) {
         int c = ld_stream(a.indices + k);
         double v = ld_stream(a.data + k);

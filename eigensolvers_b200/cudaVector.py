@@ -252,8 +252,11 @@ class CudaVector(AbstractVector):
         op = rt.operator_for(other)
         if op.shape[1] != len(self):
             raise ValueError(f"operator of shape {op.shape} cannot act on a vector of length {len(self)}")
-        out = self._like()
-        _lib.check(rt.lib.cv_spmv(rt.ctx, op.handle, self._cplx, _lib.CV_SPMV_PLAIN, 0.0, 0.0, self._ptr,
+        # a complex-valued H turns a real vector into a complex one, as `other @ array` does
+        cplx = self._cplx or op.dtype.kind == "c"
+        xin = self._as_complex_tensor() if cplx else self._t
+        out = self._like(cplx)
+        _lib.check(rt.lib.cv_spmv(rt.ctx, op.handle, int(cplx), _lib.CV_SPMV_PLAIN, 0.0, 0.0, xin.data_ptr(),
                                   out.data_ptr(), rt.stream))
         return CudaVector._wrap(out, self.options, self._n_global)
 
@@ -503,7 +506,7 @@ class CudaVector(AbstractVector):
         """M[i,j] = <v_i | H v_j>, lower triangle computed and mirrored by conjugation."""
         rt = Runtime.get()
         m = len(vectors)
-        dtype = vectors[0].dtype
+        dtype = np.result_type(vectors[0].dtype, rt.operator_for(operator).dtype)
         qtAq = np.zeros((m, m), dtype=dtype)
         for j0 in range(0, m, 4):
             kets = [vectors[j].applyOp(operator) for j in range(j0, min(j0 + 4, m))]
@@ -541,7 +544,14 @@ class CudaVector(AbstractVector):
         h_col = _lib.dbl_array(m * nr) if want_h else None
         op_handle, ket = None, None
         if want_h:
-            op_handle = rt.operator_for(operator).handle
+            dev_op = rt.operator_for(operator)
+            if dev_op.dtype.kind == "c" and not cplx:
+                cplx, nr = True, 2
+                vt = [v._as_complex_tensor() for v in vectors]
+                vp, _keep = _lib.ptr_array([t.data_ptr() for t in vt])
+                s_col = _lib.dbl_array(m * nr) if want_s else None
+                h_col = _lib.dbl_array(m * nr)
+            op_handle = dev_op.handle
             ket = rt.tmp_vector("ket", n, cplx).data_ptr()
         _lib.check(rt.lib.cv_extend_columns(rt.ctx, op_handle, n, int(cplx), m, vp, ket, s_col, h_col, rt.stream))
 
@@ -553,9 +563,8 @@ class CudaVector(AbstractVector):
     @staticmethod
     def extendMatrixRepresentation(operator, vectors, opMat):  # numpyVector.py:205-221
         m = len(vectors)
-        dtype = vectors[0].dtype
-        elems = np.empty((1, m), dtype=dtype)
         _, h = CudaVector._new_columns(operator, vectors, False, True)
+        elems = np.empty((1, m), dtype=np.result_type(vectors[0].dtype, h.dtype))   # complex-valued H on real vectors
         elems[0, :] = h
         opMat = np.append(opMat, elems[:, :-1].conj(), axis=0)
         opMat = np.append(opMat, elems.T, axis=1)
@@ -621,8 +630,8 @@ class CudaVector(AbstractVector):
         """Fused form of the two extend* calls the Lanczos driver makes back to back
         (inexact_Lanczos.py:349-350): one SpMV and ONE pass over the Krylov list."""
         m = len(vectors)
-        dtype = vectors[0].dtype
         s, h = CudaVector._new_columns(operator, vectors, True, True)
+        dtype = np.result_type(vectors[0].dtype, h.dtype)
         es = np.empty((1, m), dtype=dtype)
         eh = np.empty((1, m), dtype=dtype)
         es[0, :], eh[0, :] = s, h

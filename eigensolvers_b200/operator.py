@@ -64,9 +64,8 @@ class DeviceOperator:
                 f"CudaVector cannot apply an operator of type {type(H).__name__}: pass a "
                 "scipy.sparse matrix, a dense ndarray or a DeviceOperator (an opaque "
                 "LinearOperator has no device representation)")
-        if np.iscomplexobj(A):
-            raise NotImplementedError("complex-valued Hamiltonians are not supported yet (real "
-                                      "symmetric H with real or complex vectors is)")
+        if np.iscomplexobj(A) and not np.any(A.data.imag):
+            A = A.real                      # complex dtype, real values: the fast real-valued formats apply
         if A.shape[1] >= 2 ** 31:
             raise ValueError("column indices must fit int32")
         if not A.has_sorted_indices:
@@ -82,13 +81,25 @@ class DeviceOperator:
         op = cls(rt, A.shape)
         indptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
         indices = np.ascontiguousarray(A.indices, dtype=np.int32)
-        data = np.ascontiguousarray(A.data, dtype=np.float64)
+        zvalued = np.iscomplexobj(A)
+        if zvalued:
+            # complex (Hermitian) H, numpyVector.py:98-100 takes any `other @ array`: the real and the
+            # imaginary parts travel as two value streams over ONE sparsity pattern, in CSR storage
+            if fmt not in ("auto", "csr"):
+                raise NotImplementedError(f"a complex-valued operator is stored as CSR, not {fmt!r}")
+            fmt = "csr"
+            op.dtype = np.dtype(np.complex128)
+            op._data_im_host = np.ascontiguousarray(A.data.imag, dtype=np.float64)
+        data = np.ascontiguousarray(A.data.real if zvalued else A.data, dtype=np.float64)
+        diag = A.diagonal()
         if rt.world == 1:
-            op._diag_host = np.asarray(A.diagonal(), dtype=np.float64)
+            op._diag_host = np.asarray(diag, dtype=np.complex128 if np.any(np.imag(diag)) else np.float64)
             return op._finish(indptr, indices, data, fmt, indices, 0)
         r0, r1 = rt.local_range(A.shape[0])
-        op._diag_host = np.asarray(A.diagonal()[r0:r1], dtype=np.float64)
+        op._diag_host = np.asarray(diag[r0:r1], dtype=np.complex128 if np.any(np.imag(diag)) else np.float64)
         lo, hi = int(indptr[r0]), int(indptr[r1])
+        if zvalued:
+            op._data_im_host = op._data_im_host[lo:hi]
         return op._finish_sharded(np.ascontiguousarray(indptr[r0:r1 + 1] - lo), indices[lo:hi], data[lo:hi], r0, r1, fmt)
 
     def _finish_sharded(self, indptr, gcols, data, r0, r1, fmt):
@@ -124,6 +135,13 @@ class DeviceOperator:
         _lib.check(rt.lib.cv_op_create_csr(rt.ctx, n_rows, n_cols, op.nnz, d_indptr.data_ptr(),
                                            d_indices.data_ptr(), d_data.data_ptr(),
                                            C.byref(op.handle)))
+        im = getattr(op, "_data_im_host", None)
+        if im is not None:                 # same entry order as `data` (the halo renumbering keeps it)
+            assert len(im) == op.nnz
+            d_im = rt.upload(im) if op.nnz else t.empty(0, dtype=t.float64, device=rt.device)
+            op._keep.append(d_im)
+            _lib.check(rt.lib.cv_op_set_imag(rt.ctx, op.handle, d_im.data_ptr()))
+            op._data_im_host = None
         if rt.world > 1:
             op._register_halo()
         if fmt in ("auto", "dia") and rt.world == 1 and op.shape[0] == op.shape[1]:
@@ -317,6 +335,8 @@ class DeviceOperator:
         from .runtime import Runtime
         rt = runtime or Runtime.get()
         A = cls._as_csr(H_rows)
+        if np.iscomplexobj(A):
+            raise NotImplementedError("complex-valued operators are built from the whole matrix (from_host)")
         op = cls(rt, (n_global, n_global))
         r0, r1 = rt.local_range(n_global)
         if A.shape[0] != r1 - r0:

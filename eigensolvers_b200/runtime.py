@@ -248,7 +248,7 @@ class Runtime:
                 parts = [np.shape(H), d.ctypes.data]
             if d.size:
                 step = max(1, d.size // 4096)
-                parts += [float(d[::step].sum()), float(d[0]), float(d[-1])]
+                parts += [d[::step].sum().item(), d[0].item(), d[-1].item()]   # python float / complex
             return tuple(parts)
         except Exception:
             return None

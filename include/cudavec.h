@@ -206,6 +206,10 @@ int cv_op_create_kron(cv_ctx *ctx, int64_t n_rows, int64_t row0, int ndim, const
                       const int32_t *tab_col_dev, int tab_len, const double *dtab_dev,
                       const int32_t *dtab_off, int dtab_len, int64_t max_offset, int64_t nnz_equiv,
                       cv_op **out);
+/* Complex-valued (Hermitian) H -- numpyVector.py:98-100 applies whatever `other @ array` accepts:
+ * entry k of the CSR operator becomes data_dev[k] + i * data_im_dev[k] (same sparsity, device array
+ * borrowed).  Such an operator acts on complex vectors only and stays in CSR storage.                */
+int cv_op_set_imag(cv_ctx *ctx, cv_op *op, const double *data_im_dev);
 int cv_op_set_format(cv_op *op, int fmt);
 int cv_op_info(cv_op *op, int64_t *n_rows, int64_t *nnz, int64_t *padded_nnz, int *fmt);
 

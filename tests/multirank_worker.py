@@ -143,6 +143,34 @@ def main():
             S = CudaVector.overlapMatrix([X, Y])
             check(f"{name} overlap", np.allclose(S, np.array([[x @ x, x @ y], [x @ y, y @ y]]), rtol=1e-12))
 
+    if "kernels" in cases:
+        # complex Hermitian H, row-sharded: second CSR value stream over the general halo plan
+        import scipy.sparse as sp
+        n = 3000
+        A = sp.random(n, n, density=0.003, random_state=np.random.RandomState(11), format="csr")
+        B = sp.random(n, n, density=0.003, random_state=np.random.RandomState(12), format="csr")
+        Z = (A + 1j * B).tocsr()
+        d = np.arange(1, n + 1, dtype=np.float64)
+        d[n // 2:] += 20.0
+        Hz = ((Z + Z.conj().T) * 0.5 + sp.diags(d)).tocsr()
+        zop = DeviceOperator.from_host(Hz)
+        check("zherm format/dtype", zop.format == "csr" and zop.dtype == np.complex128 and zop.n_halo > 0)
+        xr = rng.standard_normal(n)
+        xz = xr + 1j * rng.standard_normal(n)
+        for tag, xx in (("real", xr), ("complex", xz)):
+            got = CudaVector(xx).applyOp(zop).array
+            check(f"zherm spmv on a {tag} vector", np.allclose(got, Hz @ xx, rtol=1e-12, atol=1e-12))
+        zs = n // 2 + 10.3
+        oz = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 3000, "linear_tol": 1e-9, "linear_atol": 0.0}}
+        wz = CudaVector.solve(zop, CudaVector(xr, dict(oz)), zs).array
+        res = np.linalg.norm(xr - (zs * wz - Hz @ wz)) / np.linalg.norm(xr)
+        check(f"zherm gcrotmk residual {res:.2e}", res < 1e-8)
+        vs = [CudaVector(rng.standard_normal(n) + 1j * rng.standard_normal(n)) for _ in range(3)]
+        V = np.stack([v.array for v in vs], axis=1)
+        M = CudaVector.matrixRepresentation(zop, vs)
+        refM = V.conj().T @ (Hz @ V)
+        check("zherm matrixRepresentation", np.allclose(M, refM, rtol=1e-11, atol=1e-11 * np.abs(refM).max()))
+
     if "onesided" in cases:
         # structurally one-sided coupling: only the FIRST rank's rows reference columns of other ranks, so
         # the other ranks have n_halo == 0 but non-empty send lists (such a rank used to skip the

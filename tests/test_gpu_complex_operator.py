@@ -1,0 +1,138 @@
+"""Complex-valued (Hermitian) H through CudaVector.
+
+numpyVector.py:98-100 applies whatever `other @ self.array` accepts and :147-178 hands any H to
+SciPy, so NumpyVector's applyOp / solve / matrixRepresentation work on a complex Hermitian matrix.
+Here the operator carries its imaginary parts as a second CSR value stream (cv_op_set_imag) and
+every operator application promotes real vectors to complex, as numpy does.  Checked against
+numpy/scipy on the same seeded inputs.
+
+The reference's DRIVERS do not run on such a matrix (checked with the unmodified files under
+baseline/_ref): inexact_Lanczos.py aborts in its linear-dependency branch because
+orthogonalize_against_set uses unconjugated products (numpyVector.py:133-145), and feast.py
+integrates over the upper half contour only, which assumes a real symmetric matrix
+(feast.py:185-201).  So there is no driver-level parity to assert and none is claimed.
+"""
+import warnings
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+pytestmark = pytest.mark.gpu
+
+
+def _opts(tol=1e-4, solver="gcrotmk", atol=1e-4):
+    return {"linearSystemArgs": {"linearSolver": solver, "linearIter": 1000, "linear_tol": tol, "linear_atol": atol}}
+
+
+def _hermitian_sparse(n, density, seed, diag=None):
+    rng = np.random.default_rng(seed)
+    A = sp.random(n, n, density=density, random_state=np.random.RandomState(seed), format="csr")
+    B = sp.random(n, n, density=density, random_state=np.random.RandomState(seed + 1), format="csr")
+    Z = (A + 1j * B).tocsr()
+    H = (Z + Z.conj().T) * 0.5
+    d = np.arange(1, n + 1, dtype=np.float64) if diag is None else diag
+    H = (H + sp.diags(d + rng.standard_normal(n) * 0.0)).tocsr()
+    assert abs(H - H.conj().T).max() == 0
+    return H
+
+
+@pytest.fixture(autouse=True)
+def _reset_warning_filters():
+    yield
+    warnings.resetwarnings()
+
+
+@pytest.mark.parametrize("n,density", [(2, 1.0), (37, 0.3), (3000, 0.004), (70001, 0.0001)])
+def test_apply_complex_operator(rt, n, density):
+    from eigensolvers_b200 import CudaVector
+    H = _hermitian_sparse(n, density, 3)
+    rng = np.random.default_rng(5)
+    xr = rng.standard_normal(n)
+    xc = xr + 1j * rng.standard_normal(n)
+    op = rt.operator_for(H)
+    assert op.format == "csr" and op.dtype == np.complex128
+    for x in (xr, xc):
+        Y = CudaVector(x, _opts()).applyOp(H)
+        ref = H @ x
+        assert Y.dtype == np.complex128                      # numpy promotes a real x the same way
+        np.testing.assert_allclose(Y.array, ref, rtol=1e-13, atol=1e-13 * np.abs(ref).max())
+    dense = np.asarray(H.todense()) if n <= 3000 else None
+    if dense is not None:                                        # dense ndarray H takes the same path
+        Y = CudaVector(xc, _opts()).applyOp(dense)
+        np.testing.assert_allclose(Y.array, dense @ xc, rtol=1e-12, atol=1e-12 * np.abs(dense @ xc).max())
+
+
+def test_complex_dtype_with_real_values_keeps_fast_formats(rt):
+    from eigensolvers_b200 import CudaVector, hamiltonians as hm
+    H = hm.laplacian3d(16)
+    Hz = H.astype(np.complex128)
+    op = rt.operator_for(Hz)
+    assert op.dtype == np.float64 and op.format in ("dia", "sell")
+    x = np.random.default_rng(1).standard_normal(H.shape[0])
+    np.testing.assert_allclose(CudaVector(x, _opts()).applyOp(Hz).array, H @ x, rtol=1e-13, atol=1e-13)
+
+
+def test_complex_operator_rejects_other_formats(rt):
+    from eigensolvers_b200 import DeviceOperator
+    H = _hermitian_sparse(2000, 0.003, 8)
+    for fmt in ("sell", "dia"):
+        with pytest.raises(NotImplementedError):
+            DeviceOperator.from_host(H, fmt=fmt)
+    op = DeviceOperator.from_host(H)
+    with pytest.raises(RuntimeError):
+        op.set_format("sell")
+
+
+def test_matrix_representation_complex_operator(rt):
+    from eigensolvers_b200 import CudaVector
+    n = 900
+    H = _hermitian_sparse(n, 0.01, 21)
+    rng = np.random.default_rng(2)
+    Vr = np.linalg.qr(rng.standard_normal((n, 5)))[0]
+    Vc = np.linalg.qr(rng.standard_normal((n, 5)) + 1j * rng.standard_normal((n, 5)))[0]
+    for V in (Vr, Vc):
+        vs = [CudaVector(V[:, i].copy(), _opts()) for i in range(5)]
+        M = CudaVector.matrixRepresentation(H, vs)
+        ref = V.conj().T @ (H @ V)
+        np.testing.assert_allclose(M, ref, rtol=1e-11, atol=1e-11 * np.abs(ref).max())
+        M1 = CudaVector.matrixRepresentation(H, vs[:-1])
+        S1 = CudaVector.overlapMatrix(vs[:-1])
+        np.testing.assert_allclose(CudaVector.extendMatrixRepresentation(H, vs, M1), ref, atol=1e-9 * np.abs(ref).max())
+        S2, M2 = CudaVector.extendBoth(H, vs, S1, M1)
+        np.testing.assert_allclose(M2, ref, atol=1e-9 * np.abs(ref).max())
+        np.testing.assert_allclose(S2, V.conj().T @ V, atol=1e-9)
+
+
+@pytest.mark.parametrize("sigma", [422.3, 422.3 + 0.8j])
+@pytest.mark.parametrize("solver", ["gcrotmk", "minres"])
+def test_solve_with_complex_operator(rt, sigma, solver):
+    """(sigma - H) x = b against SciPy's solver on the same system (numpyVector.py:147-178)."""
+    from eigensolvers_b200 import CudaVector
+    if solver == "minres" and np.iscomplex(sigma):
+        pytest.skip("MINRES needs a Hermitian system: real shift only")
+    n = 1500
+    d = np.arange(1, n + 1, dtype=np.float64)
+    d[411:] += 20.0                     # a gap of ~ +-10 around the shift: GCROT(20,20) converges (4.5-7.5 k applications)
+    H = _hermitian_sparse(n, 0.004, 31, diag=d)
+    rng = np.random.default_rng(7)
+    dense = sigma * np.eye(n) - np.asarray(H.todense())
+    for b in (rng.standard_normal(n), rng.standard_normal(n) + 1j * rng.standard_normal(n)):
+        b = b / np.linalg.norm(b)
+        tol = 1e-10
+        X = CudaVector.solve(H, CudaVector(b, _opts(tol, solver, atol=1e-12)), sigma)
+        assert X.dtype == np.complex128 and rt.last_solve.info == 0
+        x = X.array
+        x_direct = np.linalg.solve(dense, b)
+        r = b - (sigma * x - H @ x)
+        # GCROT stops on ||r|| <= max(atol, tol ||b||), MINRES on ||r|| <= tol ||A|| ||x|| (minres.py:292,327)
+        assert np.linalg.norm(r) <= (2e-10 if solver == "gcrotmk" else 1e-10 * 1600 * np.linalg.norm(x) * 2), np.linalg.norm(r)
+        assert np.linalg.norm(x - x_direct) / np.linalg.norm(x_direct) <= 1e-5
+        if solver == "gcrotmk":     # SciPy's GCROT on the same complex system: same stopping rule, same answer
+            lin = spla.LinearOperator((n, n), matvec=lambda v: sigma * v - H @ v, dtype=np.complex128)
+            x_ref, info = spla.gcrotmk(lin, b.astype(np.complex128), None, rtol=tol, atol=1e-12, maxiter=1000)
+            assert info == 0
+            assert np.linalg.norm(x - x_ref) / np.linalg.norm(x_ref) <= 1e-6
+        Xr = CudaVector.solve(H, CudaVector(b, _opts(tol, solver, atol=1e-12)), sigma, reverseGF=True)
+        np.testing.assert_allclose(Xr.array, -x, rtol=0, atol=1e-5 * np.linalg.norm(x))
