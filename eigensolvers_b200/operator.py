@@ -92,6 +92,8 @@ class DeviceOperator:
             op._data_im_host = np.ascontiguousarray(A.data.imag, dtype=np.float64)
         data = np.ascontiguousarray(A.data.real if zvalued else A.data, dtype=np.float64)
         diag = A.diagonal()
+        if np.iscomplexobj(diag) and not np.any(diag.imag):
+            diag = diag.real                # Hermitian: real diagonal
         if rt.world == 1:
             op._diag_host = np.asarray(diag, dtype=np.complex128 if np.any(np.imag(diag)) else np.float64)
             return op._finish(indptr, indices, data, fmt, indices, 0)

@@ -151,7 +151,7 @@ def main():
         B = sp.random(n, n, density=0.003, random_state=np.random.RandomState(12), format="csr")
         Z = (A + 1j * B).tocsr()
         d = np.arange(1, n + 1, dtype=np.float64)
-        d[n // 2:] += 20.0
+        d[n // 2:] += 200.0
         Hz = ((Z + Z.conj().T) * 0.5 + sp.diags(d)).tocsr()
         zop = DeviceOperator.from_host(Hz)
         check("zherm format/dtype", zop.format == "csr" and zop.dtype == np.complex128 and zop.n_halo > 0)
@@ -160,7 +160,7 @@ def main():
         for tag, xx in (("real", xr), ("complex", xz)):
             got = CudaVector(xx).applyOp(zop).array
             check(f"zherm spmv on a {tag} vector", np.allclose(got, Hz @ xx, rtol=1e-12, atol=1e-12))
-        zs = n // 2 + 10.3
+        zs = n // 2 + 100.5              # mid-gap: a few hundred applications
         oz = {"linearSystemArgs": {"linearSolver": "gcrotmk", "linearIter": 3000, "linear_tol": 1e-9, "linear_atol": 0.0}}
         wz = CudaVector.solve(zop, CudaVector(xr, dict(oz)), zs).array
         res = np.linalg.norm(xr - (zs * wz - Hz @ wz)) / np.linalg.norm(xr)
