@@ -11,6 +11,8 @@ baseline/_ref): inexact_Lanczos.py aborts in its linear-dependency branch becaus
 orthogonalize_against_set uses unconjugated products (numpyVector.py:133-145), and feast.py
 integrates over the upper half contour only, which assumes a real symmetric matrix
 (feast.py:185-201).  So there is no driver-level parity to assert and none is claimed.
+
+(The file name sorts last on purpose: the newest feature runs after the established suite.)
 """
 import warnings
 
@@ -27,13 +29,16 @@ def _opts(tol=1e-4, solver="gcrotmk", atol=1e-4):
 
 
 def _hermitian_sparse(n, density, seed, diag=None):
+    """Seeded complex Hermitian CSR matrix: random off-diagonal entries (O(nnz) generator -- scipy's
+    sp.random permutes all n*n positions with a legacy RandomState, minutes at n = 7e4) + real diagonal."""
     rng = np.random.default_rng(seed)
-    A = sp.random(n, n, density=density, random_state=np.random.RandomState(seed), format="csr")
-    B = sp.random(n, n, density=density, random_state=np.random.RandomState(seed + 1), format="csr")
-    Z = (A + 1j * B).tocsr()
+    k = max(1, int(density * n * n))
+    rows, cols = rng.integers(0, n, k), rng.integers(0, n, k)
+    vals = rng.random(k) + 1j * rng.random(k)
+    Z = sp.coo_matrix((vals, (rows, cols)), shape=(n, n)).tocsr()     # duplicates are summed
     H = (Z + Z.conj().T) * 0.5
     d = np.arange(1, n + 1, dtype=np.float64) if diag is None else diag
-    H = (H + sp.diags(d + rng.standard_normal(n) * 0.0)).tocsr()
+    H = (H + sp.diags(d)).tocsr()
     assert abs(H - H.conj().T).max() == 0
     return H
 
@@ -144,3 +149,12 @@ def test_minres_rejects_complex_systems(rt):
     b = np.random.default_rng(1).standard_normal(400)
     with pytest.raises(RuntimeError, match="real symmetric"):
         CudaVector.solve(H, CudaVector(b, _opts(1e-8, "minres")), -2.0)
+
+
+def test_complex_operator_row_sharded(rt):
+    """Two ranks (tests/multirank_worker.py, case zherm): the imaginary value stream follows the
+    general halo plan -- applyOp on real / complex vectors, GCROT, matrixRepresentation."""
+    from test_gpu_multirank import _spawn
+    rc, out = _spawn(2, ("zherm",), timeout=300)
+    assert rc == 0, out[-6000:]
+    assert out.count("PASS (all ranks: PASS") == 2, out[-6000:]
