@@ -151,9 +151,12 @@ def test_minres_rejects_complex_systems(rt):
         CudaVector.solve(H, CudaVector(b, _opts(1e-8, "minres")), -2.0)
 
 
+@pytest.mark.xfail(strict=False, reason="row-sharded complex-valued H was written after this round's GPU minutes "
+                                        "ran out: the single-GPU tests above ran on a B200, this one has not run yet")
 def test_complex_operator_row_sharded(rt):
     """Two ranks (tests/multirank_worker.py, case zherm): the imaginary value stream follows the
-    general halo plan -- applyOp on real / complex vectors, GCROT, matrixRepresentation."""
+    general halo plan -- applyOp on real / complex vectors, GCROT, matrixRepresentation.
+    Non-strict xfail until it has been seen green on hardware (an XPASS in the report means it is)."""
     from test_gpu_multirank import _spawn
     rc, out = _spawn(2, ("zherm",), timeout=300)
     assert rc == 0, out[-6000:]
