@@ -95,10 +95,10 @@ class DeviceOperator:
         if np.iscomplexobj(diag) and not np.any(diag.imag):
             diag = diag.real                # Hermitian: real diagonal
         if rt.world == 1:
-            op._diag_host = np.asarray(diag, dtype=np.complex128 if np.any(np.imag(diag)) else np.float64)
+            op._diag_host = np.asarray(diag, dtype=np.complex128 if np.iscomplexobj(diag) else np.float64)
             return op._finish(indptr, indices, data, fmt, indices, 0)
         r0, r1 = rt.local_range(A.shape[0])
-        op._diag_host = np.asarray(diag[r0:r1], dtype=np.complex128 if np.any(np.imag(diag)) else np.float64)
+        op._diag_host = np.asarray(diag[r0:r1], dtype=np.complex128 if np.iscomplexobj(diag) else np.float64)
         lo, hi = int(indptr[r0]), int(indptr[r1])
         if zvalued:
             op._data_im_host = op._data_im_host[lo:hi]
