@@ -18,7 +18,7 @@ DEPS = ["api.cu", "comm.cu", "peer.cu", "solvers.cu", "common.cuh", "internal.h"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "--use_fast_math=false" if False else "-Xptxas=-v",
+    "-Xptxas=-v",
     "-Xcompiler", "-fPIC", "-shared",
     "-cudart", "static",
 ]

@@ -899,7 +899,6 @@ struct LockstepSolve {
   // end of an inner cycle: least squares, new (c,u) pair, residual/solution update (_gcrotmk.py:179,430-499)
   int outer_end(cv_ctx *ctx, cv_op *op, cudaStream_t st) {
     const int64_t n = op->n_rows;
-    const int NR = cplx_ ? 2 : 1;
     double *mb = ctx->mailbox;
     if (!std::isfinite(R[(size_t)j * ldr + j].real()) || !std::isfinite(R[(size_t)j * ldr + j].imag())) {
       phase = DONE;  // scipy: LinAlgError inside _fgmres, gcrotmk reports failure
