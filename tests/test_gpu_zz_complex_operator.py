@@ -158,6 +158,6 @@ def test_complex_operator_row_sharded(rt):
     general halo plan -- applyOp on real / complex vectors, GCROT, matrixRepresentation.
     Non-strict xfail until it has been seen green on hardware (an XPASS in the report means it is)."""
     from test_gpu_multirank import _spawn
-    rc, out = _spawn(2, ("zherm",), timeout=300)
+    rc, out = _spawn(2, ("zherm",), timeout=150)
     assert rc == 0, out[-6000:]
     assert out.count("PASS (all ranks: PASS") == 2, out[-6000:]
