@@ -77,6 +77,8 @@ SIGNATURES = {
     "cv_op_set_dia_halo": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "cv_dia_halo_plan": (_i, [_vp, _i, _i, _i64, _i64, _i, _pi, _vp, _pi, _vp]),
     "cv_op_set_imag": (_i, [_vp, _vp, _vp]),
+    "cv_orth_slab_plan": (_i, [_i, _i, _i, _i, _pi, _vp, _vp]),
+    "cv_orth_batch_plan": (_i, [_i, _vp, C.c_uint, _i, _i, _pi, _vp, _vp, _vp, _vp, _vp]),
     "cv_op_set_format": (_i, [_vp, _i]),
     "cv_op_info": (_i, [_vp, _pi64, _pi64, _pi64, _pi]),
     "cv_spmv": (_i, [_vp, _vp, _i, _i, _d, _d, _vp, _vp, _vp]),

@@ -132,7 +132,7 @@ struct BatchMap {
   int start[CV_BATCH_SLABS + 1];   // phase A: first CTA of each slab
   int bstart[CV_MAX_BATCH + 1];    // phase B: first CTA of each problem (inactive problems: empty range)
 };
-__device__ inline void batch_map_build(const OrthBatchArgs &a, unsigned active_mask, int G, int MI, BatchMap &M) {
+__host__ __device__ inline void batch_map_build(const OrthBatchArgs &a, unsigned active_mask, int G, int MI, BatchMap &M) {
   int ns = 0, wsum = 0, bsum = 0;
   for (int q = 0; q < a.nprob; ++q) {
     if (!((active_mask >> q) & 1u)) continue;

@@ -1275,3 +1275,56 @@ extern "C" int cv_solve(cv_ctx *ctx, cv_op *op, int cplx_, int solver, int rever
   cv_set_error("cv_solve: unknown solver %d", solver);
   return CV_ERR_ARG;
 }
+
+// ------------------------------------------------------------------------------------------
+// work-split plans of the fused Arnoldi-step kernels, evaluated on the HOST by the very functions the
+// kernels call (orth_slab_map / batch_map_build are __host__ __device__): lets the CPU tests check the
+// index logic of the hot kernel exhaustively (every basis vector in exactly one slab, every slab and
+// every problem at least one CTA, CTA ranges tiling the grid).  No device call.
+// ------------------------------------------------------------------------------------------
+extern "C" int cv_orth_slab_plan(int m, int grid, int cplx_, int mode, int *ny_out, int *start_out, int *i0_out) {
+  CV_REQUIRE(ny_out && start_out && i0_out, "cv_orth_slab_plan: null argument");
+  CV_REQUIRE(m >= 1 && m <= CV_MAX_PTRS, "cv_orth_slab_plan: m=%d outside 1..%d", m, CV_MAX_PTRS);
+  const int MI = cplx_ ? ORTH_MI<cplx>::value : ORTH_MI<double>::value;
+  CV_REQUIRE(grid >= (m + MI - 1) / MI, "cv_orth_slab_plan: grid %d smaller than the %d slabs (the launcher refuses this too)", grid,
+             (m + MI - 1) / MI);
+  SlabMap s;
+  orth_slab_map(m, grid, MI, mode, s);
+  *ny_out = s.ny;
+  for (int i = 0; i <= s.ny; ++i) {
+    start_out[i] = s.start[i];
+    i0_out[i] = s.i0[i];
+  }
+  return CV_OK;
+}
+
+extern "C" int cv_orth_batch_plan(int nprob, const int *m, unsigned active_mask, int grid, int cplx_, int *nslab_out,
+                                  int *slab_q, int *slab_i0, int *slab_mi, int *slab_start, int *prob_start) {
+  CV_REQUIRE(m && nslab_out && slab_q && slab_i0 && slab_mi && slab_start && prob_start, "cv_orth_batch_plan: null argument");
+  CV_REQUIRE(nprob >= 1 && nprob <= CV_MAX_BATCH, "cv_orth_batch_plan: nprob=%d outside 1..%d", nprob, CV_MAX_BATCH);
+  const int MI = cplx_ ? ORTH_MI<cplx>::value : ORTH_MI<double>::value;
+  OrthBatchArgs a = {};
+  a.nprob = nprob;
+  int slabs = 0, active = 0;
+  for (int q = 0; q < nprob; ++q) {
+    CV_REQUIRE(m[q] >= 1 && m[q] <= CV_BATCH_PTRS, "cv_orth_batch_plan: m[%d]=%d outside 1..%d", q, m[q], CV_BATCH_PTRS);
+    a.prob[q].m = m[q];
+    if ((active_mask >> q) & 1u) {
+      slabs += (m[q] + MI - 1) / MI;
+      ++active;
+    }
+  }
+  CV_REQUIRE(active >= 1 && grid >= slabs && grid >= active, "cv_orth_batch_plan: grid %d smaller than %d slabs", grid, slabs);
+  BatchMap M;
+  batch_map_build(a, active_mask, grid, MI, M);
+  *nslab_out = M.nslab;
+  for (int s = 0; s < M.nslab; ++s) {
+    slab_q[s] = M.q[s];
+    slab_i0[s] = M.i0[s];
+    slab_mi[s] = M.mi[s];
+    slab_start[s] = M.start[s];
+  }
+  slab_start[M.nslab] = M.start[M.nslab];
+  for (int q = 0; q <= nprob; ++q) prob_start[q] = M.bstart[q];
+  return CV_OK;
+}

@@ -206,6 +206,20 @@ int cv_op_create_kron(cv_ctx *ctx, int64_t n_rows, int64_t row0, int ndim, const
                       const int32_t *tab_col_dev, int tab_len, const double *dtab_dev,
                       const int32_t *dtab_off, int dtab_len, int64_t max_offset, int64_t nnz_equiv,
                       cv_op **out);
+/* Work split of the fused Arnoldi-step kernels (k_orth_step / k_orth_step_batch), computed on the host by
+ * the same functions the kernels call -- pure host routines for the CPU tests (no reference counterpart:
+ * SciPy's Arnoldi step, _gcrotmk.py:112-141, is a sequential loop).
+ * cv_orth_slab_plan: the m basis vectors are cut into ny slabs; slab s holds vectors [i0[s], i0[s+1]) and is
+ *   reduced by CTAs [start[s], start[s+1]) of a grid of `grid` CTAs (arrays of ny+1 entries; mode = the
+ *   "slab_mode" option).
+ * cv_orth_batch_plan: the same for up to 4 lock-step problems of one launch with basis sizes m[q] (bit q of active_mask:
+ *   problem q takes part in this pass): slab s belongs to problem slab_q[s], holds slab_mi[s] vectors from
+ *   slab_i0[s], CTAs [slab_start[s], slab_start[s+1]); the update phase of problem q runs on CTAs
+ *   [prob_start[q], prob_start[q+1]).  Arrays sized for 32 slabs + 1 and nprob + 1.                       */
+int cv_orth_slab_plan(int m, int grid, int cplx, int mode, int *ny_out, int *start_out, int *i0_out);
+int cv_orth_batch_plan(int nprob, const int *m, unsigned active_mask, int grid, int cplx, int *nslab_out,
+                       int *slab_q, int *slab_i0, int *slab_mi, int *slab_start, int *prob_start);
+
 /* Complex-valued (Hermitian) H -- numpyVector.py:98-100 applies whatever `other @ array` accepts:
  * entry k of the CSR operator becomes data_dev[k] + i * data_im_dev[k] (same sparsity, device array
  * borrowed).  Such an operator acts on complex vectors only and stays in CSR storage.                */
